@@ -1,0 +1,190 @@
+/*
+ * libtvbf -- C ABI of the B200 (sm_100a) hybrid-similarity -> top-K path.
+ *
+ * The reference (tomboone/tvbingefriend-recommendation-service) is pure Python and has no FFI
+ * layer; its boundary for this path is the Python API of
+ *   ml/similarity_computer.py:12-190            (SimilarityComputer)
+ *   scripts/populate_database.py:85-259         (compute_and_store_similarities, loop :170-218)
+ *   services/content_based_service.py:161-338   (get_recommendations_from_matrix, bulk variant)
+ * and all arithmetic below it is sklearn.metrics.pairwise.cosine_similarity + numpy.argsort.
+ * This header declares the entry points a ctypes binding of that path uses (INTEGRATION.md
+ * shows the stub).  Every function cites the reference call it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all array pointers are DEVICE pointers owned by the caller (torch
+ *     tensors on the host side), `stream` is a cudaStream_t passed as void*;
+ *   - every function returns TVBF_OK (0) or a negative TVBF_ERR_* code; tvbf_last_error()
+ *     returns a thread-local message for the last failure; no exception crosses the boundary;
+ *   - functions enqueue work on `stream` and return without synchronising unless stated;
+ *   - thread-compatible: no global mutable state besides the thread-local last error.
+ */
+#ifndef TVBF_H_
+#define TVBF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVBF_VERSION 100 /* 0.1.0 */
+
+enum {
+  TVBF_OK = 0,
+  TVBF_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  TVBF_ERR_CUDA = -2,        /* CUDA runtime / driver error      */
+  TVBF_ERR_UNSUPPORTED = -3, /* device is not sm_100             */
+  TVBF_ERR_WORKSPACE = -4    /* workspace too small              */
+};
+
+/* text operand precision of the tensor-core pass (candidates are always rescored in fp64) */
+enum { TVBF_TEXT_FP16 = 0, TVBF_TEXT_BF16 = 1 };
+
+/* how a feature group reaches the scorer */
+enum {
+  TVBF_GROUP_ABSENT = 0, /* contributes 0                                                       */
+  TVBF_GROUP_PACKED = 1, /* genre: 64-bit multi-hot mask; metadata: one-hot category ids         */
+  TVBF_GROUP_FOLDED = 2  /* arbitrary float features: normalised, scaled by sqrt(w) and appended */
+                         /* as extra K columns of the tensor-core operand                        */
+};
+
+enum { TVBF_META_MEAN3 = 0, TVBF_META_HSTACK = 1 };
+
+/* Device-resident, prepared features of one catalogue (built by the tvbf_prep_* calls).
+ * Replaces the five matrices populate_database.py:125-131 loads and the per-iteration
+ * normalisations inside cosine_similarity (populate_database.py:180-186). */
+typedef struct tvbf_features {
+  int32_t n_shows;           /* N                                                             */
+  int32_t n_pad;             /* rows of operand / col_side / meta_scale; multiple of 256      */
+  int32_t k_pad;             /* operand columns: text vocab + folded columns, padded to 64    */
+  int32_t text_dtype;        /* TVBF_TEXT_*                                                   */
+  int32_t text_scale_log2;   /* operand text columns hold x * 2^s                             */
+  int32_t vocab;             /* V                                                             */
+  const void* operand;       /* [n_pad, k_pad] fp16/bf16 row-major (K-major), zero padded     */
+  const int64_t* text_indptr;  /* [N+1] CSR of the L2-normalised fp64 text matrix             */
+  const int32_t* text_indices; /* sorted within each row                                      */
+  const double* text_values;
+  int32_t genre_mode;        /* TVBF_GROUP_*                                                  */
+  int32_t genre_dim;         /* G                                                             */
+  const double* genre_dense; /* FOLDED: [N, G] L2-normalised fp64 rows (exact rescoring)      */
+  int32_t meta_mode;         /* TVBF_GROUP_*                                                  */
+  int32_t meta_kind;         /* TVBF_META_*: mean of 3 cosines (populate_database.py:184-187) */
+                             /* or cosine of the hstack (similarity_computer.py:84-86)        */
+  int32_t meta_groups;       /* FOLDED: number of dense groups (3 for MEAN3, 1 for HSTACK)    */
+  int32_t meta_dims[3];
+  const double* meta_dense[3]; /* FOLDED: [N, dims[g]] L2-normalised fp64 rows                */
+  const void* col_side;      /* [n_pad] 16-byte records {u64 genre bits, f32 1/sqrt(popc),    */
+                             /*  u32 ids = platform | type<<8 | language<<16 | 0xFF<<24}      */
+  const float* meta_scale;   /* [n_pad] MEAN3: 1/sqrt(3) ; HSTACK: 1/sqrt(#valid ids) or 0    */
+} tvbf_features;
+
+/* Parameters of one top-K job: populate_database.py:85-91 (weights, top_n_per_show,
+ * min_similarity) / content_based_service.py:262-264. */
+typedef struct tvbf_params {
+  double genre_weight, text_weight, metadata_weight; /* used as given (already normalised by  */
+                                                     /* the caller for variants A/C)          */
+  double min_similarity;  /* keep score >= min_similarity (populate_database.py:204-205)      */
+  int32_t k;              /* top_n_per_show                                                   */
+  int32_t exclude_self;   /* populate_database.py:199-200                                     */
+  int32_t row_begin;      /* first source row of this shard (multiple of 128)                 */
+  int32_t row_end;        /* one past the last source row                                     */
+  int32_t splits;         /* column splits per row block (0 = choose)                         */
+  int32_t candidates;     /* K' candidates kept per (row, split) before rescoring (0=choose)  */
+  int32_t force_exact;    /* 1: send every row through the exact fp64 row kernel              */
+  int32_t skip_fallback;  /* 1: do not repair flagged rows (diagnostics only)                 */
+  double text_rel_err;    /* 0 = default bound for text_dtype                                 */
+} tvbf_params;
+
+/* Result table of the shard rows [row_begin, row_end): the a9 record stream of
+ * populate_database.py:211-217 in columnar form. */
+typedef struct tvbf_topk_out {
+  int32_t* indices;  /* [rows, k] column index of the similar show, -1 padded                 */
+  int32_t* counts;   /* [rows]   number of valid entries (0 -> show omitted, :220-221)        */
+  double* hybrid;    /* [rows, k] similarity_score                                            */
+  double* genre;     /* [rows, k] genre_score                                                 */
+  double* text;      /* [rows, k] text_score                                                  */
+  double* metadata;  /* [rows, k] metadata_score                                              */
+  int32_t* stats;    /* [8] device ints: 0 flagged rows repaired by the exact kernel,         */
+                     /*     1 candidate pairs rescored, 2 rows processed, rest reserved       */
+} tvbf_topk_out;
+
+int tvbf_version(void);
+const char* tvbf_last_error(void);
+/* sm count and compute capability of the current device; TVBF_ERR_UNSUPPORTED unless 10.x */
+int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- K0: feature preparation (replaces sklearn normalize() inside every cosine_similarity
+ *      call, populate_database.py:180-186, and the dtype promotion of check_pairwise_arrays) -- */
+/* values_out[e] = values[e] / ||row||_2 in fp64; zero rows untouched. */
+int tvbf_prep_csr_normalize(const int64_t* indptr, const double* values, int32_t n_rows,
+                            double* values_out, void* stream);
+/* scatter the normalised CSR rows into operand[:, col_offset + c] = x * scale (fp16/bf16).
+ * operand must be zero-initialised. */
+int tvbf_prep_csr_to_operand(const int64_t* indptr, const int32_t* indices, const double* values,
+                             int32_t n_rows, void* operand, int32_t k_pad, int32_t col_offset,
+                             double scale, int32_t dtype, void* stream);
+/* out[r, :] = in[r, :] / ||in[r, :]||_2 (fp64, zero rows stay zero). */
+int tvbf_prep_dense_normalize(const double* in, int32_t n_rows, int32_t dim, double* out,
+                              void* stream);
+/* operand[r, col_offset + c] = dense[r, c] * scale. */
+int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim, void* operand,
+                               int32_t k_pad, int32_t col_offset, double scale, int32_t dtype,
+                               void* stream);
+/* genre multi-hot bytes [n_rows, dim<=64] -> col_side[].genre_bits / genre_rnorm. */
+int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,
+                         void* stream);
+/* one-hot bytes of platform/type/language -> col_side[].meta_ids and meta_scale[]. Rows
+ * [n_rows, n_pad) are filled with "none". */
+int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* type, int32_t t_dim,
+                       const uint8_t* language, int32_t l_dim, int32_t n_rows, int32_t n_pad,
+                       int32_t meta_kind, void* col_side, float* meta_scale, void* stream);
+
+/* ---- K1+K4+K5(+K6): hybrid all-pairs score -> per-row top-K
+ *      (replaces the loop populate_database.py:170-218 and content_based_service.py:293-308) - */
+size_t tvbf_topk_workspace_bytes(const tvbf_features* f, const tvbf_params* p);
+int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_topk_out* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* exact fp64 scoring of explicit source rows against all columns + exact top-K
+ * (replaces get_recommendations_from_matrix, content_based_service.py:161-236, for any n). */
+size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed);
+int tvbf_exact_rows(const tvbf_features* f, const tvbf_params* p, const int32_t* rows,
+                    int32_t n_rows_listed, const tvbf_topk_out* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* same selection over rows of precomputed N x N float64 matrices: the service's matrix path
+ * (_load_similarity_matrices + get_recommendations_from_matrix,
+ * content_based_service.py:113-140,161-236).  Workspace: tvbf_exact_workspace_bytes-sized
+ * (min(2*SMs, n_rows_listed) * n * 8 bytes). `rows` are absolute row numbers. */
+int tvbf_matrix_rows_topk(const double* hybrid, const double* genre, const double* text,
+                          const double* metadata, int32_t n, const tvbf_params* p,
+                          const int32_t* rows, int32_t n_rows_listed, const tvbf_topk_out* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- full-matrix variant (SimilarityComputer, ml/similarity_computer.py:30-190) ------------- */
+/* csr (normalised) -> dense fp64 [n_rows, dim]; dense must be zero-initialised. */
+int tvbf_csr_to_dense_f64(const int64_t* indptr, const int32_t* indices, const double* values,
+                          int32_t n_rows, int32_t dim, double* dense, void* stream);
+/* out[i, j] = sum_c x[i, c] * x[j, c]  (x already L2-normalised): cosine_similarity(X),
+ * similarity_computer.py:41,58,86. */
+int tvbf_cosine_matrix_f64(const double* x, int32_t n_rows, int32_t dim, double* out,
+                           void* stream);
+/* out = wg*g + wt*t + wm*m elementwise, similarity_computer.py:122-124. */
+int tvbf_hybrid_combine_f64(const double* g, const double* t, const double* m, double wg,
+                            double wt, double wm, int64_t count, double* out, void* stream);
+/* mean / std / min / max / median of the strict upper triangle (similarity_computer.py:171-190).
+ * Synchronises `stream`; out5 is a HOST pointer. */
+size_t tvbf_matrix_stats_workspace_bytes(void);
+int tvbf_matrix_stats_f64(const double* mat, int32_t n, double* out5_host, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ---- diagnostics ---------------------------------------------------------------------------- */
+/* raw tensor-core tile dump: out[i, j] = sum_k operand[row0+i, k] * operand[col0+j, k] for a
+ * 128 x 256 tile (fp32), used by the tests to validate descriptors and the error bound. */
+int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVBF_H_ */

@@ -1,0 +1,128 @@
+"""Host-side logic that needs no GPU: feature classification/staging, table -> dict conversion,
+row sharding, and the world_size-2 gather over gloo."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from tvbingefriend_recommendation_service_b200.engine import TopK, stage
+from tvbingefriend_recommendation_service_b200.sharding import gather_tables, max_shard_rows, row_shard
+from tvbingefriend_recommendation_service_b200.sinks import InMemorySimilaritySink
+from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, make_catalogue
+
+
+def test_stage_classifies_reference_feature_types():
+    cat = make_catalogue(200, 300, nnz=10, seed=1)
+    st = stage(cat.features(), "mean3", pin=False)
+    assert st.genre_packed and st.meta_packed
+    assert st.genre.dtype == torch.uint8 and st.text_values.dtype == torch.float64
+    assert st.text_indptr.dtype == torch.int64 and st.text_indices.dtype == torch.int32
+    assert st.n_shows == 200 and st.vocab == 300 and st.h2d_bytes() > 0
+
+
+def test_stage_folds_non_binary_groups():
+    rng = np.random.default_rng(0)
+    f = {"genre_features": rng.random((10, 5)), "text_features": sp.csr_matrix(rng.random((10, 20))),
+         "platform_features": rng.random((10, 3)), "type_features": rng.random((10, 3)),
+         "language_features": rng.random((10, 3))}
+    st = stage(f, "mean3", pin=False)
+    assert not st.genre_packed and not st.meta_packed and len(st.meta) == 3
+    st = stage(f, "hstack", pin=False)
+    assert len(st.meta) == 1 and st.meta[0].shape == (10, 9)
+    with pytest.raises(ValueError):
+        stage(f, "bogus", pin=False)
+
+
+def test_stage_accepts_dense_text_and_wide_genre():
+    rng = np.random.default_rng(0)
+    f = {"genre_features": (rng.random((6, 70)) < 0.1).astype(np.int64),      # > 64 bits -> folded
+         "text_features": rng.random((6, 12)), "platform_features": np.eye(6)[:, :3],
+         "type_features": np.eye(6, dtype=bool)[:, :2], "language_features": np.eye(6)[:, :2]}
+    st = stage(f, pin=False)
+    assert not st.genre_packed and st.meta_packed and st.vocab == 12
+    bad = dict(f, platform_features=np.eye(5)[:, :3])
+    with pytest.raises(ValueError):
+        stage(bad, pin=False)
+
+
+def _toy_topk():
+    idx = np.array([[1, 2], [0, -1], [-1, -1]], dtype=np.int32)
+    sc = np.array([[0.9, 0.5], [0.9, np.nan], [np.nan, np.nan]])
+    return TopK(idx, np.array([2, 1, 0], np.int32), sc, sc * 0.5, sc * 0.25, sc * 0.125)
+
+
+def test_topk_to_dict_matches_reference_record_shape():
+    d = _toy_topk().to_dict([10, 20, 30])
+    assert set(d) == {10, 20}                       # show 30 omitted: no qualifying neighbour
+    assert [r["similar_show_id"] for r in d[10]] == [20, 30]
+    assert set(d[10][0]) == {"similar_show_id", "similarity_score", "genre_score", "text_score", "metadata_score"}
+    assert all(isinstance(v, float) for k, v in d[10][0].items() if k != "similar_show_id")
+    rec = _toy_topk().records([10, 20, 30])
+    assert rec["show_id"].tolist() == [10, 10, 20] and rec["similar_show_id"].tolist() == [20, 30, 10]
+    sink = InMemorySimilaritySink()
+    assert sink.bulk_store_all_similarities(d) == 3
+    st = sink.get_similarity_stats()
+    assert st["unique_shows"] == 2 and st["avg_similarities_per_show"] == 1.5
+
+
+def test_row_shard_covers_all_rows_in_tiles():
+    for n in (1, 127, 128, 129, 1000, 100_000, 250_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [row_shard(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+                assert e0 == b1
+            assert all(b % 128 == 0 for b, _ in spans)
+            assert max_shard_rows(n, world) >= (n + world - 1) // world
+
+
+def test_configs_match_baseline_shapes():
+    assert CONFIGS["C3"]["n_shows"] == 100_000 and CONFIGS["C3"]["vocab"] == 10_000
+    assert CONFIGS["C5"]["k"] == 100 and CONFIGS["C2"]["n_shows"] == 20_000
+
+
+def _gloo_worker(rank, world, port, n, k, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = row_shard(n, world, rank)
+        rows = torch.arange(b, e)
+        local = {"indices": (rows[:, None] * 10 + torch.arange(k)[None, :]).to(torch.int32),
+                 "counts": (rows % (k + 1)).to(torch.int32),
+                 "stats": torch.tensor([rank + 1] + [0] * 7, dtype=torch.int32)}
+        for f, name in enumerate(("hybrid", "genre", "text", "metadata")):
+            local[name] = rows[:, None].double() + f + torch.arange(k)[None, :].double() / 100
+        full = gather_tables(local, n, k)
+        ok = (full["indices"].shape == (n, k)
+              and torch.equal(full["indices"][:, 0].long(), torch.arange(n) * 10)
+              and torch.equal(full["counts"].long(), torch.arange(n) % (k + 1))
+              and torch.allclose(full["text"][:, 1], torch.arange(n).double() + 2 + 0.01)
+              and int(full["stats"][0]) == sum(range(1, world + 1)))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [300, 1000])
+def test_gather_tables_world_size_2_gloo(n):
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

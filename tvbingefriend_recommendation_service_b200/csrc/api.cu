@@ -1,0 +1,361 @@
+// C ABI of libtvbf (see include/tvbf.h): argument validation, workspace carving and the launch
+// sequence K1 (tcgen05 candidate pass) -> K5 (fp64 rescore + certificate) -> K6 (exact repair).
+#include "internal.cuh"
+
+#include <cmath>
+#include <cstdarg>
+
+static thread_local char g_last_error[512] = "";
+
+void tvbf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+__global__ void iota_kernel(int* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = i;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int sm_count_cached(int* out) {
+  int dev = 0;
+  TVBF_CUDA_OK(cudaGetDevice(&dev));
+  int sms = 0, major = 0;
+  TVBF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TVBF_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    tvbf_set_error("libtvbf needs an sm_100 device (B200); found compute capability %d.x", major);
+    return TVBF_ERR_UNSUPPORTED;
+  }
+  *out = sms;
+  return TVBF_OK;
+}
+
+struct Plan {
+  int rows, rb_count, col_tiles, splits, rb_per_group, grid, entries, kp, k6_grid;
+  size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_keys, off_count, total;
+};
+
+int validate_features(const tvbf_features* f) {
+  TVBF_REQUIRE(f != nullptr, "features is NULL");
+  TVBF_REQUIRE(f->n_shows > 0, "n_shows must be positive");
+  TVBF_REQUIRE(f->n_pad >= f->n_shows && f->n_pad % 256 == 0, "n_pad must be a multiple of 256 >= n_shows");
+  TVBF_REQUIRE(f->k_pad > 0 && f->k_pad % 64 == 0, "k_pad must be a positive multiple of 64");
+  TVBF_REQUIRE(f->operand && f->col_side && f->meta_scale, "operand / col_side / meta_scale missing");
+  TVBF_REQUIRE(f->text_indptr && f->text_indices && f->text_values, "text CSR missing");
+  TVBF_REQUIRE(f->text_dtype == TVBF_TEXT_FP16 || f->text_dtype == TVBF_TEXT_BF16, "bad text_dtype");
+  TVBF_REQUIRE((reinterpret_cast<uintptr_t>(f->operand) & 127) == 0, "operand must be 128-byte aligned");
+  TVBF_REQUIRE((reinterpret_cast<uintptr_t>(f->col_side) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(f->meta_scale) & 15) == 0,
+               "col_side / meta_scale must be 16-byte aligned");
+  if (f->genre_mode == TVBF_GROUP_FOLDED)
+    TVBF_REQUIRE(f->genre_dense && f->genre_dim > 0, "folded genre needs genre_dense");
+  if (f->meta_mode == TVBF_GROUP_FOLDED) {
+    TVBF_REQUIRE(f->meta_groups == (f->meta_kind == TVBF_META_MEAN3 ? 3 : 1), "bad meta_groups");
+    for (int g = 0; g < f->meta_groups; ++g)
+      TVBF_REQUIRE(f->meta_dense[g] && f->meta_dims[g] > 0, "folded metadata group %d missing", g);
+  }
+  return TVBF_OK;
+}
+
+int validate_params(const tvbf_features* f, const tvbf_params* p) {
+  TVBF_REQUIRE(p != nullptr, "params is NULL");
+  TVBF_REQUIRE(p->k >= 1, "k must be >= 1");
+  TVBF_REQUIRE(p->row_begin >= 0 && p->row_begin % 128 == 0, "row_begin must be a multiple of 128");
+  TVBF_REQUIRE(p->row_end > p->row_begin && p->row_end <= f->n_shows, "bad row range [%d, %d)",
+               p->row_begin, p->row_end);
+  TVBF_REQUIRE(std::isfinite(p->genre_weight) && std::isfinite(p->text_weight) &&
+                   std::isfinite(p->metadata_weight),
+               "weights must be finite");
+  return TVBF_OK;
+}
+
+int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
+  int sms = 0;
+  int rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  pl->rows = p->row_end - p->row_begin;
+  pl->rb_count = (pl->rows + 127) / 128;
+  pl->col_tiles = (f->n_shows + 255) / 256;
+  pl->entries = tvbf::k1_entries_per_lane(p->k);
+  pl->kp = 0;
+  pl->splits = 1;
+  pl->rb_per_group = 1;
+  pl->grid = 1;
+  const bool use_k1 = !p->force_exact && pl->entries != 0;
+  if (use_k1) {
+    pl->kp = p->candidates > 0 ? p->candidates : tvbf::k1_default_candidates(p->k);
+    const int cap = 32 * pl->entries;
+    TVBF_REQUIRE(pl->kp >= p->k && pl->kp <= cap - 64, "candidates=%d must lie in [k, %d]", pl->kp,
+                 cap - 64);
+    pl->splits = p->splits > 0 ? p->splits : tvbf::k1_choose_splits(pl->rb_count, pl->col_tiles, sms);
+    if (pl->splits > pl->col_tiles) pl->splits = pl->col_tiles;
+    while (pl->splits > 1 && pl->splits * pl->kp > 1024) --pl->splits;
+    TVBF_REQUIRE(pl->splits >= 1 && pl->splits <= sms, "bad splits %d", pl->splits);
+    pl->rb_per_group = sms / pl->splits;
+    if (pl->rb_per_group > pl->rb_count) pl->rb_per_group = pl->rb_count;
+    pl->grid = pl->rb_per_group * pl->splits;
+  }
+  pl->k6_grid = 2 * sms;
+  if (pl->k6_grid > pl->rows) pl->k6_grid = pl->rows;
+  size_t off = 0;
+  pl->off_scratch = off; off = align_up(off + (use_k1 ? static_cast<size_t>(pl->grid) * 128 * 32 * pl->entries * 8 : 0), 256);
+  pl->off_cand = off;    off = align_up(off + (use_k1 ? static_cast<size_t>(pl->rows) * pl->splits * pl->kp * 8 : 0), 256);
+  pl->off_cnt = off;     off = align_up(off + static_cast<size_t>(pl->rows) * pl->splits * 4, 256);
+  pl->off_theta = off;   off = align_up(off + static_cast<size_t>(pl->rows) * pl->splits * 4, 256);
+  pl->off_flag = off;    off = align_up(off + static_cast<size_t>(pl->rows) * 4, 256);
+  pl->off_count = off;   off = align_up(off + 256, 256);
+  pl->off_keys = off;    off = align_up(off + static_cast<size_t>(pl->k6_grid) * f->n_shows * 8, 256);
+  pl->total = off;
+  return TVBF_OK;
+}
+
+tvbf::ScoreParams score_params(const tvbf_features* f, const tvbf_params* p) {
+  tvbf::ScoreParams sp;
+  sp.f = *f;
+  sp.wg = p->genre_weight;
+  sp.wt = p->text_weight;
+  sp.wm = p->metadata_weight;
+  sp.min_similarity = p->min_similarity;
+  sp.k = p->k;
+  sp.exclude_self = p->exclude_self;
+  return sp;
+}
+
+// Bound on the relative error of one fp16/bf16 x fp16/bf16 product against the exact product of
+// the unrounded operands, plus an allowance for the fp32 accumulation inside the tensor core.
+double default_text_rel_err(int dtype) {
+  const double u = dtype == TVBF_TEXT_BF16 ? 1.0 / 256.0 : 1.0 / 2048.0;  // unit roundoff
+  return (2.0 * u + u * u) * 1.01 + 1.0 / 262144.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvbf_version(void) { return TVBF_VERSION; }
+
+const char* tvbf_last_error(void) { return g_last_error; }
+
+int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  TVBF_CUDA_OK(cudaGetDevice(&dev));
+  int sms = 0, major = 0, minor = 0;
+  TVBF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TVBF_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  TVBF_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = major;
+  if (cc_minor) *cc_minor = minor;
+  if (major != 10) {
+    tvbf_set_error("libtvbf needs an sm_100 device (B200); found compute capability %d.%d", major,
+                   minor);
+    return TVBF_ERR_UNSUPPORTED;
+  }
+  return TVBF_OK;
+}
+
+size_t tvbf_topk_workspace_bytes(const tvbf_features* f, const tvbf_params* p) {
+  if (validate_features(f) != TVBF_OK || validate_params(f, p) != TVBF_OK) return 0;
+  Plan pl;
+  if (make_plan(f, p, &pl) != TVBF_OK) return 0;
+  return pl.total;
+}
+
+int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_topk_out* out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  rc = validate_params(f, p);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(out && out->indices && out->counts && out->hybrid && out->genre && out->text &&
+                   out->metadata && out->stats,
+               "output table has NULL members");
+  TVBF_REQUIRE(workspace != nullptr, "workspace is NULL");
+  Plan pl;
+  rc = make_plan(f, p, &pl);
+  if (rc != TVBF_OK) return rc;
+  if (workspace_bytes < pl.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + pl.off_keys);
+  TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
+  const tvbf::ScoreParams sp = score_params(f, p);
+
+  const bool use_k1 = !p->force_exact && pl.entries != 0;
+  if (!use_k1) {
+    // every row through the exact kernel
+    iota_kernel<<<(pl.rows + 255) / 256, 256, 0, st>>>(flagged, pl.rows);
+    TVBF_LAUNCH_OK("iota_kernel");
+    rc = tvbf::k6_launch(sp, flagged, pl.rows, nullptr, p->row_begin, 1, keys, pl.k6_grid, *out, st);
+    if (rc != TVBF_OK) return rc;
+    return TVBF_OK;
+  }
+
+  const int s = f->text_scale_log2;
+  const double inv_scale2 = std::ldexp(1.0, -2 * s);
+  const double rel = p->text_rel_err > 0 ? p->text_rel_err : default_text_rel_err(f->text_dtype);
+  // folded groups live inside the accumulator already weighted; their error is bounded
+  // absolutely (Cauchy-Schwarz on unit rows): |err| <= rel * weight
+  double folded_w = 0.0;
+  if (f->genre_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->genre_weight);
+  if (f->meta_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->metadata_weight);
+  const bool any_folded = folded_w > 0.0;
+  const double wsum = std::fabs(p->genre_weight) + std::fabs(p->text_weight) + std::fabs(p->metadata_weight);
+  if (any_folded) {
+    TVBF_REQUIRE(p->text_weight > 0.0, "folded feature groups need text_weight > 0");
+    TVBF_REQUIRE(p->genre_weight >= 0.0 && p->metadata_weight >= 0.0,
+                 "folded feature groups need non-negative weights");
+  }
+
+  tvbf::K1Params kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.col_side = static_cast<const TvbfColSide*>(f->col_side);
+  kp.meta_scale = f->meta_scale;
+  kp.scratch = reinterpret_cast<uint2*>(ws + pl.off_scratch);
+  kp.cand = reinterpret_cast<uint2*>(ws + pl.off_cand);
+  kp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
+  kp.cand_theta = reinterpret_cast<float*>(ws + pl.off_theta);
+  kp.n_shows = f->n_shows;
+  kp.row_begin = p->row_begin;
+  kp.row_end = p->row_end;
+  kp.k_blocks = f->k_pad / 64;
+  kp.col_tiles = pl.col_tiles;
+  kp.splits = pl.splits;
+  kp.rb_count = pl.rb_count;
+  kp.rb_per_group = pl.rb_per_group;
+  kp.kp = pl.kp;
+  kp.exclude_self = p->exclude_self;
+  if (any_folded) {
+    // operand columns were scaled by 2^s * sqrt(w_group / text_weight): acc * text_weight * 2^-2s
+    // is the whole folded part of the hybrid; bound the error absolutely.
+    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
+    kp.w_text_err = 0.0f;
+    kp.eps = static_cast<float>(rel * (std::fabs(p->text_weight) + folded_w) + 4e-6 * (wsum + 1.0));
+  } else {
+    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
+    kp.w_text_err = static_cast<float>(std::fabs(p->text_weight) * inv_scale2 * rel);
+    kp.eps = static_cast<float>(4e-6 * (wsum + 1.0));
+  }
+  kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
+  kp.w_meta8 = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight / 8.0) : 0.0f;
+  {
+    // strictly below min_similarity in fp32 so that U >= min_similarity always passes "U > theta"
+    const double ms = p->min_similarity;
+    float th = static_cast<float>(ms);
+    if (!(ms > -3.0e38)) th = -3.0e38f;
+    th = std::nextafterf(th, -INFINITY);
+    if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
+    kp.theta_init = th;
+  }
+  rc = tvbf::k1_launch(f, kp, pl.entries, pl.grid, st);
+  if (rc != TVBF_OK) return rc;
+  rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.splits, pl.kp, p->row_begin,
+                       pl.rows, *out, flagged, st);
+  if (rc != TVBF_OK) return rc;
+  if (!p->skip_fallback) {
+    rc = tvbf::k6_launch(sp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, pl.k6_grid, *out, st);
+    if (rc != TVBF_OK) return rc;
+  }
+  return TVBF_OK;
+}
+
+size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed) {
+  if (f == nullptr || n_rows_listed <= 0) return 0;
+  int sms = 0;
+  if (sm_count_cached(&sms) != TVBF_OK) return 0;
+  int grid = 2 * sms;
+  if (grid > n_rows_listed) grid = n_rows_listed;
+  return align_up(static_cast<size_t>(grid) * f->n_shows * 8, 256);
+}
+
+int tvbf_exact_rows(const tvbf_features* f, const tvbf_params* p, const int32_t* rows,
+                    int32_t n_rows_listed, const tvbf_topk_out* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(p && p->k >= 1 && rows && n_rows_listed > 0, "tvbf_exact_rows: bad arguments");
+  TVBF_REQUIRE(out && out->indices && out->counts && out->hybrid && out->genre && out->text &&
+                   out->metadata,
+               "output table has NULL members");
+  const size_t need = tvbf_exact_workspace_bytes(f, n_rows_listed);
+  if (need == 0) return TVBF_ERR_UNSUPPORTED;
+  if (workspace == nullptr || workspace_bytes < need) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return TVBF_ERR_WORKSPACE;
+  }
+  int sms = 0;
+  rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  int grid = 2 * sms;
+  if (grid > n_rows_listed) grid = n_rows_listed;
+  const tvbf::ScoreParams sp = score_params(f, p);
+  return tvbf::k6_launch(sp, rows, n_rows_listed, nullptr, 0, 0,
+                         static_cast<unsigned long long*>(workspace), grid, *out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int tvbf_matrix_rows_topk(const double* hybrid, const double* genre, const double* text,
+                          const double* metadata, int32_t n, const tvbf_params* p,
+                          const int32_t* rows, int32_t n_rows_listed, const tvbf_topk_out* out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  TVBF_REQUIRE(hybrid && genre && text && metadata && n > 0, "tvbf_matrix_rows_topk: bad matrices");
+  TVBF_REQUIRE(p && p->k >= 1 && rows && n_rows_listed > 0, "tvbf_matrix_rows_topk: bad arguments");
+  TVBF_REQUIRE(out && out->indices && out->counts && out->hybrid && out->genre && out->text &&
+                   out->metadata,
+               "output table has NULL members");
+  int sms = 0;
+  int rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  int grid = 2 * sms;
+  if (grid > n_rows_listed) grid = n_rows_listed;
+  const size_t need = align_up(static_cast<size_t>(grid) * n * 8, 256);
+  if (workspace == nullptr || workspace_bytes < need) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return TVBF_ERR_WORKSPACE;
+  }
+  return tvbf::k6_launch_matrix(hybrid, genre, text, metadata, n, p->k, p->exclude_self,
+                                p->min_similarity, rows, n_rows_listed,
+                                static_cast<unsigned long long*>(workspace), grid, *out,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
+                         void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(out != nullptr, "out is NULL");
+  TVBF_REQUIRE(row0 >= 0 && row0 + 128 <= f->n_pad && col0 >= 0 && col0 + 256 <= f->n_pad,
+               "tile origin outside the padded operand");
+  int sms = 0;
+  rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  tvbf::K1Params kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.col_side = static_cast<const TvbfColSide*>(f->col_side);
+  kp.meta_scale = f->meta_scale;
+  kp.dump = out;
+  kp.n_shows = f->n_shows;
+  kp.row_begin = row0;
+  kp.row_end = row0 + 128;
+  kp.k_blocks = f->k_pad / 64;
+  kp.col_tiles = 1;
+  kp.splits = 1;
+  kp.rb_count = 1;
+  kp.rb_per_group = 1;
+  kp.dump_col0 = col0;
+  kp.kp = 32;
+  return tvbf::k1_launch_dump(f, kp, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

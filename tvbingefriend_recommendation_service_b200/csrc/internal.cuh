@@ -1,0 +1,63 @@
+// Types and launchers shared between the translation units of libtvbf (not part of the ABI).
+#pragma once
+
+#include "common.cuh"
+
+namespace tvbf {
+
+// parameters of the tcgen05 candidate kernel (hybrid_topk.cu)
+struct K1Params {
+  const TvbfColSide* col_side;
+  const float* meta_scale;
+  uint2* scratch;      // [gridDim.x][128][32*E] working candidate lists (score bits, column)
+  uint2* cand;         // [rows][splits][kp] sorted candidates
+  int* cand_cnt;       // [rows][splits]
+  float* cand_theta;   // [rows][splits] bound on every dropped U, -inf if nothing was dropped
+  float* dump;         // dump kernel only: [128][256] raw accumulators of one tile
+  int n_shows;
+  int row_begin;       // multiple of 128
+  int row_end;
+  int k_blocks;        // k_pad / 64
+  int col_tiles;       // ceil(n_shows / 256)
+  int splits;
+  int rb_count;        // row blocks of this shard
+  int rb_per_group;    // row blocks processed concurrently (grid = rb_per_group * splits)
+  int dump_col0;       // dump kernel only
+  int kp;              // candidates kept per (row, split)
+  int exclude_self;
+  float w_text;        // text_weight * 2^-2s
+  float w_text_err;    // |text_weight| * 2^-2s * rel_err  (multiplies |acc|)
+  float w_genre;
+  float w_meta8;       // metadata_weight / 8 (the byte-compare popcount counts 8 per match)
+  float eps;           // absolute slack: fp32 rounding of the epilogue (+ folded-group bounds)
+  float theta_init;    // just below min_similarity
+};
+
+// parameters of the exact fp64 scorers (rescore.cu)
+struct ScoreParams {
+  tvbf_features f;
+  double wg, wt, wm;
+  double min_similarity;
+  int k;
+  int exclude_self;
+};
+
+int k1_entries_per_lane(int k);
+int k1_default_candidates(int k);
+int k1_choose_splits(int rb_count, int col_tiles, int sm_count);
+int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int grid,
+              cudaStream_t st);
+int k1_launch_dump(const tvbf_features* f, const K1Params& kp, cudaStream_t st);
+int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
+              const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
+              const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st);
+int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
+              int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
+              const tvbf_topk_out& out, cudaStream_t st);
+
+int k6_launch_matrix(const double* h, const double* g, const double* t, const double* m, int n,
+                     int k, int exclude_self, double min_similarity, const int* rows, int n_listed,
+                     unsigned long long* key_scratch, int grid, const tvbf_topk_out& out,
+                     cudaStream_t st);
+
+}  // namespace tvbf

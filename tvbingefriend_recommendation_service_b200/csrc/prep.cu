@@ -1,0 +1,250 @@
+// K0 -- feature preparation kernels (HBM-bound, one pass over the inputs).
+//
+// They replace what sklearn does inside every cosine_similarity call of the reference
+// (scripts/populate_database.py:180-186; ml/similarity_computer.py:41,58,86): dtype promotion to
+// float64 and row-wise L2 normalisation with zero rows left untouched, done ONCE per catalogue
+// instead of five times per source show, plus the packing of the binary groups.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(tvbf::kFullMask, v, o);
+  return v;
+}
+
+// one warp per CSR row: values_out = values / sqrt(sum(values^2)); zero rows untouched
+__global__ void csr_normalize_kernel(const int64_t* __restrict__ indptr,
+                                     const double* __restrict__ values, int n_rows,
+                                     double* __restrict__ out) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  int64_t b = indptr[row], e = indptr[row + 1];
+  double s = 0.0;
+  for (int64_t i = b + lane; i < e; i += 32) s += values[i] * values[i];
+  s = warp_sum(s);
+  double norm = sqrt(s);
+  if (norm == 0.0) norm = 1.0;
+  for (int64_t i = b + lane; i < e; i += 32) out[i] = values[i] / norm;
+}
+
+template <typename T>
+__device__ __forceinline__ T cvt_operand(double v);
+template <>
+__device__ __forceinline__ __half cvt_operand<__half>(double v) {
+  return __double2half(v);  // round-to-nearest-even from fp64: a single rounding
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_operand<__nv_bfloat16>(double v) {
+  return __double2bfloat16(v);
+}
+
+template <typename T>
+__global__ void csr_to_operand_kernel(const int64_t* __restrict__ indptr,
+                                      const int32_t* __restrict__ indices,
+                                      const double* __restrict__ values, int n_rows,
+                                      T* __restrict__ operand, int k_pad, int col_offset,
+                                      double scale) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  int64_t b = indptr[row], e = indptr[row + 1];
+  T* dst = operand + static_cast<size_t>(row) * k_pad + col_offset;
+  for (int64_t i = b + lane; i < e; i += 32) dst[indices[i]] = cvt_operand<T>(values[i] * scale);
+}
+
+__global__ void dense_normalize_kernel(const double* __restrict__ in, int n_rows, int dim,
+                                       double* __restrict__ out) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const double* x = in + static_cast<size_t>(row) * dim;
+  double s = 0.0;
+  for (int c = 0; c < dim; ++c) s += x[c] * x[c];
+  double norm = sqrt(s);
+  if (norm == 0.0) norm = 1.0;
+  double* y = out + static_cast<size_t>(row) * dim;
+  for (int c = 0; c < dim; ++c) y[c] = x[c] / norm;
+}
+
+template <typename T>
+__global__ void dense_to_operand_kernel(const double* __restrict__ dense, int n_rows, int dim,
+                                        T* __restrict__ operand, int k_pad, int col_offset,
+                                        double scale) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t total = static_cast<size_t>(n_rows) * dim;
+  if (i >= total) return;
+  size_t row = i / dim;
+  int c = static_cast<int>(i - row * dim);
+  operand[row * k_pad + col_offset + c] = cvt_operand<T>(dense[i] * scale);
+}
+
+__global__ void genre_bits_kernel(const uint8_t* __restrict__ genre, int n_rows, int dim,
+                                  TvbfColSide* __restrict__ col_side) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const uint8_t* g = genre + static_cast<size_t>(row) * dim;
+  unsigned long long bits = 0ull;
+  for (int c = 0; c < dim; ++c)
+    if (g[c]) bits |= 1ull << c;
+  int pc = __popcll(bits);
+  col_side[row].genre_bits = bits;
+  col_side[row].genre_rnorm = pc ? 1.0f / sqrtf(static_cast<float>(pc)) : 0.0f;
+}
+
+__device__ __forceinline__ uint32_t one_hot_id(const uint8_t* m, int dim, int row) {
+  if (m == nullptr || dim <= 0) return 0xFFu;
+  const uint8_t* x = m + static_cast<size_t>(row) * dim;
+  uint32_t id = 0xFFu;
+  for (int c = 0; c < dim; ++c)
+    if (x[c]) id = static_cast<uint32_t>(c);
+  return id;
+}
+
+__global__ void meta_ids_kernel(const uint8_t* __restrict__ platform, int p_dim,
+                                const uint8_t* __restrict__ type, int t_dim,
+                                const uint8_t* __restrict__ language, int l_dim, int n_rows,
+                                int n_pad, int meta_kind, TvbfColSide* __restrict__ col_side,
+                                float* __restrict__ meta_scale) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_pad) return;
+  uint32_t p = 0xFFu, t = 0xFFu, l = 0xFFu;
+  if (row < n_rows) {
+    p = one_hot_id(platform, p_dim, row);
+    t = one_hot_id(type, t_dim, row);
+    l = one_hot_id(language, l_dim, row);
+  }
+  col_side[row].meta_ids = p | (t << 8) | (l << 16) | (0xFFu << 24);
+  int valid = (p != 0xFFu) + (t != 0xFFu) + (l != 0xFFu);
+  float s;
+  if (row >= n_rows) s = 0.0f;
+  else if (meta_kind == TVBF_META_MEAN3) s = 0.57735026918962576f;  // 1/sqrt(3)
+  else s = valid ? 1.0f / sqrtf(static_cast<float>(valid)) : 0.0f;
+  meta_scale[row] = s;
+}
+
+__global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr,
+                                    const int32_t* __restrict__ indices,
+                                    const double* __restrict__ values, int n_rows, int dim,
+                                    double* __restrict__ dense) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  int64_t b = indptr[row], e = indptr[row + 1];
+  double* dst = dense + static_cast<size_t>(row) * dim;
+  for (int64_t i = b + lane; i < e; i += 32) dst[indices[i]] = values[i];
+}
+
+inline unsigned blocks_for(size_t work, unsigned per_block) {
+  return static_cast<unsigned>((work + per_block - 1) / per_block);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tvbf_prep_csr_normalize(const int64_t* indptr, const double* values, int32_t n_rows,
+                            double* values_out, void* stream) {
+  TVBF_REQUIRE(indptr && values_out && n_rows >= 0, "tvbf_prep_csr_normalize: bad arguments");
+  if (n_rows == 0) return TVBF_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  csr_normalize_kernel<<<blocks_for(static_cast<size_t>(n_rows) * 32, 256), 256, 0, st>>>(
+      indptr, values, n_rows, values_out);
+  TVBF_LAUNCH_OK("csr_normalize_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_csr_to_operand(const int64_t* indptr, const int32_t* indices, const double* values,
+                             int32_t n_rows, void* operand, int32_t k_pad, int32_t col_offset,
+                             double scale, int32_t dtype, void* stream) {
+  TVBF_REQUIRE(indptr && operand && n_rows >= 0 && k_pad > 0 && col_offset >= 0,
+               "tvbf_prep_csr_to_operand: bad arguments");
+  TVBF_REQUIRE(dtype == TVBF_TEXT_FP16 || dtype == TVBF_TEXT_BF16,
+               "tvbf_prep_csr_to_operand: dtype must be TVBF_TEXT_FP16 or TVBF_TEXT_BF16");
+  if (n_rows == 0) return TVBF_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  unsigned grid = blocks_for(static_cast<size_t>(n_rows) * 32, 256);
+  if (dtype == TVBF_TEXT_FP16)
+    csr_to_operand_kernel<__half><<<grid, 256, 0, st>>>(indptr, indices, values, n_rows,
+                                                        static_cast<__half*>(operand), k_pad,
+                                                        col_offset, scale);
+  else
+    csr_to_operand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        indptr, indices, values, n_rows, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset,
+        scale);
+  TVBF_LAUNCH_OK("csr_to_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_dense_normalize(const double* in, int32_t n_rows, int32_t dim, double* out,
+                              void* stream) {
+  TVBF_REQUIRE(in && out && n_rows >= 0 && dim > 0, "tvbf_prep_dense_normalize: bad arguments");
+  if (n_rows == 0) return TVBF_OK;
+  dense_normalize_kernel<<<blocks_for(n_rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, n_rows, dim, out);
+  TVBF_LAUNCH_OK("dense_normalize_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim, void* operand,
+                               int32_t k_pad, int32_t col_offset, double scale, int32_t dtype,
+                               void* stream) {
+  TVBF_REQUIRE(dense && operand && n_rows >= 0 && dim > 0 && col_offset >= 0 &&
+                   col_offset + dim <= k_pad,
+               "tvbf_prep_dense_to_operand: bad arguments");
+  TVBF_REQUIRE(dtype == TVBF_TEXT_FP16 || dtype == TVBF_TEXT_BF16,
+               "tvbf_prep_dense_to_operand: dtype must be TVBF_TEXT_FP16 or TVBF_TEXT_BF16");
+  if (n_rows == 0) return TVBF_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  unsigned grid = blocks_for(static_cast<size_t>(n_rows) * dim, 256);
+  if (dtype == TVBF_TEXT_FP16)
+    dense_to_operand_kernel<__half><<<grid, 256, 0, st>>>(
+        dense, n_rows, dim, static_cast<__half*>(operand), k_pad, col_offset, scale);
+  else
+    dense_to_operand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        dense, n_rows, dim, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset, scale);
+  TVBF_LAUNCH_OK("dense_to_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,
+                         void* stream) {
+  TVBF_REQUIRE(genre && col_side && n_rows >= 0, "tvbf_prep_genre_bits: bad arguments");
+  TVBF_REQUIRE(dim >= 1 && dim <= 64, "tvbf_prep_genre_bits: dim %d outside 1..64", dim);
+  if (n_rows == 0) return TVBF_OK;
+  genre_bits_kernel<<<blocks_for(n_rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      genre, n_rows, dim, static_cast<TvbfColSide*>(col_side));
+  TVBF_LAUNCH_OK("genre_bits_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* type, int32_t t_dim,
+                       const uint8_t* language, int32_t l_dim, int32_t n_rows, int32_t n_pad,
+                       int32_t meta_kind, void* col_side, float* meta_scale, void* stream) {
+  TVBF_REQUIRE(col_side && meta_scale && n_rows >= 0 && n_pad >= n_rows,
+               "tvbf_prep_meta_ids: bad arguments");
+  TVBF_REQUIRE(p_dim <= 254 && t_dim <= 254 && l_dim <= 254,
+               "tvbf_prep_meta_ids: one-hot groups wider than 254 columns are not packable");
+  TVBF_REQUIRE(meta_kind == TVBF_META_MEAN3 || meta_kind == TVBF_META_HSTACK,
+               "tvbf_prep_meta_ids: bad meta_kind");
+  if (n_pad == 0) return TVBF_OK;
+  meta_ids_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      platform, p_dim, type, t_dim, language, l_dim, n_rows, n_pad, meta_kind,
+      static_cast<TvbfColSide*>(col_side), meta_scale);
+  TVBF_LAUNCH_OK("meta_ids_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_csr_to_dense_f64(const int64_t* indptr, const int32_t* indices, const double* values,
+                          int32_t n_rows, int32_t dim, double* dense, void* stream) {
+  TVBF_REQUIRE(indptr && dense && n_rows >= 0 && dim > 0, "tvbf_csr_to_dense_f64: bad arguments");
+  if (n_rows == 0) return TVBF_OK;
+  csr_to_dense_kernel<<<blocks_for(static_cast<size_t>(n_rows) * 32, 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(indptr, indices, values, n_rows, dim,
+                                                             dense);
+  TVBF_LAUNCH_OK("csr_to_dense_kernel");
+  return TVBF_OK;
+}
+
+}  // extern "C"

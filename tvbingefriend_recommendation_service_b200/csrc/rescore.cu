@@ -1,0 +1,435 @@
+// K5 + K6 -- exact fp64 scoring.
+//
+// K5 (rescore_kernel): recomputes every candidate pair the tensor-core pass kept, in float64 from
+// the normalised inputs and with the reference's operation order
+//   hybrid = genre_weight * genre + text_weight * text + metadata_weight * metadata
+// (scripts/populate_database.py:187-192), applies the reference's selection rule -- skip self,
+// drop score < min_similarity, keep top_n (populate_database.py:195-218) -- with the stated
+// tie-break (score descending, column index ascending), and CERTIFIES the row: every column the
+// candidate pass dropped has upper bound U <= theta, so the row is final iff theta < the k-th
+// exact score (or < min_similarity when fewer than k qualify).  Rows that cannot be certified
+// (tie plateaus wider than the candidate list, near-ties below the fp16 bound) go to K6.
+//
+// K6 (exact_rows_kernel): scores ONE source row against all N columns in fp64 and selects the
+// exact top-k with a radix select over order-preserving 64-bit keys; also the engine behind the
+// single-show query of services/content_based_service.py:161-236 for arbitrary n.
+#include "internal.cuh"
+
+namespace tvbf {
+
+
+__device__ __forceinline__ double text_dot(const tvbf_features& f, int i, int j) {
+  const int64_t bi = f.text_indptr[i], ei = f.text_indptr[i + 1];
+  const int64_t bj = f.text_indptr[j], ej = f.text_indptr[j + 1];
+  if (bi == ei || bj == ej) return 0.0;
+  int64_t a = bi, b = bj;
+  int ca = f.text_indices[a], cb = f.text_indices[b];
+  double s = 0.0;
+  while (true) {
+    if (ca == cb) {
+      s += f.text_values[a] * f.text_values[b];
+      ++a; ++b;
+      if (a >= ei || b >= ej) break;
+      ca = f.text_indices[a];
+      cb = f.text_indices[b];
+    } else if (ca < cb) {
+      if (++a >= ei) break;
+      ca = f.text_indices[a];
+    } else {
+      if (++b >= ej) break;
+      cb = f.text_indices[b];
+    }
+  }
+  return s;
+}
+
+__device__ __forceinline__ double dense_dot(const double* x, int dim, int i, int j) {
+  const double* a = x + static_cast<size_t>(i) * dim;
+  const double* b = x + static_cast<size_t>(j) * dim;
+  double s = 0.0;
+  for (int c = 0; c < dim; ++c) s += a[c] * b[c];
+  return s;
+}
+
+__device__ __forceinline__ double genre_score(const tvbf_features& f, int i, int j) {
+  if (f.genre_mode == TVBF_GROUP_PACKED) {
+    const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+    const unsigned long long bi = cs[i].genre_bits, bj = cs[j].genre_bits;
+    const int ni = __popcll(bi), nj = __popcll(bj);
+    if (ni == 0 || nj == 0) return 0.0;
+    const int c = __popcll(bi & bj);
+    return static_cast<double>(c) * ((1.0 / sqrt(static_cast<double>(ni))) *
+                                     (1.0 / sqrt(static_cast<double>(nj))));
+  }
+  if (f.genre_mode == TVBF_GROUP_FOLDED) return dense_dot(f.genre_dense, f.genre_dim, i, j);
+  return 0.0;
+}
+
+__device__ __forceinline__ int id_matches(uint32_t a, uint32_t b, int* na, int* nb) {
+  int eq = 0, va = 0, vb = 0;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const uint32_t x = (a >> (8 * g)) & 0xFFu, y = (b >> (8 * g)) & 0xFFu;
+    va += (x != 0xFFu);
+    vb += (y != 0xFFu);
+    eq += (x == y && x != 0xFFu);
+  }
+  *na = va;
+  *nb = vb;
+  return eq;
+}
+
+__device__ __forceinline__ double meta_score(const tvbf_features& f, int i, int j) {
+  if (f.meta_mode == TVBF_GROUP_PACKED) {
+    const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+    int ni, nj;
+    const int eq = id_matches(cs[i].meta_ids, cs[j].meta_ids, &ni, &nj);
+    if (f.meta_kind == TVBF_META_MEAN3) return static_cast<double>(eq) / 3.0;
+    if (ni == 0 || nj == 0) return 0.0;
+    return static_cast<double>(eq) * ((1.0 / sqrt(static_cast<double>(ni))) *
+                                      (1.0 / sqrt(static_cast<double>(nj))));
+  }
+  if (f.meta_mode == TVBF_GROUP_FOLDED) {
+    if (f.meta_kind == TVBF_META_MEAN3) {
+      const double p = dense_dot(f.meta_dense[0], f.meta_dims[0], i, j);
+      const double t = dense_dot(f.meta_dense[1], f.meta_dims[1], i, j);
+      const double l = dense_dot(f.meta_dense[2], f.meta_dims[2], i, j);
+      return (p + t + l) / 3;
+    }
+    return dense_dot(f.meta_dense[0], f.meta_dims[0], i, j);
+  }
+  return 0.0;
+}
+
+struct Scores {
+  double h, g, t, m;
+};
+
+__device__ __forceinline__ Scores score_pair(const ScoreParams& sp, int i, int j) {
+  Scores s;
+  s.g = genre_score(sp.f, i, j);
+  s.t = text_dot(sp.f, i, j);
+  s.m = meta_score(sp.f, i, j);
+  s.h = sp.wg * s.g + sp.wt * s.t + sp.wm * s.m;
+  return s;
+}
+
+// (score desc, column asc) strict "a ranks before b"
+__device__ __forceinline__ bool ranks_before(double ha, int ja, double hb, int jb) {
+  return ha > hb || (ha == hb && ja < jb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: one warp per source row
+// ---------------------------------------------------------------------------------------------
+constexpr int K5_WARPS = 4;
+
+__global__ void __launch_bounds__(K5_WARPS * 32)
+rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
+               const int* __restrict__ cand_cnt, const float* __restrict__ cand_theta, int splits,
+               int kp, int row_begin, int n_rows, tvbf_topk_out out, int* flagged_rows,
+               int max_cand) {
+  extern __shared__ __align__(16) uint8_t k5_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * K5_WARPS + warp;
+  if (r >= n_rows) return;
+  const int i = row_begin + r;
+  uint8_t* base = k5_smem + static_cast<size_t>(warp) * max_cand * 40;
+  double* sh = reinterpret_cast<double*>(base);
+  double* sg = sh + max_cand;
+  double* st = sg + max_cand;
+  double* sm = st + max_cand;
+  int* sj = reinterpret_cast<int*>(sm + max_cand);
+  __shared__ double s_kth[K5_WARPS];
+
+  // gather the candidate columns of all splits
+  int total = 0;
+  float theta = __int_as_float(0xff800000);
+  for (int s = 0; s < splits; ++s) {
+    const size_t slot = static_cast<size_t>(r) * splits + s;
+    const int n = cand_cnt[slot];
+    theta = fmaxf(theta, cand_theta[slot]);
+    for (int e = lane; e < n; e += 32) sj[total + e] = static_cast<int>(cand[slot * kp + e].y);
+    total += n;
+  }
+  __syncwarp();
+  // exact scores
+  int valid = 0;
+  for (int e = lane; e < total; e += 32) {
+    const int j = sj[e];
+    const Scores s = score_pair(sp, i, j);
+    const bool ok = (s.h >= sp.min_similarity) && !(sp.exclude_self && j == i);
+    sh[e] = ok ? s.h : -INFINITY;
+    sg[e] = s.g;
+    st[e] = s.t;
+    sm[e] = s.m;
+    valid += ok;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(kFullMask, valid, o);
+  __syncwarp();
+  const int k = sp.k;
+  const int count = valid < k ? valid : k;
+  if (lane == 0) s_kth[warp] = sp.min_similarity;
+  __syncwarp();
+  // rank by counting: position = number of entries that rank before this one
+  const size_t obase = static_cast<size_t>(r) * k;
+  for (int e = lane; e < total; e += 32) {
+    const double he = sh[e];
+    if (he == -INFINITY) continue;
+    const int je = sj[e];
+    int rank = 0;
+    for (int o = 0; o < total; ++o) rank += ranks_before(sh[o], sj[o], he, je);
+    if (rank < k) {
+      out.indices[obase + rank] = je;
+      out.hybrid[obase + rank] = he;
+      out.genre[obase + rank] = sg[e];
+      out.text[obase + rank] = st[e];
+      out.metadata[obase + rank] = sm[e];
+      if (rank == k - 1) s_kth[warp] = he;
+    }
+  }
+  for (int e = count + lane; e < k; e += 32) {
+    out.indices[obase + e] = -1;
+    out.hybrid[obase + e] = NAN;
+    out.genre[obase + e] = NAN;
+    out.text[obase + e] = NAN;
+    out.metadata[obase + e] = NAN;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    out.counts[r] = count;
+    atomicAdd(&out.stats[1], total);
+    // certificate: all dropped columns have exact score <= U <= theta
+    const double bound = s_kth[warp];  // k-th exact score, or min_similarity if fewer than k
+    const bool safe = static_cast<double>(theta) < bound;
+    if (!safe) {
+      const int pos = atomicAdd(&out.stats[0], 1);
+      flagged_rows[pos] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: exact row kernel -- one CTA per listed source row, persistent over the list
+// ---------------------------------------------------------------------------------------------
+constexpr int K6_THREADS = 512;
+constexpr int K6_MAXK = 1024;
+
+__device__ __forceinline__ unsigned long long f64_orderable(double d) {
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(d));
+  return b ^ ((b >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_orderable(unsigned long long u) {
+  unsigned long long b = u ^ ((u >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+  return __longlong_as_double(static_cast<long long>(b));
+}
+
+// rows: shard-local row numbers when `rows_are_local`, else absolute source rows.
+// count_ptr (device) overrides n_listed when non-null (flagged rows of K5).
+struct FeatureScorer {
+  ScoreParams sp;
+  __device__ __forceinline__ Scores operator()(int i, int j) const { return score_pair(sp, i, j); }
+};
+// variant C: rows of precomputed N x N matrices (services/content_based_service.py:206-231)
+struct MatrixScorer {
+  const double* h;
+  const double* g;
+  const double* t;
+  const double* m;
+  int n;
+  __device__ __forceinline__ Scores operator()(int i, int j) const {
+    const size_t e = static_cast<size_t>(i) * n + j;
+    Scores s;
+    s.h = h[e]; s.g = g[e]; s.t = t[e]; s.m = m[e];
+    return s;
+  }
+};
+
+struct SelectParams {
+  int n;
+  int k;
+  int exclude_self;
+  double min_similarity;
+};
+
+template <class Scorer>
+__global__ void __launch_bounds__(K6_THREADS)
+exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __restrict__ rows,
+                  int n_listed, const int* __restrict__ count_ptr, int row_begin,
+                  int rows_are_local, unsigned long long* __restrict__ key_scratch,
+                  tvbf_topk_out out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_rank, s_valid, s_above, s_taken, s_warp_tot[K6_THREADS / 32];
+  __shared__ unsigned long long win_key[K6_MAXK];
+  __shared__ int win_j[K6_MAXK];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = sel.n;
+  const int listed = count_ptr ? *count_ptr : n_listed;
+  unsigned long long* keys = key_scratch + static_cast<size_t>(blockIdx.x) * n;
+  const int k = sel.k;
+
+  for (int t = blockIdx.x; t < listed; t += gridDim.x) {
+    const int r = rows[t];
+    const int i = rows_are_local ? row_begin + r : r;
+    const int orow = rows_are_local ? r : t;
+    // ---- 1. exact scores of row i against every column -> order-preserving keys (0 = invalid)
+    if (tid == 0) { s_valid = 0; s_above = 0; s_taken = 0; }
+    __syncthreads();
+    int my_valid = 0;
+    for (int j = tid; j < n; j += K6_THREADS) {
+      const Scores s = scorer(i, j);
+      const bool ok = (s.h >= sel.min_similarity) && !(sel.exclude_self && j == i);
+      keys[j] = ok ? f64_orderable(s.h) : 0ull;
+      my_valid += ok;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(kFullMask, my_valid, o);
+    if (lane == 0 && my_valid) atomicAdd(&s_valid, my_valid);
+    __syncthreads();
+    const int count = s_valid < k ? s_valid : k;
+    const size_t obase = static_cast<size_t>(orow) * k;
+    if (count > 0) {
+      // ---- 2. radix select: value of the count-th largest key
+      if (tid == 0) { s_prefix = 0ull; s_rank = count; }
+      for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += K6_THREADS) hist[b] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int j = tid; j < n; j += K6_THREADS) {
+          const unsigned long long key = keys[j];
+          if (key != 0ull && (key & hi_mask) == prefix)
+            atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int rank = s_rank;  // rank-th largest among keys matching the prefix
+          int d = 255;
+          for (; d > 0; --d) {
+            const int c = static_cast<int>(hist[d]);
+            if (rank <= c) break;
+            rank -= c;
+          }
+          s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+          s_rank = rank;
+        }
+        __syncthreads();
+      }
+      const unsigned long long vstar = s_prefix;  // count-th largest key
+      // ---- 3a. everything strictly above v*
+      for (int j = tid; j < n; j += K6_THREADS) {
+        const unsigned long long key = keys[j];
+        if (key > vstar) {
+          const int pos = atomicAdd(&s_above, 1);
+          win_key[pos] = key;
+          win_j[pos] = j;
+        }
+      }
+      __syncthreads();
+      const int above = s_above;
+      const int need = count - above;  // >= 1 : lowest column indices among keys == v*
+      // ---- 3b. ordered take of the ties
+      for (int base = 0; base < n; base += K6_THREADS) {
+        const int j = base + tid;
+        const bool flag = j < n && keys[j] == vstar;
+        const unsigned bal = __ballot_sync(kFullMask, flag);
+        if (lane == 0) s_warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_taken;
+        for (int w = 0; w < warp; ++w) before += s_warp_tot[w];
+        int chunk_total = 0;
+        for (int w = 0; w < K6_THREADS / 32; ++w) chunk_total += s_warp_tot[w];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        if (flag && pos < need) {
+          win_key[above + pos] = vstar;
+          win_j[above + pos] = j;
+        }
+        __syncthreads();
+        if (tid == 0) s_taken += chunk_total;
+        __syncthreads();
+        if (s_taken >= need) break;
+      }
+      __syncthreads();
+      // ---- 4. order the winners (score desc, column asc) and emit
+      for (int e = tid; e < count; e += K6_THREADS) {
+        const unsigned long long ke = win_key[e];
+        const int je = win_j[e];
+        int rank = 0;
+        for (int o = 0; o < count; ++o)
+          rank += (win_key[o] > ke) || (win_key[o] == ke && win_j[o] < je);
+        const Scores s = scorer(i, je);
+        out.indices[obase + rank] = je;
+        out.hybrid[obase + rank] = f64_from_orderable(ke);
+        out.genre[obase + rank] = s.g;
+        out.text[obase + rank] = s.t;
+        out.metadata[obase + rank] = s.m;
+      }
+    }
+    for (int e = count + tid; e < k; e += K6_THREADS) {
+      out.indices[obase + e] = -1;
+      out.hybrid[obase + e] = NAN;
+      out.genre[obase + e] = NAN;
+      out.text[obase + e] = NAN;
+      out.metadata[obase + e] = NAN;
+    }
+    if (tid == 0) out.counts[orow] = count;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers used by api.cu
+// ---------------------------------------------------------------------------------------------
+int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
+              const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
+              const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st) {
+  const int max_cand = splits * kp;
+  const size_t smem = static_cast<size_t>(K5_WARPS) * max_cand * 40;
+  if (smem > 200 * 1024) {
+    tvbf_set_error("rescore: splits*candidates = %d is too large", max_cand);
+    return TVBF_ERR_INVALID;
+  }
+  TVBF_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+  const int grid = (n_rows + K5_WARPS - 1) / K5_WARPS;
+  rescore_kernel<<<grid, K5_WARPS * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, kp,
+                                                    row_begin, n_rows, out, flagged_rows, max_cand);
+  TVBF_LAUNCH_OK("rescore_kernel");
+  return TVBF_OK;
+}
+
+int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
+              int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
+              const tvbf_topk_out& out, cudaStream_t st) {
+  if (sp.k > K6_MAXK) {
+    tvbf_set_error("exact rows: k=%d exceeds %d", sp.k, K6_MAXK);
+    return TVBF_ERR_INVALID;
+  }
+  FeatureScorer sc{sp};
+  SelectParams sel{sp.f.n_shows, sp.k, sp.exclude_self, sp.min_similarity};
+  exact_rows_kernel<FeatureScorer><<<grid, K6_THREADS, 0, st>>>(
+      sc, sel, rows, n_listed, count_ptr, row_begin, rows_are_local, key_scratch, out);
+  TVBF_LAUNCH_OK("exact_rows_kernel");
+  return TVBF_OK;
+}
+
+int k6_launch_matrix(const double* h, const double* g, const double* t, const double* m, int n,
+                     int k, int exclude_self, double min_similarity, const int* rows, int n_listed,
+                     unsigned long long* key_scratch, int grid, const tvbf_topk_out& out,
+                     cudaStream_t st) {
+  if (k > K6_MAXK) {
+    tvbf_set_error("matrix rows: k=%d exceeds %d", k, K6_MAXK);
+    return TVBF_ERR_INVALID;
+  }
+  MatrixScorer sc{h, g, t, m, n};
+  SelectParams sel{n, k, exclude_self, min_similarity};
+  exact_rows_kernel<MatrixScorer><<<grid, K6_THREADS, 0, st>>>(sc, sel, rows, n_listed, nullptr, 0,
+                                                               0, key_scratch, out);
+  TVBF_LAUNCH_OK("exact_rows_kernel<matrix>");
+  return TVBF_OK;
+}
+
+}  // namespace tvbf

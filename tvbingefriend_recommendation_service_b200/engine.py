@@ -1,0 +1,497 @@
+"""Host side of the B200 hybrid-similarity -> top-K path.
+
+PyTorch is plumbing here: it owns device memory, streams and (for several GPUs)
+``torch.distributed``; all arithmetic is in ``libtvbf.so`` (hand-written sm_100a CUDA) reached
+through the C ABI of ``include/tvbf.h``.  There is no CPU fallback.
+
+Pipeline for one catalogue (reference: scripts/populate_database.py:125-218):
+
+    stage()   host: classify the five feature matrices, convert to the transfer layout, pin
+    upload()  H2D + K0 prep kernels: fp64 row normalisation, fp16 operand, genre bitmasks, ids
+    top_k()   K1 tcgen05 candidate pass -> K5 fp64 rescore + certificate -> K6 exact repair
+    to_host() D2H of the [rows, k] table
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from ._lib import Features, Params, TopKOut, check
+
+TEXT_SCALE_LOG2 = 8          # operand text columns hold x * 2^8 (keeps tiny tf-idf values normal in fp16)
+_DTYPES = {"fp16": (_lib.TEXT_FP16, torch.float16), "bf16": (_lib.TEXT_BF16, torch.bfloat16)}
+
+
+def _is_binary(a: np.ndarray) -> bool:
+    if a.dtype == np.bool_:
+        return True
+    return bool(np.all((a == 0) | (a == 1)))
+
+
+def _is_one_hot(a: np.ndarray) -> bool:
+    """values in {0,1}, at most one 1 per row, narrow enough for a byte id."""
+    if a.ndim != 2 or a.shape[1] > 254 or a.shape[1] == 0:
+        return False
+    if not _is_binary(a):
+        return False
+    return bool((np.count_nonzero(a, axis=1) <= 1).all())
+
+
+def _pin(t: torch.Tensor, pin: bool) -> torch.Tensor:
+    return t.pin_memory() if pin and torch.cuda.is_available() else t
+
+
+@dataclass
+class StagedCatalogue:
+    """Host-side transfer buffers (pinned when a GPU is present) + how each group is scored."""
+
+    n_shows: int
+    vocab: int
+    metadata_mode: str                      # "mean3" | "hstack"
+    text_indptr: torch.Tensor               # int64 [N+1]
+    text_indices: torch.Tensor              # int32 [nnz]
+    text_values: torch.Tensor               # float64 [nnz]
+    genre_packed: bool
+    genre: torch.Tensor                     # uint8 [N,G] (packed) or float64 [N,G] (folded)
+    meta_packed: bool
+    meta: list                              # 3 x uint8 one-hot (packed) or float64 groups (folded)
+
+    def h2d_bytes(self) -> int:
+        ts = [self.text_indptr, self.text_indices, self.text_values, self.genre, *self.meta]
+        return int(sum(t.numel() * t.element_size() for t in ts))
+
+
+def stage(features: dict, metadata_mode: str = "mean3", pin: bool = True) -> StagedCatalogue:
+    """Classify and convert the reference's feature dict (keys of compute_all_similarities,
+    ml/similarity_computer.py:132-155) into transfer buffers.  Pure host code."""
+    if metadata_mode not in ("mean3", "hstack"):
+        raise ValueError(f"metadata_mode must be 'mean3' or 'hstack', got {metadata_mode!r}")
+    genre = np.asarray(features["genre_features"])
+    text = features["text_features"]
+    plat = np.asarray(features["platform_features"])
+    typ = np.asarray(features["type_features"])
+    lang = np.asarray(features["language_features"])
+    n = int(genre.shape[0])
+    text = sp.csr_matrix(text, dtype=np.float64) if not sp.issparse(text) or text.format != "csr" \
+        or text.dtype != np.float64 else text
+    if not text.has_canonical_format:
+        text = text.copy()
+        text.sum_duplicates()
+        text.sort_indices()
+    for name, a in (("text", text), ("platform", plat), ("type", typ), ("language", lang)):
+        if a.shape[0] != n:
+            raise ValueError(f"{name}_features has {a.shape[0]} rows, genre_features has {n}")
+    genre_packed = genre.ndim == 2 and 1 <= genre.shape[1] <= 64 and _is_binary(genre)
+    meta_packed = all(_is_one_hot(a) for a in (plat, typ, lang))
+    if genre_packed:
+        g_t = torch.from_numpy(np.ascontiguousarray(genre != 0).astype(np.uint8))
+    else:
+        g_t = torch.from_numpy(np.ascontiguousarray(genre, dtype=np.float64))
+    if meta_packed:
+        meta = [torch.from_numpy(np.ascontiguousarray(a != 0).astype(np.uint8)) for a in (plat, typ, lang)]
+    elif metadata_mode == "mean3":
+        meta = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)) for a in (plat, typ, lang)]
+    else:  # similarity_computer.py:84 -- one cosine over the concatenation
+        meta = [torch.from_numpy(np.ascontiguousarray(np.hstack([plat, typ, lang]), dtype=np.float64))]
+    return StagedCatalogue(
+        n_shows=n, vocab=int(text.shape[1]), metadata_mode=metadata_mode,
+        text_indptr=_pin(torch.from_numpy(text.indptr.astype(np.int64)), pin),
+        text_indices=_pin(torch.from_numpy(text.indices.astype(np.int32)), pin),
+        text_values=_pin(torch.from_numpy(np.ascontiguousarray(text.data, dtype=np.float64)), pin),
+        genre_packed=genre_packed, genre=_pin(g_t, pin),
+        meta_packed=meta_packed, meta=[_pin(m, pin) for m in meta])
+
+
+@dataclass
+class DeviceCatalogue:
+    """Prepared, device-resident features (``tvbf_features``) and the tensors that back it."""
+
+    c: Features
+    n_shows: int
+    folded: bool
+    weights_baked: tuple | None            # folded groups bake sqrt(w/w_text) into the operand
+    keep: list = field(default_factory=list)
+
+
+@dataclass
+class TopK:
+    """Columnar top-K table of source rows [row_begin, row_begin + R) -- the record stream of
+    scripts/populate_database.py:211-217."""
+
+    indices: np.ndarray      # int32 [R, k], -1 padded (column = position in show_ids)
+    counts: np.ndarray       # int32 [R]
+    hybrid: np.ndarray       # float64 [R, k] similarity_score
+    genre: np.ndarray        # float64 [R, k]
+    text: np.ndarray         # float64 [R, k]
+    metadata: np.ndarray     # float64 [R, k]
+    row_begin: int = 0
+    flagged_rows: int = 0    # rows the certificate sent to the exact kernel
+    rescored_pairs: int = 0
+
+    @property
+    def k(self) -> int:
+        return int(self.indices.shape[1])
+
+    def to_dict(self, show_ids, id_key: str = "similar_show_id") -> dict:
+        """``all_similarities`` exactly as the hot loop builds it (populate_database.py:208-221):
+        shows without a qualifying neighbour are omitted."""
+        ids = list(show_ids)
+        out = {}
+        idx, cnt = self.indices, self.counts
+        for r in range(idx.shape[0]):
+            c = int(cnt[r])
+            if c == 0:
+                continue
+            out[ids[self.row_begin + r]] = [
+                {id_key: ids[int(idx[r, e])],
+                 "similarity_score": float(self.hybrid[r, e]),
+                 "genre_score": float(self.genre[r, e]),
+                 "text_score": float(self.text[r, e]),
+                 "metadata_score": float(self.metadata[r, e])}
+                for e in range(c)]
+        return out
+
+    def records(self, show_ids) -> dict:
+        """Flat columnar records (one per kept pair) for a bulk sink
+        (repos/similarity_repository.py:72-108 row shape) without building N*k dicts."""
+        ids = np.asarray(list(show_ids))
+        mask = np.arange(self.k)[None, :] < self.counts[:, None]
+        rows = np.nonzero(mask)[0]
+        return {"show_id": ids[self.row_begin + rows],
+                "similar_show_id": ids[self.indices[mask]],
+                "similarity_score": self.hybrid[mask], "genre_score": self.genre[mask],
+                "text_score": self.text[mask], "metadata_score": self.metadata[mask]}
+
+
+class HybridTopKEngine:
+    """One engine per process / GPU."""
+
+    def __init__(self, device: int | str | torch.device | None = None, text_dtype: str = "fp16"):
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device("cuda", 0)
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        with torch.cuda.device(self.device) if torch.cuda.is_available() else _NullCtx():
+            self.sm_count, self.cc_major, self.cc_minor = _lib.require_device()
+        if text_dtype not in _DTYPES:
+            raise ValueError(f"text_dtype must be one of {list(_DTYPES)}")
+        self.text_dtype = text_dtype
+        self.kernel_launches = 0      # kernels of libtvbf launched through this engine
+        self._ws: torch.Tensor | None = None
+
+    # ------------------------------------------------------------------------------------ utils
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------------------------ upload
+    def upload(self, st: StagedCatalogue, weights: tuple[float, float, float] = (0.4, 0.5, 0.1)) -> DeviceCatalogue:
+        """H2D copies + K0 prep kernels.  ``weights`` matter only when a group is folded into the
+        tensor-core operand (general float features)."""
+        lib, dev, stream = self.lib, self.device, None
+        gw, tw, mw = (float(w) for w in weights)
+        with torch.cuda.device(dev):
+            stream = self._stream()
+            n, v = st.n_shows, st.vocab
+            n_pad = (n + 255) // 256 * 256
+            folded_dims = (0 if st.genre_packed else st.genre.shape[1]) + \
+                (0 if st.meta_packed else sum(m.shape[1] for m in st.meta))
+            k_pad = max(64, (v + folded_dims + 63) // 64 * 64)
+            code, tdt = _DTYPES[self.text_dtype]
+            keep = []
+            indptr = st.text_indptr.to(dev, non_blocking=True)
+            indices = st.text_indices.to(dev, non_blocking=True)
+            raw = st.text_values.to(dev, non_blocking=True)
+            values = torch.empty_like(raw)
+            operand = torch.zeros((n_pad, k_pad), dtype=tdt, device=dev)
+            col_side = torch.zeros((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
+            meta_scale = torch.zeros((n_pad,), dtype=torch.float32, device=dev)
+            keep += [indptr, indices, values, operand, col_side, meta_scale]
+            check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), raw.data_ptr(), n, values.data_ptr(), stream),
+                  "tvbf_prep_csr_normalize")
+            scale = float(2 ** TEXT_SCALE_LOG2)
+            check(lib.tvbf_prep_csr_to_operand(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n,
+                                               operand.data_ptr(), k_pad, 0, scale, code, stream),
+                  "tvbf_prep_csr_to_operand")
+            self.kernel_launches += 2
+
+            f = Features()
+            f.n_shows, f.n_pad, f.k_pad, f.text_dtype = n, n_pad, k_pad, code
+            f.text_scale_log2, f.vocab = TEXT_SCALE_LOG2, v
+            f.operand = operand.data_ptr()
+            f.text_indptr, f.text_indices, f.text_values = indptr.data_ptr(), indices.data_ptr(), values.data_ptr()
+            f.col_side, f.meta_scale = col_side.data_ptr(), meta_scale.data_ptr()
+            f.meta_kind = _lib.META_MEAN3 if st.metadata_mode == "mean3" else _lib.META_HSTACK
+            col = v
+            folded = False
+
+            def fold(group: torch.Tensor, weight: float, what: str) -> int:
+                nonlocal col, folded
+                if tw <= 0.0 or weight < 0.0:
+                    raise _lib.TvbfError(
+                        f"{what} features are not binary/one-hot and must be folded into the tensor-core "
+                        "operand, which needs text_weight > 0 and non-negative weights; "
+                        "use force_exact=True for this weight combination")
+                ratio = weight / tw
+                if ratio > 6.0e4:
+                    raise _lib.TvbfError(f"{what}: weight ratio {ratio} overflows the fp16 operand")
+                g_raw = group.to(dev, non_blocking=True)
+                g_norm = torch.empty_like(g_raw)
+                check(lib.tvbf_prep_dense_normalize(g_raw.data_ptr(), n, g_raw.shape[1], g_norm.data_ptr(), stream),
+                      "tvbf_prep_dense_normalize")
+                check(lib.tvbf_prep_dense_to_operand(g_norm.data_ptr(), n, g_norm.shape[1], operand.data_ptr(),
+                                                     k_pad, col, scale * float(np.sqrt(ratio)), code, stream),
+                      "tvbf_prep_dense_to_operand")
+                self.kernel_launches += 2
+                keep.append(g_norm)
+                col += g_norm.shape[1]
+                folded = True
+                return g_norm.data_ptr()
+
+            if st.genre_packed:
+                g8 = st.genre.to(dev, non_blocking=True)
+                check(lib.tvbf_prep_genre_bits(g8.data_ptr(), n, g8.shape[1], col_side.data_ptr(), stream),
+                      "tvbf_prep_genre_bits")
+                self.kernel_launches += 1
+                keep.append(g8)
+                f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(g8.shape[1])
+            else:
+                f.genre_mode, f.genre_dim = _lib.GROUP_FOLDED, int(st.genre.shape[1])
+                f.genre_dense = fold(st.genre, gw, "genre")
+            if st.meta_packed:
+                m8 = [m.to(dev, non_blocking=True) for m in st.meta]
+                check(lib.tvbf_prep_meta_ids(m8[0].data_ptr(), m8[0].shape[1], m8[1].data_ptr(), m8[1].shape[1],
+                                             m8[2].data_ptr(), m8[2].shape[1], n, n_pad, f.meta_kind,
+                                             col_side.data_ptr(), meta_scale.data_ptr(), stream),
+                      "tvbf_prep_meta_ids")
+                self.kernel_launches += 1
+                keep += m8
+                f.meta_mode = _lib.GROUP_PACKED
+            else:
+                f.meta_mode = _lib.GROUP_FOLDED
+                f.meta_groups = len(st.meta)
+                per_group_w = mw / 3.0 if st.metadata_mode == "mean3" else mw
+                for gi, m in enumerate(st.meta):
+                    f.meta_dims[gi] = int(m.shape[1])
+                    f.meta_dense[gi] = fold(m, per_group_w, "metadata")
+            keep.append(raw)
+        return DeviceCatalogue(c=f, n_shows=n, folded=folded,
+                               weights_baked=(gw, tw, mw) if folded else None, keep=keep)
+
+    # ------------------------------------------------------------------------------------ top-k
+    def top_k_device(self, cat: DeviceCatalogue, weights=(0.4, 0.5, 0.1), k: int = 20,
+                     min_similarity: float = 0.1, exclude_self: bool = True, row_begin: int = 0,
+                     row_end: int | None = None, splits: int = 0, candidates: int = 0,
+                     force_exact: bool = False, skip_fallback: bool = False) -> dict:
+        """Launch the K1 -> K5 -> K6 sequence on the current stream; returns device tensors."""
+        gw, tw, mw = (float(w) for w in weights)
+        if cat.folded and cat.weights_baked != (gw, tw, mw) and not force_exact:
+            raise _lib.TvbfError("this catalogue was uploaded with folded (non-binary) groups for weights "
+                                 f"{cat.weights_baked}; upload again for weights {(gw, tw, mw)}")
+        row_end = cat.n_shows if row_end is None else int(row_end)
+        rows = row_end - row_begin
+        p = Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=float(min_similarity),
+                   k=int(k), exclude_self=int(bool(exclude_self)), row_begin=int(row_begin), row_end=row_end,
+                   splits=int(splits), candidates=int(candidates), force_exact=int(bool(force_exact)),
+                   skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0)
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(cat.c), C.byref(p))
+            if nbytes == 0:
+                check(-1, "tvbf_topk_workspace_bytes")
+            ws = self._workspace(nbytes)
+            dev = self.device
+            t = {
+                "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
+                "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
+                "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
+            }
+            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
+            check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(out), ws.data_ptr(),
+                                            ws.numel(), self._stream()), "tvbf_hybrid_topk")
+            self.kernel_launches += 2 if force_exact else (2 if skip_fallback else 3)
+        t["row_begin"] = row_begin
+        return t
+
+    @staticmethod
+    def to_host(t: dict) -> TopK:
+        """D2H of a result table (synchronises)."""
+        host = {n: t[n].cpu().numpy() for n in ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")}
+        return TopK(indices=host["indices"], counts=host["counts"], hybrid=host["hybrid"], genre=host["genre"],
+                    text=host["text"], metadata=host["metadata"], row_begin=int(t.get("row_begin", 0)),
+                    flagged_rows=int(host["stats"][0]), rescored_pairs=int(host["stats"][1]))
+
+    def compute_top_k(self, features: dict, weights=(0.4, 0.5, 0.1), k: int = 20, min_similarity: float = 0.1,
+                      metadata_mode: str = "mean3", exclude_self: bool = True, **kw) -> TopK:
+        """features dict -> TopK for all rows on this GPU."""
+        cat = self.upload(stage(features, metadata_mode), weights)
+        return self.to_host(self.top_k_device(cat, weights, k, min_similarity, exclude_self, **kw))
+
+    # ------------------------------------------------------------------------------------ exact
+    def exact_rows(self, cat: DeviceCatalogue, rows, weights=(0.4, 0.5, 0.1), k: int = 10,
+                   min_similarity: float = 0.0, exclude_self: bool = True) -> TopK:
+        """Exact fp64 top-k of explicit source rows (the single-show query of
+        services/content_based_service.py:161-236, any n up to 1024)."""
+        rows_np = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        if rows_np.size == 0:
+            z = np.zeros((0, k))
+            return TopK(np.zeros((0, k), np.int32), np.zeros(0, np.int32), z, z.copy(), z.copy(), z.copy())
+        gw, tw, mw = (float(w) for w in weights)
+        p = Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=float(min_similarity),
+                   k=int(k), exclude_self=int(bool(exclude_self)), row_begin=0, row_end=cat.n_shows)
+        with torch.cuda.device(self.device):
+            dev = self.device
+            r = rows_np.shape[0]
+            rows_d = torch.from_numpy(rows_np).to(dev)
+            t = {
+                "indices": torch.empty((r, k), dtype=torch.int32, device=dev),
+                "counts": torch.empty((r,), dtype=torch.int32, device=dev),
+                "hybrid": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "genre": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "text": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "metadata": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
+            }
+            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
+            nbytes = self.lib.tvbf_exact_workspace_bytes(C.byref(cat.c), r)
+            ws = self._workspace(nbytes)
+            check(self.lib.tvbf_exact_rows(C.byref(cat.c), C.byref(p), rows_d.data_ptr(), r, C.byref(out),
+                                           ws.data_ptr(), ws.numel(), self._stream()), "tvbf_exact_rows")
+            self.kernel_launches += 1
+        return self.to_host(t)
+
+    def matrix_rows_topk(self, hybrid: torch.Tensor, genre: torch.Tensor, text: torch.Tensor,
+                         metadata: torch.Tensor, rows, k: int = 10, min_similarity: float = 0.0) -> TopK:
+        """Top-k over rows of precomputed N x N device matrices (variant C,
+        content_based_service.py:206-234)."""
+        rows_np = np.ascontiguousarray(np.asarray(rows, dtype=np.int32))
+        n = int(hybrid.shape[0])
+        r = rows_np.shape[0]
+        p = Params(genre_weight=0.0, text_weight=0.0, metadata_weight=0.0, min_similarity=float(min_similarity),
+                   k=int(k), exclude_self=1, row_begin=0, row_end=n)
+        with torch.cuda.device(self.device):
+            dev = self.device
+            rows_d = torch.from_numpy(rows_np).to(dev)
+            t = {
+                "indices": torch.empty((r, k), dtype=torch.int32, device=dev),
+                "counts": torch.empty((r,), dtype=torch.int32, device=dev),
+                "hybrid": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "genre": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "text": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "metadata": torch.empty((r, k), dtype=torch.float64, device=dev),
+                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
+            }
+            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
+            nbytes = min(2 * self.sm_count, r) * n * 8 + 256
+            ws = self._workspace(nbytes)
+            check(self.lib.tvbf_matrix_rows_topk(hybrid.data_ptr(), genre.data_ptr(), text.data_ptr(),
+                                                 metadata.data_ptr(), n, C.byref(p), rows_d.data_ptr(), r,
+                                                 C.byref(out), ws.data_ptr(), ws.numel(), self._stream()),
+                  "tvbf_matrix_rows_topk")
+            self.kernel_launches += 1
+        return self.to_host(t)
+
+    # ------------------------------------------------------------------------------------ matrices
+    def cosine_matrix(self, x) -> torch.Tensor:
+        """cosine_similarity(X) as an N x N float64 device tensor (similarity_computer.py:41,58,86);
+        ``x`` is a dense array or a scipy sparse matrix."""
+        with torch.cuda.device(self.device):
+            dev, stream = self.device, self._stream()
+            if sp.issparse(x):
+                m = sp.csr_matrix(x, dtype=np.float64)
+                if not m.has_canonical_format:
+                    m = m.copy()
+                    m.sum_duplicates()
+                    m.sort_indices()
+                n, d = m.shape
+                indptr = torch.from_numpy(m.indptr.astype(np.int64)).to(dev)
+                indices = torch.from_numpy(m.indices.astype(np.int32)).to(dev)
+                raw = torch.from_numpy(np.ascontiguousarray(m.data, dtype=np.float64)).to(dev)
+                vals = torch.empty_like(raw)
+                check(self.lib.tvbf_prep_csr_normalize(indptr.data_ptr(), raw.data_ptr(), n, vals.data_ptr(), stream),
+                      "tvbf_prep_csr_normalize")
+                xn = torch.zeros((n, d), dtype=torch.float64, device=dev)
+                check(self.lib.tvbf_csr_to_dense_f64(indptr.data_ptr(), indices.data_ptr(), vals.data_ptr(), n, d,
+                                                     xn.data_ptr(), stream), "tvbf_csr_to_dense_f64")
+                self.kernel_launches += 2
+            else:
+                a = np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+                if a.ndim != 2:
+                    raise ValueError("feature matrix must be 2-D")
+                n, d = a.shape
+                raw = torch.from_numpy(a).to(dev)
+                xn = torch.empty_like(raw)
+                check(self.lib.tvbf_prep_dense_normalize(raw.data_ptr(), n, d, xn.data_ptr(), stream),
+                      "tvbf_prep_dense_normalize")
+                self.kernel_launches += 1
+            out = torch.empty((n, n), dtype=torch.float64, device=dev)
+            check(self.lib.tvbf_cosine_matrix_f64(xn.data_ptr(), n, d, out.data_ptr(), stream),
+                  "tvbf_cosine_matrix_f64")
+            self.kernel_launches += 1
+        return out
+
+    def hybrid_combine(self, g: torch.Tensor, t: torch.Tensor, m: torch.Tensor, wg: float, wt: float,
+                       wm: float) -> torch.Tensor:
+        """wg*g + wt*t + wm*m elementwise on the device (similarity_computer.py:122-124)."""
+        with torch.cuda.device(self.device):
+            out = torch.empty_like(g)
+            check(self.lib.tvbf_hybrid_combine_f64(g.data_ptr(), t.data_ptr(), m.data_ptr(), float(wg), float(wt),
+                                                   float(wm), g.numel(), out.data_ptr(), self._stream()),
+                  "tvbf_hybrid_combine_f64")
+            self.kernel_launches += 1
+        return out
+
+    def matrix_stats(self, mat: torch.Tensor) -> dict:
+        """Upper-triangle statistics (similarity_computer.py:171-190)."""
+        n = int(mat.shape[0])
+        with torch.cuda.device(self.device):
+            ws = self._workspace(self.lib.tvbf_matrix_stats_workspace_bytes())
+            out5 = (C.c_double * 5)()
+            check(self.lib.tvbf_matrix_stats_f64(mat.data_ptr(), n, out5, ws.data_ptr(), ws.numel(), self._stream()),
+                  "tvbf_matrix_stats_f64")
+            self.kernel_launches += 4 + 2 * 17
+        return {"mean": float(out5[0]), "std": float(out5[1]), "min": float(out5[2]),
+                "max": float(out5[3]), "median": float(out5[4])}
+
+    def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int) -> torch.Tensor:
+        """Raw fp32 accumulators of one 128 x 256 tensor-core tile (diagnostics / tests)."""
+        with torch.cuda.device(self.device):
+            out = torch.zeros((128, 256), dtype=torch.float32, device=self.device)
+            check(self.lib.tvbf_debug_gemm_tile(C.byref(cat.c), int(row0), int(col0), out.data_ptr(), self._stream()),
+                  "tvbf_debug_gemm_tile")
+            self.kernel_launches += 1
+        return out
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_default_engine: HybridTopKEngine | None = None
+
+
+def default_engine() -> HybridTopKEngine:
+    """Process-wide engine on the current CUDA device (raises without a B200)."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = HybridTopKEngine()
+    return _default_engine

@@ -1,0 +1,64 @@
+"""Several GPUs of one box: features replicated, source rows sharded in 128-row tiles, result
+tables gathered.  Two drivers over the same shard arithmetic:
+
+* ``compute_top_k_distributed`` -- one process per GPU under ``torch.distributed`` (NCCL over
+  NVLink); the gather is ``sharding.gather_tables``.  This is what ``bench.py --gpus N`` runs.
+* ``compute_top_k_multi_gpu``   -- a single process driving ``device_ids`` (kernels are launched
+  asynchronously on every device, tables are read back per shard); convenience for the drop-in
+  API's ``device_ids`` argument.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import HybridTopKEngine, TopK, stage
+from .sharding import gather_tables, row_shard
+
+
+def compute_top_k_distributed(features: dict, weights=(0.4, 0.5, 0.1), k: int = 20,
+                              min_similarity: float = 0.1, metadata_mode: str = "mean3",
+                              exclude_self: bool = True, engine: HybridTopKEngine | None = None,
+                              group=None, staged=None, **kw) -> TopK:
+    """Every rank calls this with the same features; every rank returns the full table."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    eng = engine or HybridTopKEngine(torch.cuda.current_device())
+    st = staged or stage(features, metadata_mode)
+    cat = eng.upload(st, weights)
+    b, e = row_shard(st.n_shows, world, rank)
+    if e > b:
+        local = eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e, **kw)
+    else:
+        dev = eng.device
+        local = {"indices": torch.empty((0, k), dtype=torch.int32, device=dev),
+                 "counts": torch.empty((0,), dtype=torch.int32, device=dev),
+                 "stats": torch.zeros((8,), dtype=torch.int32, device=dev)}
+        for name in ("hybrid", "genre", "text", "metadata"):
+            local[name] = torch.empty((0, k), dtype=torch.float64, device=dev)
+    full = gather_tables(local, st.n_shows, k, group)
+    full["row_begin"] = 0
+    return eng.to_host(full)
+
+
+def compute_top_k_multi_gpu(features: dict, weights=(0.4, 0.5, 0.1), k: int = 20,
+                            min_similarity: float = 0.1, metadata_mode: str = "mean3",
+                            exclude_self: bool = True, device_ids=(0,), **kw) -> TopK:
+    st = stage(features, metadata_mode)
+    world = len(device_ids)
+    pending = []
+    for rank, dev in enumerate(device_ids):
+        b, e = row_shard(st.n_shows, world, rank)
+        if e <= b:
+            continue
+        eng = HybridTopKEngine(dev)
+        cat = eng.upload(st, weights)
+        pending.append((eng, cat, eng.top_k_device(cat, weights, k, min_similarity, exclude_self,
+                                                   row_begin=b, row_end=e, **kw)))
+    parts = [eng.to_host(t) for eng, _cat, t in pending]
+    cat_ = lambda name: np.concatenate([getattr(p, name) for p in parts], axis=0)  # noqa: E731
+    return TopK(indices=cat_("indices"), counts=cat_("counts"), hybrid=cat_("hybrid"), genre=cat_("genre"),
+                text=cat_("text"), metadata=cat_("metadata"), row_begin=0,
+                flagged_rows=sum(p.flagged_rows for p in parts),
+                rescored_pairs=sum(p.rescored_pairs for p in parts))
