@@ -94,6 +94,10 @@ typedef struct tvbf_params {
   int32_t force_exact;    /* 1: send every row through the exact fp64 row kernel              */
   int32_t skip_fallback;  /* 1: do not repair flagged rows (diagnostics only)                 */
   double text_rel_err;    /* 0 = default bound for text_dtype                                 */
+  int32_t phases;         /* 0 = all; else bitmask 1: K1 candidate pass, 2: K5 rescore+certify, */
+                          /* 4: K6 exact repair -- lets a caller time the kernels separately     */
+                          /* (same workspace must be passed to every phase call)                 */
+  int32_t reserved;
 } tvbf_params;
 
 /* Result table of the shard rows [row_begin, row_end): the a9 record stream of

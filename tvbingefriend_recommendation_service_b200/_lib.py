@@ -46,6 +46,7 @@ class Params(C.Structure):
         ("splits", c_int32), ("candidates", c_int32), ("force_exact", c_int32),
         ("skip_fallback", c_int32),
         ("text_rel_err", c_double),
+        ("phases", c_int32), ("reserved", c_int32),
     ]
 
 

@@ -189,7 +189,8 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + pl.off_keys);
-  TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
+  const int phases = p->phases == 0 ? 7 : p->phases;
+  if (phases & 1) TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
   const tvbf::ScoreParams sp = score_params(f, p);
 
   const bool use_k1 = !p->force_exact && pl.entries != 0;
@@ -258,12 +259,16 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
     kp.theta_init = th;
   }
-  rc = tvbf::k1_launch(f, kp, pl.entries, pl.grid, st);
-  if (rc != TVBF_OK) return rc;
-  rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.splits, pl.kp, p->row_begin,
-                       pl.rows, *out, flagged, st);
-  if (rc != TVBF_OK) return rc;
-  if (!p->skip_fallback) {
+  if (phases & 1) {
+    rc = tvbf::k1_launch(f, kp, pl.entries, pl.grid, st);
+    if (rc != TVBF_OK) return rc;
+  }
+  if (phases & 2) {
+    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.splits, pl.kp, p->row_begin,
+                         pl.rows, *out, flagged, st);
+    if (rc != TVBF_OK) return rc;
+  }
+  if ((phases & 4) && !p->skip_fallback) {
     rc = tvbf::k6_launch(sp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, pl.k6_grid, *out, st);
     if (rc != TVBF_OK) return rc;
   }

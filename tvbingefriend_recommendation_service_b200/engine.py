@@ -197,10 +197,26 @@ class HybridTopKEngine:
         return self._ws
 
     # ------------------------------------------------------------------------------------ upload
+    def h2d(self, st: StagedCatalogue) -> dict:
+        """Host -> device copies of the staged buffers on the current stream (no kernels)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            return {"st": st,
+                    "indptr": st.text_indptr.to(dev, non_blocking=True),
+                    "indices": st.text_indices.to(dev, non_blocking=True),
+                    "values": st.text_values.to(dev, non_blocking=True),
+                    "genre": st.genre.to(dev, non_blocking=True),
+                    "meta": [m.to(dev, non_blocking=True) for m in st.meta]}
+
     def upload(self, st: StagedCatalogue, weights: tuple[float, float, float] = (0.4, 0.5, 0.1)) -> DeviceCatalogue:
-        """H2D copies + K0 prep kernels.  ``weights`` matter only when a group is folded into the
-        tensor-core operand (general float features)."""
+        """H2D copies + K0 prep kernels."""
+        return self.prepare(self.h2d(st), weights)
+
+    def prepare(self, raw: dict, weights: tuple[float, float, float] = (0.4, 0.5, 0.1)) -> DeviceCatalogue:
+        """K0 prep kernels on device-resident raw features.  ``weights`` matter only when a group
+        is folded into the tensor-core operand (general float features)."""
         lib, dev, stream = self.lib, self.device, None
+        st: StagedCatalogue = raw["st"]
         gw, tw, mw = (float(w) for w in weights)
         with torch.cuda.device(dev):
             stream = self._stream()
@@ -211,15 +227,13 @@ class HybridTopKEngine:
             k_pad = max(64, (v + folded_dims + 63) // 64 * 64)
             code, tdt = _DTYPES[self.text_dtype]
             keep = []
-            indptr = st.text_indptr.to(dev, non_blocking=True)
-            indices = st.text_indices.to(dev, non_blocking=True)
-            raw = st.text_values.to(dev, non_blocking=True)
-            values = torch.empty_like(raw)
+            indptr, indices, rawv = raw["indptr"], raw["indices"], raw["values"]
+            values = torch.empty_like(rawv)
             operand = torch.zeros((n_pad, k_pad), dtype=tdt, device=dev)
             col_side = torch.zeros((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
             meta_scale = torch.zeros((n_pad,), dtype=torch.float32, device=dev)
             keep += [indptr, indices, values, operand, col_side, meta_scale]
-            check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), raw.data_ptr(), n, values.data_ptr(), stream),
+            check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), rawv.data_ptr(), n, values.data_ptr(), stream),
                   "tvbf_prep_csr_normalize")
             scale = float(2 ** TEXT_SCALE_LOG2)
             check(lib.tvbf_prep_csr_to_operand(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n,
@@ -237,7 +251,7 @@ class HybridTopKEngine:
             col = v
             folded = False
 
-            def fold(group: torch.Tensor, weight: float, what: str) -> int:
+            def fold(g_raw: torch.Tensor, weight: float, what: str) -> int:
                 nonlocal col, folded
                 if tw <= 0.0 or weight < 0.0:
                     raise _lib.TvbfError(
@@ -247,7 +261,6 @@ class HybridTopKEngine:
                 ratio = weight / tw
                 if ratio > 6.0e4:
                     raise _lib.TvbfError(f"{what}: weight ratio {ratio} overflows the fp16 operand")
-                g_raw = group.to(dev, non_blocking=True)
                 g_norm = torch.empty_like(g_raw)
                 check(lib.tvbf_prep_dense_normalize(g_raw.data_ptr(), n, g_raw.shape[1], g_norm.data_ptr(), stream),
                       "tvbf_prep_dense_normalize")
@@ -261,29 +274,27 @@ class HybridTopKEngine:
                 return g_norm.data_ptr()
 
             if st.genre_packed:
-                g8 = st.genre.to(dev, non_blocking=True)
+                g8 = raw["genre"]
                 check(lib.tvbf_prep_genre_bits(g8.data_ptr(), n, g8.shape[1], col_side.data_ptr(), stream),
                       "tvbf_prep_genre_bits")
                 self.kernel_launches += 1
-                keep.append(g8)
                 f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(g8.shape[1])
             else:
                 f.genre_mode, f.genre_dim = _lib.GROUP_FOLDED, int(st.genre.shape[1])
-                f.genre_dense = fold(st.genre, gw, "genre")
+                f.genre_dense = fold(raw["genre"], gw, "genre")
             if st.meta_packed:
-                m8 = [m.to(dev, non_blocking=True) for m in st.meta]
+                m8 = raw["meta"]
                 check(lib.tvbf_prep_meta_ids(m8[0].data_ptr(), m8[0].shape[1], m8[1].data_ptr(), m8[1].shape[1],
                                              m8[2].data_ptr(), m8[2].shape[1], n, n_pad, f.meta_kind,
                                              col_side.data_ptr(), meta_scale.data_ptr(), stream),
                       "tvbf_prep_meta_ids")
                 self.kernel_launches += 1
-                keep += m8
                 f.meta_mode = _lib.GROUP_PACKED
             else:
                 f.meta_mode = _lib.GROUP_FOLDED
                 f.meta_groups = len(st.meta)
                 per_group_w = mw / 3.0 if st.metadata_mode == "mean3" else mw
-                for gi, m in enumerate(st.meta):
+                for gi, m in enumerate(raw["meta"]):
                     f.meta_dims[gi] = int(m.shape[1])
                     f.meta_dense[gi] = fold(m, per_group_w, "metadata")
             keep.append(raw)
@@ -294,8 +305,11 @@ class HybridTopKEngine:
     def top_k_device(self, cat: DeviceCatalogue, weights=(0.4, 0.5, 0.1), k: int = 20,
                      min_similarity: float = 0.1, exclude_self: bool = True, row_begin: int = 0,
                      row_end: int | None = None, splits: int = 0, candidates: int = 0,
-                     force_exact: bool = False, skip_fallback: bool = False) -> dict:
-        """Launch the K1 -> K5 -> K6 sequence on the current stream; returns device tensors."""
+                     force_exact: bool = False, skip_fallback: bool = False, phases: int = 0,
+                     out: dict | None = None) -> dict:
+        """Launch the K1 -> K5 -> K6 sequence on the current stream; returns device tensors.
+        ``phases`` (bitmask 1|2|4) launches a subset so that a caller can bracket each kernel with
+        its own CUDA events; pass the dict returned by the first call as ``out`` to the others."""
         gw, tw, mw = (float(w) for w in weights)
         if cat.folded and cat.weights_baked != (gw, tw, mw) and not force_exact:
             raise _lib.TvbfError("this catalogue was uploaded with folded (non-binary) groups for weights "
@@ -305,14 +319,14 @@ class HybridTopKEngine:
         p = Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=float(min_similarity),
                    k=int(k), exclude_self=int(bool(exclude_self)), row_begin=int(row_begin), row_end=row_end,
                    splits=int(splits), candidates=int(candidates), force_exact=int(bool(force_exact)),
-                   skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0)
+                   skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0, phases=int(phases), reserved=0)
         with torch.cuda.device(self.device):
             nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(cat.c), C.byref(p))
             if nbytes == 0:
                 check(-1, "tvbf_topk_workspace_bytes")
             ws = self._workspace(nbytes)
             dev = self.device
-            t = {
+            t = out if out is not None else {
                 "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
                 "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
                 "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
@@ -321,10 +335,15 @@ class HybridTopKEngine:
                 "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
                 "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
             }
-            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
-            check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(out), ws.data_ptr(),
+            cout = TopKOut(**{name: t[name].data_ptr() for name in
+                              ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+            check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(cout), ws.data_ptr(),
                                             ws.numel(), self._stream()), "tvbf_hybrid_topk")
-            self.kernel_launches += 2 if force_exact else (2 if skip_fallback else 3)
+            ph = 7 if phases == 0 else phases
+            if force_exact:
+                self.kernel_launches += 2
+            else:
+                self.kernel_launches += bin(ph & (3 if skip_fallback else 7)).count("1")
         t["row_begin"] = row_begin
         return t
 

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 from .engine import HybridTopKEngine, TopK, stage
-from .sharding import gather_tables, row_shard
+from .sharding import empty_tables, gather_tables, row_shard
 
 
 def compute_top_k_distributed(features: dict, weights=(0.4, 0.5, 0.1), k: int = 20,
@@ -31,12 +31,7 @@ def compute_top_k_distributed(features: dict, weights=(0.4, 0.5, 0.1), k: int = 
     if e > b:
         local = eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e, **kw)
     else:
-        dev = eng.device
-        local = {"indices": torch.empty((0, k), dtype=torch.int32, device=dev),
-                 "counts": torch.empty((0,), dtype=torch.int32, device=dev),
-                 "stats": torch.zeros((8,), dtype=torch.int32, device=dev)}
-        for name in ("hybrid", "genre", "text", "metadata"):
-            local[name] = torch.empty((0, k), dtype=torch.float64, device=dev)
+        local = empty_tables(k, eng.device)
     full = gather_tables(local, st.n_shows, k, group)
     full["row_begin"] = 0
     return eng.to_host(full)

@@ -31,6 +31,16 @@ def max_shard_rows(n_shows: int, world_size: int) -> int:
                for r in range(world_size))
 
 
+def empty_tables(k: int, device) -> dict:
+    """Local tables of a rank that owns no rows."""
+    t = {"indices": torch.empty((0, k), dtype=torch.int32, device=device),
+         "counts": torch.empty((0,), dtype=torch.int32, device=device),
+         "stats": torch.zeros((8,), dtype=torch.int32, device=device)}
+    for name in ("hybrid", "genre", "text", "metadata"):
+        t[name] = torch.empty((0, k), dtype=torch.float64, device=device)
+    return t
+
+
 def gather_tables(local: dict, n_shows: int, k: int, group=None) -> dict:
     """All-gather the per-rank tables into full ``[n_shows, k]`` tensors (on every rank).
 
