@@ -165,6 +165,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--splits", type=int, default=0)
+    ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
     args = ap.parse_args()
 
     from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, make_config
@@ -213,13 +214,13 @@ def main() -> None:
         if re_ <= rb:
             return gather_tables(empty_tables(k, eng.device), n, k) if world > 1 else None
         if timing is None:
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits)
+            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, tuning=args.tuning)
         else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=1)
+            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=1, tuning=args.tuning)
             e1.record()
-            eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=6, out=t)
+            eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=6, out=t, tuning=args.tuning)
             timing.setdefault("k1", []).append((e0, e1))
         if world > 1:
             t = gather_tables(t, n, k)
@@ -264,7 +265,7 @@ def main() -> None:
         raw2 = eng.h2d(st)
         dc = eng.prepare(raw2, weights)
         if re_ > rb:
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits)
+            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, tuning=args.tuning)
         else:
             t = empty_tables(k, eng.device)
         if world > 1:

@@ -75,8 +75,8 @@ typedef struct tvbf_features {
   int32_t meta_dims[3];
   const double* meta_dense[3]; /* FOLDED: [N, dims[g]] L2-normalised fp64 rows                */
   const void* col_side;      /* [n_pad] 16-byte records {u64 genre bits, f32 1/sqrt(popc),    */
-                             /*  u32 ids = platform | type<<8 | language<<16 | 0xFF<<24}      */
-  const float* meta_scale;   /* [n_pad] MEAN3: 1/sqrt(3) ; HSTACK: 1/sqrt(#valid ids) or 0    */
+                             /*  u32 one-hot bits platform | type<<P | language<<(P+T)}       */
+  const float* meta_scale;   /* [n_pad] MEAN3: 1/sqrt(3) ; HSTACK: 1/sqrt(#categories) or 0   */
 } tvbf_features;
 
 /* Parameters of one top-K job: populate_database.py:85-91 (weights, top_n_per_show,
@@ -97,7 +97,11 @@ typedef struct tvbf_params {
   int32_t phases;         /* 0 = all; else bitmask 1: K1 candidate pass, 2: K5 rescore+certify, */
                           /* 4: K6 exact repair -- lets a caller time the kernels separately     */
                           /* (same workspace must be passed to every phase call)                 */
-  int32_t reserved;
+  int32_t tuning;         /* 0 = defaults. bits 0-3: tcgen05 cta_group (1 or 2; default 2);     */
+                          /* bits 4-11: producer pacing chunk in 64-wide k-blocks (default 8,   */
+                          /* 255 = off); bits 12-15: pacing slack in chunks (default 2);        */
+                          /* bits 16-19: smem ring stages; bits 20-29: L2 prefetch distance and */
+                          /* mode (experimental, default off); bit 30: non-cooperative launch   */
 } tvbf_params;
 
 /* Result table of the shard rows [row_begin, row_end): the a9 record stream of
@@ -138,7 +142,7 @@ int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim,
 /* genre multi-hot bytes [n_rows, dim<=64] -> col_side[].genre_bits / genre_rnorm. */
 int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,
                          void* stream);
-/* one-hot bytes of platform/type/language -> col_side[].meta_ids and meta_scale[]. Rows
+/* one-hot bytes of platform/type/language (P+T+L <= 32) -> col_side[].meta_bits and meta_scale[]. Rows
  * [n_rows, n_pad) are filled with "none". */
 int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* type, int32_t t_dim,
                        const uint8_t* language, int32_t l_dim, int32_t n_rows, int32_t n_pad,
@@ -187,6 +191,9 @@ int tvbf_matrix_stats_f64(const double* mat, int32_t n, double* out5_host, void*
  * 128 x 256 tile (fp32), used by the tests to validate descriptors and the error bound. */
 int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
                          void* stream);
+/* same through the cta_group::2 path: a 256 x 256 tile computed by a CTA pair. */
+int tvbf_debug_gemm_tile_pair(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,11 +57,13 @@ def test_prep_operand_and_packing(engine, cat2k):
     pc = cat2k.genre_features.sum(axis=1)
     want = np.where(pc > 0, 1.0 / np.sqrt(np.maximum(pc, 1)), 0.0).astype(np.float32)
     assert np.allclose(rnorm, want, rtol=1e-6)
-    ids = (low >> np.uint64(32)).astype(np.uint32)
-    p = np.where(cat2k.platform_features.any(1), cat2k.platform_features.argmax(1), 255)
-    t = np.where(cat2k.type_features.any(1), cat2k.type_features.argmax(1), 255)
-    l = np.where(cat2k.language_features.any(1), cat2k.language_features.argmax(1), 255)
-    assert np.array_equal(ids, (p | (t << 8) | (l << 16) | (255 << 24)).astype(np.uint32))
+    mbits = (low >> np.uint64(32)).astype(np.uint32)
+    P, T = cat2k.platform_features.shape[1], cat2k.type_features.shape[1]
+    want_bits = np.zeros(2000, dtype=np.uint32)
+    for off, m in ((0, cat2k.platform_features), (P, cat2k.type_features), (P + T, cat2k.language_features)):
+        for c in range(m.shape[1]):
+            want_bits |= ((m[:, c] != 0).astype(np.uint32) << np.uint32(off + c))
+    assert np.array_equal(mbits, want_bits)
     assert np.allclose(meta_scale.cpu().numpy()[:2000], 1 / np.sqrt(3), rtol=1e-6)
 
 
@@ -76,6 +78,19 @@ def test_tensor_core_tile_matches_fp32_reference(engine, cat2k, row0, col0):
     a = operand[row0:row0 + 128].float().cpu()
     b = operand[col0:col0 + 256].float().cpu()
     ref = a @ b.T
+    err = (tile - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("row0,col0", [(0, 0), (256, 512), (1792, 1792)])
+def test_cta_pair_tile_matches_fp32_reference(engine, cat2k, row0, col0):
+    """cta_group::2: M = 256 spans two CTAs' TMEM, each CTA stages half of the B tile."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+
+    dc = engine.upload(stage(cat2k.features()))
+    operand = dc.keep[3]
+    tile = engine.debug_gemm_tile(dc, row0, col0, pair=True).cpu()
+    ref = operand[row0:row0 + 256].float().cpu() @ operand[col0:col0 + 256].float().cpu().T
     err = (tile - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item() + 1e-3, err
 
@@ -130,6 +145,14 @@ def test_column_splits_do_not_change_the_table(engine, cat2k, splits):
     a = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, splits=splits)
     b = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, force_exact=True)
     assert np.array_equal(a.indices, b.indices)
+
+
+@pytest.mark.parametrize("tuning", [0x1, 0x2, 0x1 | (255 << 4), 0x2 | (255 << 4), 0x2 | (1 << 4) | (1 << 12)])
+def test_kernel_variants_give_the_same_table(engine, cat2k, tuning):
+    """cta_group 1 / 2, producer pacing on / off / tight: same certified result."""
+    a = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, tuning=tuning, splits=3)
+    b = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, force_exact=True)
+    assert np.array_equal(a.indices, b.indices) and np.array_equal(a.counts, b.counts)
 
 
 @pytest.mark.parametrize("name", ["populate_n300", "populate_random_float_n48"])

@@ -46,7 +46,7 @@ class Params(C.Structure):
         ("splits", c_int32), ("candidates", c_int32), ("force_exact", c_int32),
         ("skip_fallback", c_int32),
         ("text_rel_err", c_double),
-        ("phases", c_int32), ("reserved", c_int32),
+        ("phases", c_int32), ("tuning", c_int32),
     ]
 
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "tvbf_matrix_stats_f64": (C.c_int, [c_void_p, c_int32, C.POINTER(c_double), c_void_p, c_size_t,
                                         c_void_p]),
     "tvbf_debug_gemm_tile": (C.c_int, [C.POINTER(Features), c_int32, c_int32, c_void_p, c_void_p]),
+    "tvbf_debug_gemm_tile_pair": (C.c_int, [C.POINTER(Features), c_int32, c_int32, c_void_p, c_void_p]),
 }
 
 _lib = None

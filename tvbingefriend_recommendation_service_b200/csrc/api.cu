@@ -38,7 +38,8 @@ int sm_count_cached(int* out) {
 }
 
 struct Plan {
-  int rows, rb_count, col_tiles, splits, rb_per_group, grid, entries, kp, k6_grid;
+  int rows, cg, sb_count, col_tiles, splits, sb_per_group, grid, entries, kp, k6_grid;
+  int tiles_per_split, sync_kb, sync_slack, stages, prefetch_kb, prefetch_mode;
   size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_keys, off_count, total;
 };
 
@@ -81,26 +82,45 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   int rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
   pl->rows = p->row_end - p->row_begin;
-  pl->rb_count = (pl->rows + 127) / 128;
+  // tuning: bits 0-3 cta_group (0 = 2), bits 4-11 pacing chunk in k-blocks (0 = 8, 255 = off),
+  // bits 12-15 pacing slack in chunks (0 = 2)
+  const int tune = p->tuning;
+  pl->cg = (tune & 0xF) == 1 ? 1 : 2;
+  pl->sync_kb = ((tune >> 4) & 0xFF) == 0 ? 8 : (((tune >> 4) & 0xFF) == 255 ? 0 : ((tune >> 4) & 0xFF));
+  pl->sync_slack = ((tune >> 12) & 0xF) == 0 ? 2 : ((tune >> 12) & 0xF);
+  // bits 16-19 ring stages (0 = all), bits 20-27 L2 prefetch distance in k-blocks (0 = off),
+  // bits 28-29 prefetch mode (0 -> 2)
+  const int max_stages = pl->cg == 2 ? 6 : 4;
+  pl->stages = ((tune >> 16) & 0xF) == 0 ? max_stages : ((tune >> 16) & 0xF);
+  if (pl->stages > max_stages) pl->stages = max_stages;
+  if (pl->stages < 2) pl->stages = 2;
+  pl->prefetch_kb = (tune >> 20) & 0xFF;
+  pl->prefetch_mode = ((tune >> 28) & 0x3) == 0 ? 2 : ((tune >> 28) & 0x3);
+  const int sb_rows = 128 * pl->cg;
+  pl->sb_count = (pl->rows + sb_rows - 1) / sb_rows;
   pl->col_tiles = (f->n_shows + 255) / 256;
   pl->entries = tvbf::k1_entries_per_lane(p->k);
   pl->kp = 0;
   pl->splits = 1;
-  pl->rb_per_group = 1;
-  pl->grid = 1;
+  pl->sb_per_group = 1;
+  pl->grid = pl->cg;
+  pl->tiles_per_split = pl->col_tiles;
   const bool use_k1 = !p->force_exact && pl->entries != 0;
   if (use_k1) {
     pl->kp = p->candidates > 0 ? p->candidates : tvbf::k1_default_candidates(p->k);
     const int cap = 32 * pl->entries;
     TVBF_REQUIRE(pl->kp >= p->k && pl->kp <= cap - 64, "candidates=%d must lie in [k, %d]", pl->kp,
                  cap - 64);
-    pl->splits = p->splits > 0 ? p->splits : tvbf::k1_choose_splits(pl->rb_count, pl->col_tiles, sms);
+    const int clusters = sms / pl->cg;
+    pl->splits = p->splits > 0 ? p->splits : tvbf::k1_choose_splits(pl->sb_count, pl->col_tiles, clusters);
     if (pl->splits > pl->col_tiles) pl->splits = pl->col_tiles;
+    if (pl->splits > clusters) pl->splits = clusters;
     while (pl->splits > 1 && pl->splits * pl->kp > 1024) --pl->splits;
-    TVBF_REQUIRE(pl->splits >= 1 && pl->splits <= sms, "bad splits %d", pl->splits);
-    pl->rb_per_group = sms / pl->splits;
-    if (pl->rb_per_group > pl->rb_count) pl->rb_per_group = pl->rb_count;
-    pl->grid = pl->rb_per_group * pl->splits;
+    TVBF_REQUIRE(pl->splits >= 1, "bad splits %d", pl->splits);
+    pl->sb_per_group = clusters / pl->splits;
+    if (pl->sb_per_group > pl->sb_count) pl->sb_per_group = pl->sb_count;
+    pl->grid = pl->sb_per_group * pl->splits * pl->cg;
+    pl->tiles_per_split = (pl->col_tiles + pl->splits - 1) / pl->splits;
   }
   pl->k6_grid = 2 * sms;
   if (pl->k6_grid > pl->rows) pl->k6_grid = pl->rows;
@@ -233,8 +253,16 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   kp.k_blocks = f->k_pad / 64;
   kp.col_tiles = pl.col_tiles;
   kp.splits = pl.splits;
-  kp.rb_count = pl.rb_count;
-  kp.rb_per_group = pl.rb_per_group;
+  kp.rb_count = pl.sb_count;
+  kp.rb_per_group = pl.sb_per_group;
+  kp.tiles_per_split = pl.tiles_per_split;
+  kp.sync_kb = pl.sync_kb;
+  kp.sync_slack = pl.sync_slack;
+  kp.stages = pl.stages;
+  kp.prefetch_kb = pl.prefetch_kb;
+  kp.prefetch_mode = pl.prefetch_mode;
+  kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
+  kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
   kp.kp = pl.kp;
   kp.exclude_self = p->exclude_self;
   if (any_folded) {
@@ -249,7 +277,8 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     kp.eps = static_cast<float>(4e-6 * (wsum + 1.0));
   }
   kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
-  kp.w_meta8 = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight / 8.0) : 0.0f;
+  kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight) : 0.0f;
+  kp.meta_hstack = f->meta_kind == TVBF_META_HSTACK ? 1 : 0;
   {
     // strictly below min_similarity in fp32 so that U >= min_similarity always passes "U > theta"
     const double ms = p->min_similarity;
@@ -260,7 +289,8 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     kp.theta_init = th;
   }
   if (phases & 1) {
-    rc = tvbf::k1_launch(f, kp, pl.entries, pl.grid, st);
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+    rc = tvbf::k1_launch(f, kp, pl.entries, pl.cg, pl.grid, st);
     if (rc != TVBF_OK) return rc;
   }
   if (phases & 2) {
@@ -335,12 +365,12 @@ int tvbf_matrix_rows_topk(const double* hybrid, const double* genre, const doubl
                                 static_cast<cudaStream_t>(stream));
 }
 
-int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
-                         void* stream) {
+static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out, int cg,
+                      void* stream) {
   int rc = validate_features(f);
   if (rc != TVBF_OK) return rc;
   TVBF_REQUIRE(out != nullptr, "out is NULL");
-  TVBF_REQUIRE(row0 >= 0 && row0 + 128 <= f->n_pad && col0 >= 0 && col0 + 256 <= f->n_pad,
+  TVBF_REQUIRE(row0 >= 0 && row0 + 128 * cg <= f->n_pad && col0 >= 0 && col0 + 256 <= f->n_pad,
                "tile origin outside the padded operand");
   int sms = 0;
   rc = sm_count_cached(&sms);
@@ -352,15 +382,27 @@ int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, flo
   kp.dump = out;
   kp.n_shows = f->n_shows;
   kp.row_begin = row0;
-  kp.row_end = row0 + 128;
+  kp.row_end = row0 + 128 * cg;
   kp.k_blocks = f->k_pad / 64;
   kp.col_tiles = 1;
   kp.splits = 1;
   kp.rb_count = 1;
   kp.rb_per_group = 1;
+  kp.tiles_per_split = 1;
+  kp.stages = cg == 2 ? 6 : 4;
   kp.dump_col0 = col0;
   kp.kp = 32;
-  return tvbf::k1_launch_dump(f, kp, static_cast<cudaStream_t>(stream));
+  return tvbf::k1_launch_dump(f, kp, cg, static_cast<cudaStream_t>(stream));
+}
+
+int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
+                         void* stream) {
+  return debug_tile(f, row0, col0, out, 1, stream);
+}
+
+int tvbf_debug_gemm_tile_pair(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
+                              void* stream) {
+  return debug_tile(f, row0, col0, out, 2, stream);
 }
 
 }  // extern "C"

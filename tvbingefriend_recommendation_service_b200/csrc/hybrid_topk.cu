@@ -25,24 +25,35 @@ namespace tvbf {
 constexpr int BM = 128;     // rows per CTA tile (= TMEM lanes)
 constexpr int BN = 256;     // columns per tile (= TMEM columns per accumulator)
 constexpr int BK = 64;      // K elements per stage: 64 halves = one 128-byte swizzle row
-constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr uint32_t A_BYTES = BM * BK * 2;
-constexpr uint32_t B_BYTES = BN * BK * 2;
 constexpr uint32_t COL_BYTES = BN * sizeof(TvbfColSide);
 constexpr uint32_t MS_BYTES = BN * sizeof(float);
-constexpr uint32_t OFF_A = 0;
-constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
-constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
-constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
-constexpr uint32_t OFF_BAR = OFF_MS + 2 * MS_BYTES;
-constexpr int NUM_BARS = 2 * STAGES + 6;
-constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
-constexpr uint32_t SMEM_BYTES = SMEM_USED + 1024;  // slack for manual 1024-byte alignment
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
+// warps 0-3: epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4: TMA producer; warp 5: MMA
+// issuer.  The SM's issue arbiter favours higher warp ids, so the two single-thread roles, which
+// share schedulers with epilogue warps 0 and 1, are never starved by the epilogue's ALU stream.
+constexpr int PRODUCER_WARP = 4;
+constexpr int MMA_WARP = 5;
 
+// Shared-memory plan.  CG = CTAs cooperating on one MMA (tcgen05 cta_group): with CG = 2 the pair
+// computes a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the B tile, so the
+// L2 -> SM operand traffic per MAC drops by a third and the ring gets two more stages.
+template <int CG>
+struct Smem {
+  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr uint32_t B_ROWS = BN / CG;
+  static constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
+  static constexpr uint32_t OFF_A = 0;
+  static constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
+  static constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
+  static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_MS + 2 * MS_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr uint32_t USED = OFF_TMEM + 16;
+  static constexpr uint32_t BYTES = USED + 1024;  // slack for manual 1024-byte alignment
+};
 
 // ---- warp-cooperative bitonic sort (descending) of 32*E 64-bit keys, E per lane ----------------
 // element index = q * 32 + lane
@@ -84,9 +95,11 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long (&key)[E], 
 
 // Sort the `n` entries of one row's list and write the best min(n, kp) to dst (may alias src).
 // Returns (to every lane) the score of entry kp-1, i.e. the bound on everything dropped.
+// Deliberately NOT inlined: it runs a few times per row per sweep, while the scoring loop around
+// it runs for every accumulator element and must stay small enough for the instruction cache.
 template <int E>
-__device__ __forceinline__ float warp_compact(const uint2* src, int n, uint2* dst, int kp,
-                                              int lane) {
+__device__ __noinline__ float warp_compact(const uint2* src, int n, uint2* dst, int kp,
+                                           int lane) {
   unsigned long long key[E];
   __syncwarp();  // the owner lane's appends (st.cg) are ordered before these loads
 #pragma unroll
@@ -118,7 +131,7 @@ __device__ __forceinline__ float warp_compact(const uint2* src, int n, uint2* ds
 }
 
 struct ItemCoord {
-  int rb;      // row block within the shard, -1 = nothing to do
+  int sb;      // super block (128*CG rows) within the shard, -1 = nothing to do
   int split;
   int tile0, tile1;
 };
@@ -129,33 +142,76 @@ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
   const int w = item - g * per_group;
   ItemCoord c;
   c.split = w / p.rb_per_group;
-  c.rb = g * p.rb_per_group + (w - c.split * p.rb_per_group);
-  if (c.rb >= p.rb_count) c.rb = -1;
-  c.tile0 = static_cast<int>(static_cast<long long>(p.col_tiles) * c.split / p.splits);
-  c.tile1 = static_cast<int>(static_cast<long long>(p.col_tiles) * (c.split + 1) / p.splits);
+  c.sb = g * p.rb_per_group + (w - c.split * p.rb_per_group);
+  if (c.sb >= p.rb_count) c.sb = -1;
+  // every split walks tiles_per_split tiles so that all CTAs stay in step; tiles at or past
+  // col_tiles are phantom (no loads, no MMA, no epilogue)
+  c.tile0 = c.split * p.tiles_per_split;
+  c.tile1 = c.tile0 + p.tiles_per_split;
   return c;
 }
 
-template <int E, bool kDump>
+// Grid-wide pacing of the TMA producers.  Operand tiles are shared between CTAs only through L2
+// (all CTAs of a column split stream the same B tiles, all CTAs of a row block the same A rows),
+// which works only while they request the same bytes within the L2 retention window; without
+// pacing the CTAs drift apart (data-dependent epilogues) and every CTA pulls its operands from
+// HBM.  Rule: nobody issues chunk c before everybody has issued chunk c - slack.
+struct Pacer {
+  unsigned int* counter;
+  unsigned int n_ctas;
+  int slack;
+  unsigned int chunk;  // chunks this CTA has issued
+  __device__ __forceinline__ void wait_turn() {
+    if (counter == nullptr || static_cast<int>(chunk) < slack) return;
+    const unsigned int target = n_ctas * (chunk - static_cast<unsigned int>(slack) + 1u);
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        printf("tvbf: pacing wait timed out (block %d chunk %u have %u want %u)\n", (int)blockIdx.x,
+               chunk, v, target);
+        __trap();
+      }
+    }
+  }
+  __device__ __forceinline__ void done_chunk() {
+    if (counter != nullptr) atomicAdd(counter, 1u);
+    ++chunk;
+  }
+};
+
+template <int E, bool kDump, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
                    const uint32_t idesc) {
+  using L = Smem<CG>;
+  constexpr int STAGES = L::STAGES;
+  const uint32_t nstages = static_cast<uint32_t>(p.stages);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full = bars;                      // [STAGES]
-  uint64_t* empty = bars + STAGES;            // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;     // [2]
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
-  uint64_t* col_full = bars + 2 * STAGES + 4;   // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  // 1024-byte alignment for the 128B-swizzled tiles; done as an OFFSET so the compiler still knows
+  // these are shared-memory addresses (LDS/STS instead of generic loads)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* full = bars;                          // [STAGES] operands landed (leader's copy is used)
+  uint64_t* empty = bars + STAGES;                // [STAGES] MMAs finished reading the stage
+  uint64_t* acc_full = bars + 2 * STAGES;         // [2] accumulator complete
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;    // [2] accumulator drained (leader's copy is used)
+  uint64_t* col_full = bars + 2 * STAGES + 4;     // [2] column-side records landed
+  uint64_t* col_empty = bars + 2 * STAGES + 6;    // [2] column-side buffer free again
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
@@ -164,14 +220,18 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 128);
+      mbar_init(&acc_empty[b], 128 * CG);
       mbar_init(&col_full[b], 1);
+      mbar_init(&col_empty[b], 128);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_holder, 512);
+  if (warp == MMA_WARP) {
+    if (CG == 2) tmem_alloc_pair(tmem_holder, 512);
+    else tmem_alloc(tmem_holder, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -179,63 +239,106 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             : ((p.rb_count + p.rb_per_group - 1) / p.rb_per_group) *
                                   p.rb_per_group * p.splits;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      Pacer pacer{p.sync_kb > 0 ? p.progress : nullptr, gridDim.x, p.sync_slack, 0u};
+      const int chunks_per_tile = p.sync_kb > 0 ? (p.k_blocks + p.sync_kb - 1) / p.sync_kb : 0;
+      for (int item = cluster_id; item < n_items; item += num_clusters) {
         ItemCoord c = item_coord(p, item);
-        if (kDump) { c.rb = 0; c.tile0 = 0; c.tile1 = 1; }
-        if (c.rb < 0) continue;
-        const int row0 = kDump ? p.row_begin : p.row_begin + c.rb * BM;
-        for (int jt = c.tile0; jt < c.tile1; ++jt, ++it) {
+        if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
+        const int row0 = p.row_begin + (kDump ? 0 : c.sb * BM * CG) + static_cast<int>(cta_rank) * BM;
+        // who prefetches: everyone (mode 1), or one CTA per shared stream (mode 2): the A rows of a
+        // super block are streamed by `splits` clusters, the B tiles of a split by rb_per_group
+        const bool pf_a = p.prefetch_mode == 1 || (p.prefetch_mode == 2 && c.split == 0);
+        const bool pf_b = p.prefetch_mode == 1 ||
+                          (p.prefetch_mode == 2 && c.sb >= 0 && (c.sb % p.rb_per_group) == 0);
+        for (int jt = c.tile0; jt < c.tile1; ++jt) {
+          if (c.sb < 0 || (!kDump && jt >= p.col_tiles)) {
+            // phantom tile: keep the pacing counter moving, touch nothing else
+            for (int ch = 0; ch < chunks_per_tile; ++ch) { pacer.wait_turn(); pacer.done_chunk(); }
+            continue;
+          }
           const uint32_t b = it & 1;
           const int col0 = kDump ? p.dump_col0 : jt * BN;
-          mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // column-side buffer b is free
           if (!kDump) {
+            mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES);
-            bulk_load_1d(smem + OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES,
-                         &col_full[b]);
-            bulk_load_1d(smem + OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES,
-                         &col_full[b]);
+            bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
+            bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
           }
+          const int brow0 = col0 + static_cast<int>(cta_rank) * static_cast<int>(L::B_ROWS);
           for (int kb = 0; kb < p.k_blocks; ++kb) {
+            if (p.sync_kb > 0 && kb % p.sync_kb == 0) {
+              if (kb) pacer.done_chunk();
+              pacer.wait_turn();
+            }
+            if (p.prefetch_kb > 0) {
+              // pull operands that will be needed prefetch_kb k-blocks from now into L2
+              int t = kb + p.prefetch_kb, pj = jt;
+              if (t >= p.k_blocks) { t -= p.k_blocks; ++pj; }
+              const int pend = c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles;
+              if (t < p.k_blocks && pj < pend) {
+                if (pf_a) tma_prefetch_2d(&tmap_a, t * BK, row0);
+                if (pf_b) tma_prefetch_2d(&tmap_b, t * BK, pj * BN + static_cast<int>(cta_rank) * static_cast<int>(L::B_ROWS));
+              }
+            }
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
-            tma_load_2d(smem + OFF_A + stage * A_BYTES, &tmap_a, &full[stage], kb * BK, row0);
-            tma_load_2d(smem + OFF_B + stage * B_BYTES, &tmap_b, &full[stage], kb * BK, col0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            uint8_t* sa = smem + L::OFF_A + stage * A_BYTES;
+            uint8_t* sb = smem + L::OFF_B + stage * L::B_BYTES;
+            if (CG == 2) {
+              // both CTAs' bytes are accounted on the leader's barrier
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + L::B_BYTES));
+              tma_load_2d_pair(sa, &tmap_a, &full[stage], kb * BK, row0);
+              tma_load_2d_pair(sb, &tmap_b, &full[stage], kb * BK, brow0);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], A_BYTES + L::B_BYTES);
+              tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, row0);
+              tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, brow0);
+            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
+          if (p.sync_kb > 0) pacer.done_chunk();
+          ++it;
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =================================
-    if (lane == 0) {
+  } else if (warp == MMA_WARP) {
+    // =============================== MMA issuer (leader CTA) ====================
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = cluster_id; item < n_items; item += num_clusters) {
         ItemCoord c = item_coord(p, item);
-        if (kDump) { c.rb = 0; c.tile0 = 0; c.tile1 = 1; }
-        if (c.rb < 0) continue;
-        for (int jt = c.tile0; jt < c.tile1; ++jt, ++it) {
+        if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
+        if (c.sb < 0) continue;
+        const int tile_end = kDump ? c.tile1 : (c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles);
+        for (int jt = c.tile0; jt < tile_end; ++jt, ++it) {
           const uint32_t b = it & 1;
-          mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue drained accumulator b
+          mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // every epilogue drained accumulator b
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + b * BN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + OFF_A + stage * A_BYTES));
-            const uint64_t db = umma_desc_sw128(smem_u32(smem + OFF_B + stage * B_BYTES));
+            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::OFF_A + stage * A_BYTES));
+            const uint64_t db = umma_desc_sw128(smem_u32(smem + L::OFF_B + stage * L::B_BYTES));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 32 bytes (16 halves) along K inside the 128-byte swizzle row
-              umma_f16(tmem_d, da + static_cast<uint64_t>(k * 2), db + static_cast<uint64_t>(k * 2),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint64_t ka = da + static_cast<uint64_t>(k * 2), kb2 = db + static_cast<uint64_t>(k * 2);
+              if (CG == 2) umma_f16_pair(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-            if (kb == p.k_blocks - 1) umma_commit(&acc_full[b]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            // smem slot reusable once these MMAs have read it; accumulator ready after the last
+            if (CG == 2) {
+              umma_commit_pair(&empty[stage]);
+              if (kb == p.k_blocks - 1) umma_commit_pair(&acc_full[b]);
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb == p.k_blocks - 1) umma_commit(&acc_full[b]);
+            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -248,71 +351,92 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int CAP = 32 * E;
     uint2* my_list = p.scratch + (static_cast<size_t>(blockIdx.x) * BM + row_in_tile) * CAP;
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = cluster_id; item < n_items; item += num_clusters) {
       ItemCoord c = item_coord(p, item);
-      if (kDump) { c.rb = 0; c.tile0 = 0; c.tile1 = 1; }
-      if (c.rb < 0) continue;
-      const int row = (kDump ? p.row_begin : p.row_begin + c.rb * BM) + row_in_tile;
+      if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
+      if (c.sb < 0) continue;
+      const int row_local0 = (kDump ? 0 : c.sb * BM * CG) + static_cast<int>(cta_rank) * BM;  // within shard
+      const int row = p.row_begin + row_local0 + row_in_tile;
       const bool row_valid = row < p.row_end;
       // row-side operands of the fused scores
       unsigned long long g_bits = 0ull;
-      float rn_wg = 0.0f, ci_wm8 = 0.0f;
-      uint32_t ids_row = 0xFEFEFEFEu;
+      uint32_t m_bits = 0u;
+      float rn_wg = 0.0f, ci_wm = 0.0f;
       if (row_valid && !kDump) {
         const TvbfColSide rs = p.col_side[row];
         g_bits = rs.genre_bits;
+        m_bits = rs.meta_bits;
         rn_wg = rs.genre_rnorm * p.w_genre;
-        // "none" (0xFF) must never equal a column's "none": recode it to 0xFE on the row side
-        const uint32_t none = __vcmpeq4(rs.meta_ids, 0xFFFFFFFFu);
-        ids_row = (rs.meta_ids & ~none) | (0xFEFEFEFEu & none);
-        ci_wm8 = p.meta_scale[row] * p.w_meta8;
+        // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories)
+        ci_wm = p.meta_scale[row] * p.w_meta * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
       }
       float theta = row_valid ? p.theta_init : __int_as_float(0x7f800000);  // +inf: never append
       int cnt = 0;
       bool dropped = false;
       const int self_col = p.exclude_self ? row : -1;
+      const float w_text = p.w_text, w_text_err = p.w_text_err, eps = p.eps;
+      const bool hstack = p.meta_hstack != 0;
 
-      for (int jt = c.tile0; jt < c.tile1; ++jt, ++it) {
+      const int tile_end = kDump ? c.tile1 : (c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles);
+      for (int jt = c.tile0; jt < tile_end; ++jt, ++it) {
         const uint32_t b = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int col0 = kDump ? p.dump_col0 : jt * BN;
         if (!kDump) mbar_wait(&col_full[b], ph);
         mbar_wait(&acc_full[b], ph);
         tc_fence_after();
-        const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + OFF_COL + b * COL_BYTES);
-        const float* sms = reinterpret_cast<const float*>(smem + OFF_MS + b * MS_BYTES);
+        const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + L::OFF_COL + b * COL_BYTES);
+        const float* sms = reinterpret_cast<const float*>(smem + L::OFF_MS + b * MS_BYTES);
         const uint32_t taddr = tmem_base + tmem_lane + b * BN;
 
-        uint32_t acc[2][32];
-        tmem_ld_32x32(taddr, acc[0]);
+        // score 16 accumulator columns held in registers
+        auto score16 = [&](const uint32_t (&acc)[16], int cbase) {
 #pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          tmem_ld_wait();
-          if (ch + 1 < BN / 32) tmem_ld_32x32(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
-          if (kDump) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              p.dump[row_in_tile * BN + ch * 32 + e] = __uint_as_float(acc[ch & 1][e]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float a = __uint_as_float(acc[ch & 1][e]);
-              const TvbfColSide cs = scol[ch * 32 + e];
-              const float ms = sms[ch * 32 + e];
+          for (int e = 0; e < 16; ++e) {
+            const float a = __uint_as_float(acc[e]);
+            if (kDump) {
+              p.dump[(row_local0 + row_in_tile) * BN + cbase + e] = a;
+            } else {
+              const TvbfColSide cs = scol[cbase + e];
               const float gdot = static_cast<float>(__popcll(g_bits & cs.genre_bits)) * cs.genre_rnorm;
-              const float mdot = static_cast<float>(__popc(__vcmpeq4(ids_row, cs.meta_ids))) * ms;
-              float u = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm8, p.eps));
-              u = fmaf(a, p.w_text, u);
-              u = fmaf(fabsf(a), p.w_text_err, u);
+              float mdot = static_cast<float>(__popc(m_bits & cs.meta_bits));
+              if (hstack) mdot *= sms[cbase + e];
+              float u = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
+              u = fmaf(a, w_text, u);
+              u = fmaf(fabsf(a), w_text_err, u);
               if (u > theta) {
-                const int col = col0 + ch * 32 + e;
+                const int col = col0 + cbase + e;
                 if (col != self_col && col < p.n_shows) {
                   __stcg(my_list + cnt, make_uint2(__float_as_uint(u), static_cast<uint32_t>(col)));
                   ++cnt;
                 }
               }
             }
-            // keep 32 free slots for the next chunk; compact rows that are nearly full
+          }
+        };
+
+        // 16 chunks of 16 columns, two per loop iteration so that the TMEM load of the next chunk
+        // is in flight while the current one is scored.  The loop is kept rolled on purpose: the
+        // whole body (~700 instructions) stays resident in the instruction cache.
+        uint32_t acc_a[16], acc_b[16];
+        tmem_ld_32x16(taddr, acc_a);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 16; ch += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x16(taddr + (ch + 1) * 16, acc_b);
+          score16(acc_a, ch * 16);
+          tmem_ld_wait();
+          if (ch + 2 < BN / 16) {
+            tmem_ld_32x16(taddr + (ch + 2) * 16, acc_a);
+          } else {
+            // every accumulator column of this tile is in registers: hand the TMEM buffer back
+            tc_fence_before();
+            if (CG == 2) mbar_arrive_cluster(&acc_empty[b], 0u);
+            else mbar_arrive(&acc_empty[b]);
+          }
+          score16(acc_b, (ch + 1) * 16);
+          if (!kDump) {
+            // keep 32 free slots for the next 32 columns; compact rows that are nearly full
             unsigned need = __ballot_sync(kFullMask, cnt > CAP - 32);
             while (need) {
               const int src_lane = __ffs(need) - 1;
@@ -329,17 +453,15 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        // accumulator b and column-side buffer b are free again
-        tc_fence_before();
-        mbar_arrive(&acc_empty[b]);
+        if (!kDump) mbar_arrive(&col_empty[b]);  // column-side buffer b may be refilled
       }
 
       if (!kDump) {
         // final compaction of every row of this warp: sorted best-kp list -> cand
         const int rows_in_shard = p.row_end - p.row_begin;
         for (int src_lane = 0; src_lane < 32; ++src_lane) {
-          const int r = c.rb * BM + quarter * 32 + src_lane;  // row within the shard
-          if (r >= rows_in_shard) break;                      // warp-uniform
+          const int r = row_local0 + quarter * 32 + src_lane;  // row within the shard
+          if (r >= rows_in_shard) break;                       // warp-uniform
           const uint2* lp = reinterpret_cast<const uint2*>(__shfl_sync(
               kFullMask, reinterpret_cast<unsigned long long>(my_list), src_lane));
           const int n = __shfl_sync(kFullMask, cnt, src_lane);
@@ -357,10 +479,11 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -422,6 +545,7 @@ int k1_default_candidates(int k) {
 }
 
 int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
+  // rb_count: super blocks (128*CG rows); sm_count: concurrently resident clusters
   // concurrently running CTAs should cover (row blocks) x (column splits) so that both operand
   // streams are shared through L2; prefer the split count with the best wave efficiency.
   int best = 1;
@@ -440,36 +564,61 @@ int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
   return best;
 }
 
-template <int E, bool kDump>
+template <int E, bool kDump, int CG>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
+  using L = Smem<CG>;
   CUtensorMap ta, tb;
   int rc = make_operand_map(f, BM, &ta);
   if (rc != TVBF_OK) return rc;
-  rc = make_operand_map(f, BN, &tb);
+  rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(SMEM_BYTES)));
-  const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM, BN);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, kp, idesc);
-  TVBF_LAUNCH_OK("hybrid_topk_kernel");
+                                    static_cast<int>(L::BYTES)));
+  const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  // the pacing counter makes CTAs wait on one another: require co-residency of the whole grid
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = (kp.sync_kb > 0 && kp.cooperative) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  TVBF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, kp, idesc));
   return TVBF_OK;
 }
 
-int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int grid,
-              cudaStream_t st) {
-  switch (entries_per_lane) {
-    case 4: return launch_k1<4, false>(f, kp, grid, st);
-    case 8: return launch_k1<8, false>(f, kp, grid, st);
-    case 16: return launch_k1<16, false>(f, kp, grid, st);
-    default:
-      tvbf_set_error("unsupported candidate capacity (entries per lane %d)", entries_per_lane);
-      return TVBF_ERR_INVALID;
+int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
+              int grid, cudaStream_t st) {
+  if (cta_group == 2) {
+    switch (entries_per_lane) {
+      case 4: return launch_k1<4, false, 2>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 2>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 2>(f, kp, grid, st);
+      default: break;
+    }
+  } else {
+    switch (entries_per_lane) {
+      case 4: return launch_k1<4, false, 1>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 1>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 1>(f, kp, grid, st);
+      default: break;
+    }
   }
+  tvbf_set_error("unsupported candidate capacity (entries per lane %d)", entries_per_lane);
+  return TVBF_ERR_INVALID;
 }
 
-int k1_launch_dump(const tvbf_features* f, const K1Params& kp, cudaStream_t st) {
-  return launch_k1<4, true>(f, kp, 1, st);
+int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st) {
+  return cta_group == 2 ? launch_k1<4, true, 2>(f, kp, 2, st) : launch_k1<4, true, 1>(f, kp, 1, st);
 }
 
 }  // namespace tvbf

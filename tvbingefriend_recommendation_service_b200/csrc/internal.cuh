@@ -13,22 +13,31 @@ struct K1Params {
   uint2* cand;         // [rows][splits][kp] sorted candidates
   int* cand_cnt;       // [rows][splits]
   float* cand_theta;   // [rows][splits] bound on every dropped U, -inf if nothing was dropped
-  float* dump;         // dump kernel only: [128][256] raw accumulators of one tile
+  float* dump;         // dump kernel only: [128*CG][256] raw accumulators of one tile
+  unsigned int* progress;  // grid-wide pacing counter (zeroed before launch), see sync_kb
   int n_shows;
   int row_begin;       // multiple of 128
   int row_end;
   int k_blocks;        // k_pad / 64
   int col_tiles;       // ceil(n_shows / 256)
   int splits;
-  int rb_count;        // row blocks of this shard
-  int rb_per_group;    // row blocks processed concurrently (grid = rb_per_group * splits)
+  int rb_count;        // super blocks (128 * cta_group rows) of this shard
+  int rb_per_group;    // super blocks processed concurrently (clusters = rb_per_group * splits)
   int dump_col0;       // dump kernel only
+  int tiles_per_split; // every item walks exactly this many column tiles (phantom past the end)
+  int sync_kb;         // producers pace themselves every sync_kb k-blocks (0 = no pacing)
+  int sync_slack;      // ... staying at most this many chunks ahead of the slowest CTA
+  int stages;          // smem ring depth actually used (<= compiled maximum)
+  int prefetch_kb;     // L2 prefetch distance in k-blocks (0 = off)
+  int prefetch_mode;   // 1: every CTA prefetches its operands; 2: one designated CTA per stream
+  int cooperative;     // launch with the cooperative attribute (co-residency guaranteed)
   int kp;              // candidates kept per (row, split)
   int exclude_self;
   float w_text;        // text_weight * 2^-2s
   float w_text_err;    // |text_weight| * 2^-2s * rel_err  (multiplies |acc|)
   float w_genre;
-  float w_meta8;       // metadata_weight / 8 (the byte-compare popcount counts 8 per match)
+  float w_meta;        // metadata_weight
+  int meta_hstack;     // 1: per-column 1/sqrt(#categories) scale is read from meta_scale
   float eps;           // absolute slack: fp32 rounding of the epilogue (+ folded-group bounds)
   float theta_init;    // just below min_similarity
 };
@@ -45,9 +54,9 @@ struct ScoreParams {
 int k1_entries_per_lane(int k);
 int k1_default_candidates(int k);
 int k1_choose_splits(int rb_count, int col_tiles, int sm_count);
-int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int grid,
-              cudaStream_t st);
-int k1_launch_dump(const tvbf_features* f, const K1Params& kp, cudaStream_t st);
+int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
+              int grid, cudaStream_t st);
+int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st);
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st);

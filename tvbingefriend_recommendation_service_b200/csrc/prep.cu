@@ -93,30 +93,30 @@ __global__ void genre_bits_kernel(const uint8_t* __restrict__ genre, int n_rows,
   col_side[row].genre_rnorm = pc ? 1.0f / sqrtf(static_cast<float>(pc)) : 0.0f;
 }
 
-__device__ __forceinline__ uint32_t one_hot_id(const uint8_t* m, int dim, int row) {
-  if (m == nullptr || dim <= 0) return 0xFFu;
+__device__ __forceinline__ uint32_t one_hot_bits(const uint8_t* m, int dim, int row, int offset) {
+  if (m == nullptr || dim <= 0) return 0u;
   const uint8_t* x = m + static_cast<size_t>(row) * dim;
-  uint32_t id = 0xFFu;
+  uint32_t bits = 0u;
   for (int c = 0; c < dim; ++c)
-    if (x[c]) id = static_cast<uint32_t>(c);
-  return id;
+    if (x[c]) bits |= 1u << (offset + c);
+  return bits;
 }
 
-__global__ void meta_ids_kernel(const uint8_t* __restrict__ platform, int p_dim,
-                                const uint8_t* __restrict__ type, int t_dim,
-                                const uint8_t* __restrict__ language, int l_dim, int n_rows,
-                                int n_pad, int meta_kind, TvbfColSide* __restrict__ col_side,
-                                float* __restrict__ meta_scale) {
+// one-hot platform / type / language rows -> one 32-bit mask per show; the number of matching
+// groups of two shows is then popc(a & b)
+__global__ void meta_bits_kernel(const uint8_t* __restrict__ platform, int p_dim,
+                                 const uint8_t* __restrict__ type, int t_dim,
+                                 const uint8_t* __restrict__ language, int l_dim, int n_rows,
+                                 int n_pad, int meta_kind, TvbfColSide* __restrict__ col_side,
+                                 float* __restrict__ meta_scale) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_pad) return;
-  uint32_t p = 0xFFu, t = 0xFFu, l = 0xFFu;
-  if (row < n_rows) {
-    p = one_hot_id(platform, p_dim, row);
-    t = one_hot_id(type, t_dim, row);
-    l = one_hot_id(language, l_dim, row);
-  }
-  col_side[row].meta_ids = p | (t << 8) | (l << 16) | (0xFFu << 24);
-  int valid = (p != 0xFFu) + (t != 0xFFu) + (l != 0xFFu);
+  uint32_t bits = 0u;
+  if (row < n_rows)
+    bits = one_hot_bits(platform, p_dim, row, 0) | one_hot_bits(type, t_dim, row, p_dim) |
+           one_hot_bits(language, l_dim, row, p_dim + t_dim);
+  col_side[row].meta_bits = bits;
+  const int valid = __popc(bits);
   float s;
   if (row >= n_rows) s = 0.0f;
   else if (meta_kind == TVBF_META_MEAN3) s = 0.57735026918962576f;  // 1/sqrt(3)
@@ -224,15 +224,15 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
                        int32_t meta_kind, void* col_side, float* meta_scale, void* stream) {
   TVBF_REQUIRE(col_side && meta_scale && n_rows >= 0 && n_pad >= n_rows,
                "tvbf_prep_meta_ids: bad arguments");
-  TVBF_REQUIRE(p_dim <= 254 && t_dim <= 254 && l_dim <= 254,
-               "tvbf_prep_meta_ids: one-hot groups wider than 254 columns are not packable");
+  TVBF_REQUIRE(p_dim >= 0 && t_dim >= 0 && l_dim >= 0 && p_dim + t_dim + l_dim <= 32,
+               "tvbf_prep_meta_ids: the three one-hot groups must fit 32 bits together");
   TVBF_REQUIRE(meta_kind == TVBF_META_MEAN3 || meta_kind == TVBF_META_HSTACK,
                "tvbf_prep_meta_ids: bad meta_kind");
   if (n_pad == 0) return TVBF_OK;
-  meta_ids_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  meta_bits_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       platform, p_dim, type, t_dim, language, l_dim, n_rows, n_pad, meta_kind,
       static_cast<TvbfColSide*>(col_side), meta_scale);
-  TVBF_LAUNCH_OK("meta_ids_kernel");
+  TVBF_LAUNCH_OK("meta_bits_kernel");
   return TVBF_OK;
 }
 

@@ -65,26 +65,13 @@ __device__ __forceinline__ double genre_score(const tvbf_features& f, int i, int
   return 0.0;
 }
 
-__device__ __forceinline__ int id_matches(uint32_t a, uint32_t b, int* na, int* nb) {
-  int eq = 0, va = 0, vb = 0;
-#pragma unroll
-  for (int g = 0; g < 3; ++g) {
-    const uint32_t x = (a >> (8 * g)) & 0xFFu, y = (b >> (8 * g)) & 0xFFu;
-    va += (x != 0xFFu);
-    vb += (y != 0xFFu);
-    eq += (x == y && x != 0xFFu);
-  }
-  *na = va;
-  *nb = vb;
-  return eq;
-}
-
 __device__ __forceinline__ double meta_score(const tvbf_features& f, int i, int j) {
   if (f.meta_mode == TVBF_GROUP_PACKED) {
     const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
-    int ni, nj;
-    const int eq = id_matches(cs[i].meta_ids, cs[j].meta_ids, &ni, &nj);
+    const uint32_t a = cs[i].meta_bits, b = cs[j].meta_bits;
+    const int eq = __popc(a & b);  // groups (platform, type, language) with the same category
     if (f.meta_kind == TVBF_META_MEAN3) return static_cast<double>(eq) / 3.0;
+    const int ni = __popc(a), nj = __popc(b);
     if (ni == 0 || nj == 0) return 0.0;
     return static_cast<double>(eq) * ((1.0 / sqrt(static_cast<double>(ni))) *
                                       (1.0 / sqrt(static_cast<double>(nj))));

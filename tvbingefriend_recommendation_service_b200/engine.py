@@ -35,8 +35,8 @@ def _is_binary(a: np.ndarray) -> bool:
 
 
 def _is_one_hot(a: np.ndarray) -> bool:
-    """values in {0,1}, at most one 1 per row, narrow enough for a byte id."""
-    if a.ndim != 2 or a.shape[1] > 254 or a.shape[1] == 0:
+    """values in {0,1}, at most one 1 per row."""
+    if a.ndim != 2 or a.shape[1] == 0:
         return False
     if not _is_binary(a):
         return False
@@ -88,7 +88,10 @@ def stage(features: dict, metadata_mode: str = "mean3", pin: bool = True) -> Sta
         if a.shape[0] != n:
             raise ValueError(f"{name}_features has {a.shape[0]} rows, genre_features has {n}")
     genre_packed = genre.ndim == 2 and 1 <= genre.shape[1] <= 64 and _is_binary(genre)
-    meta_packed = all(_is_one_hot(a) for a in (plat, typ, lang))
+    # the three one-hot groups are packed into one 32-bit mask per show (reference defaults:
+    # 21 platforms + 5 types + 6 languages = 32 columns, feature_extractor.py:122-193)
+    meta_packed = (plat.shape[1] + typ.shape[1] + lang.shape[1] <= 32) and \
+        all(_is_one_hot(a) for a in (plat, typ, lang))
     if genre_packed:
         g_t = torch.from_numpy(np.ascontiguousarray(genre != 0).astype(np.uint8))
     else:
@@ -306,7 +309,7 @@ class HybridTopKEngine:
                      min_similarity: float = 0.1, exclude_self: bool = True, row_begin: int = 0,
                      row_end: int | None = None, splits: int = 0, candidates: int = 0,
                      force_exact: bool = False, skip_fallback: bool = False, phases: int = 0,
-                     out: dict | None = None) -> dict:
+                     out: dict | None = None, tuning: int = 0) -> dict:
         """Launch the K1 -> K5 -> K6 sequence on the current stream; returns device tensors.
         ``phases`` (bitmask 1|2|4) launches a subset so that a caller can bracket each kernel with
         its own CUDA events; pass the dict returned by the first call as ``out`` to the others."""
@@ -319,7 +322,7 @@ class HybridTopKEngine:
         p = Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=float(min_similarity),
                    k=int(k), exclude_self=int(bool(exclude_self)), row_begin=int(row_begin), row_end=row_end,
                    splits=int(splits), candidates=int(candidates), force_exact=int(bool(force_exact)),
-                   skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0, phases=int(phases), reserved=0)
+                   skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0, phases=int(phases), tuning=int(tuning))
         with torch.cuda.device(self.device):
             nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(cat.c), C.byref(p))
             if nbytes == 0:
@@ -487,11 +490,13 @@ class HybridTopKEngine:
         return {"mean": float(out5[0]), "std": float(out5[1]), "min": float(out5[2]),
                 "max": float(out5[3]), "median": float(out5[4])}
 
-    def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int) -> torch.Tensor:
-        """Raw fp32 accumulators of one 128 x 256 tensor-core tile (diagnostics / tests)."""
+    def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int, pair: bool = False) -> torch.Tensor:
+        """Raw fp32 accumulators of one tensor-core tile (diagnostics / tests): 128 x 256 through
+        cta_group::1, or 256 x 256 through a cta_group::2 CTA pair."""
         with torch.cuda.device(self.device):
-            out = torch.zeros((128, 256), dtype=torch.float32, device=self.device)
-            check(self.lib.tvbf_debug_gemm_tile(C.byref(cat.c), int(row0), int(col0), out.data_ptr(), self._stream()),
+            out = torch.zeros((256 if pair else 128, 256), dtype=torch.float32, device=self.device)
+            fn = self.lib.tvbf_debug_gemm_tile_pair if pair else self.lib.tvbf_debug_gemm_tile
+            check(fn(C.byref(cat.c), int(row0), int(col0), out.data_ptr(), self._stream()),
                   "tvbf_debug_gemm_tile")
             self.kernel_launches += 1
         return out
