@@ -270,7 +270,7 @@ def main() -> None:
             t = empty_tables(k, eng.device)
         if world > 1:
             t = gather_tables(t, n, k)
-        return eng.to_host(t) if rank == 0 else None
+        return eng.to_host(t, copy=False) if rank == 0 else None
 
     step_e2e()
     sync()

@@ -98,7 +98,7 @@ typedef struct tvbf_params {
                           /* 4: K6 exact repair -- lets a caller time the kernels separately     */
                           /* (same workspace must be passed to every phase call)                 */
   int32_t tuning;         /* 0 = defaults. bits 0-3: tcgen05 cta_group (1 or 2; default 2);     */
-                          /* bits 4-11: producer pacing chunk in 64-wide k-blocks (default 8,   */
+                          /* bits 4-11: producer pacing chunk in 64-wide k-blocks (default 16,   */
                           /* 255 = off); bits 12-15: pacing slack in chunks (default 2);        */
                           /* bits 16-19: smem ring stages; bits 20-29: L2 prefetch distance and */
                           /* mode (experimental, default off); bit 30: non-cooperative launch   */

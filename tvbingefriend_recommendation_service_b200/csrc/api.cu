@@ -82,11 +82,11 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   int rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
   pl->rows = p->row_end - p->row_begin;
-  // tuning: bits 0-3 cta_group (0 = 2), bits 4-11 pacing chunk in k-blocks (0 = 8, 255 = off),
+  // tuning: bits 0-3 cta_group (0 = 2), bits 4-11 pacing chunk in k-blocks (0 = 16, 255 = off),
   // bits 12-15 pacing slack in chunks (0 = 2)
   const int tune = p->tuning;
   pl->cg = (tune & 0xF) == 1 ? 1 : 2;
-  pl->sync_kb = ((tune >> 4) & 0xFF) == 0 ? 8 : (((tune >> 4) & 0xFF) == 255 ? 0 : ((tune >> 4) & 0xFF));
+  pl->sync_kb = ((tune >> 4) & 0xFF) == 0 ? 16 : (((tune >> 4) & 0xFF) == 255 ? 0 : ((tune >> 4) & 0xFF));
   pl->sync_slack = ((tune >> 12) & 0xF) == 0 ? 2 : ((tune >> 12) & 0xF);
   // bits 16-19 ring stages (0 = all), bits 20-27 L2 prefetch distance in k-blocks (0 = off),
   // bits 28-29 prefetch mode (0 -> 2)

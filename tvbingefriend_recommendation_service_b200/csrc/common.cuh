@@ -98,6 +98,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp (warp-uniform control flow keeps addresses and descriptors
+// in uniform registers; a divergent `if (lane == 0)` region makes the compiler wrap every TMA /
+// tcgen05 instruction in an elect-and-loop sequence that costs more than the MMA it issues).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

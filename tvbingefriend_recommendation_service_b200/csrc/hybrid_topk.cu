@@ -177,8 +177,8 @@ struct Pacer {
       }
     }
   }
-  __device__ __forceinline__ void done_chunk() {
-    if (counter != nullptr) atomicAdd(counter, 1u);
+  __device__ __forceinline__ void done_chunk(bool do_add) {
+    if (counter != nullptr && do_add) atomicAdd(counter, 1u);
     ++chunk;
   }
 };
@@ -241,7 +241,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == PRODUCER_WARP) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // the whole warp walks the loops (uniform control flow); one elected lane issues
+    {
       uint32_t stage = 0, phase = 0, it = 0;
       Pacer pacer{p.sync_kb > 0 ? p.progress : nullptr, gridDim.x, p.sync_slack, 0u};
       const int chunks_per_tile = p.sync_kb > 0 ? (p.k_blocks + p.sync_kb - 1) / p.sync_kb : 0;
@@ -257,24 +258,30 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int jt = c.tile0; jt < c.tile1; ++jt) {
           if (c.sb < 0 || (!kDump && jt >= p.col_tiles)) {
             // phantom tile: keep the pacing counter moving, touch nothing else
-            for (int ch = 0; ch < chunks_per_tile; ++ch) { pacer.wait_turn(); pacer.done_chunk(); }
+            for (int ch = 0; ch < chunks_per_tile; ++ch) {
+              pacer.wait_turn();
+              pacer.done_chunk(lane == 0);
+            }
             continue;
           }
           const uint32_t b = it & 1;
           const int col0 = kDump ? p.dump_col0 : jt * BN;
           if (!kDump) {
             mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
-            mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES);
-            bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
-            bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES);
+              bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
+              bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
+            }
+            __syncwarp();
           }
           const int brow0 = col0 + static_cast<int>(cta_rank) * static_cast<int>(L::B_ROWS);
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             if (p.sync_kb > 0 && kb % p.sync_kb == 0) {
-              if (kb) pacer.done_chunk();
+              if (kb) pacer.done_chunk(lane == 0);
               pacer.wait_turn();
             }
-            if (p.prefetch_kb > 0) {
+            if (p.prefetch_kb > 0 && lane == 0) {
               // pull operands that will be needed prefetch_kb k-blocks from now into L2
               int t = kb + p.prefetch_kb, pj = jt;
               if (t >= p.k_blocks) { t -= p.k_blocks; ++pj; }
@@ -285,29 +292,36 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               }
             }
             mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sa = smem + L::OFF_A + stage * A_BYTES;
-            uint8_t* sb = smem + L::OFF_B + stage * L::B_BYTES;
-            if (CG == 2) {
-              // both CTAs' bytes are accounted on the leader's barrier
-              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + L::B_BYTES));
-              tma_load_2d_pair(sa, &tmap_a, &full[stage], kb * BK, row0);
-              tma_load_2d_pair(sb, &tmap_b, &full[stage], kb * BK, brow0);
-            } else {
-              mbar_arrive_expect_tx(&full[stage], A_BYTES + L::B_BYTES);
-              tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, row0);
-              tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, brow0);
+            if (elect_one()) {
+              uint8_t* sa = smem + L::OFF_A + stage * A_BYTES;
+              uint8_t* sb = smem + L::OFF_B + stage * L::B_BYTES;
+              if (CG == 2) {
+                // both CTAs' bytes are accounted on the leader's barrier
+                if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + L::B_BYTES));
+                tma_load_2d_pair(sa, &tmap_a, &full[stage], kb * BK, row0);
+                tma_load_2d_pair(sb, &tmap_b, &full[stage], kb * BK, brow0);
+              } else {
+                mbar_arrive_expect_tx(&full[stage], A_BYTES + L::B_BYTES);
+                tma_load_2d(sa, &tmap_a, &full[stage], kb * BK, row0);
+                tma_load_2d(sb, &tmap_b, &full[stage], kb * BK, brow0);
+              }
             }
+            __syncwarp();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
-          if (p.sync_kb > 0) pacer.done_chunk();
+          if (p.sync_kb > 0) pacer.done_chunk(lane == 0);
           ++it;
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer (leader CTA) ====================
-    if (lane == 0 && leader) {
+    // whole warp in the loops, one elected lane issues: keeps the descriptors in uniform registers
+    if (leader) {
       uint32_t stage = 0, phase = 0, it = 0;
+      // descriptor of stage 0; stage s / K sub-block k are reached by adding to the address field
+      const uint64_t desc_a0 = umma_desc_sw128(smem_u32(smem + L::OFF_A));
+      const uint64_t desc_b0 = umma_desc_sw128(smem_u32(smem + L::OFF_B));
       for (int item = cluster_id; item < n_items; item += num_clusters) {
         ItemCoord c = item_coord(p, item);
         if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
@@ -321,23 +335,26 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(smem + L::OFF_A + stage * A_BYTES));
-            const uint64_t db = umma_desc_sw128(smem_u32(smem + L::OFF_B + stage * L::B_BYTES));
+            if (elect_one()) {
+              const uint64_t da = desc_a0 + static_cast<uint64_t>(stage * (A_BYTES >> 4));
+              const uint64_t db = desc_b0 + static_cast<uint64_t>(stage * (L::B_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              // advance 32 bytes (16 halves) along K inside the 128-byte swizzle row
-              const uint64_t ka = da + static_cast<uint64_t>(k * 2), kb2 = db + static_cast<uint64_t>(k * 2);
-              if (CG == 2) umma_f16_pair(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_f16(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                // advance 32 bytes (16 halves) along K inside the 128-byte swizzle row
+                const uint64_t ka = da + static_cast<uint64_t>(k * 2), kb2 = db + static_cast<uint64_t>(k * 2);
+                if (CG == 2) umma_f16_pair(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_f16(tmem_d, ka, kb2, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              // smem slot reusable once these MMAs have read it; accumulator ready after the last
+              if (CG == 2) {
+                umma_commit_pair(&empty[stage]);
+                if (kb == p.k_blocks - 1) umma_commit_pair(&acc_full[b]);
+              } else {
+                umma_commit(&empty[stage]);
+                if (kb == p.k_blocks - 1) umma_commit(&acc_full[b]);
+              }
             }
-            // smem slot reusable once these MMAs have read it; accumulator ready after the last
-            if (CG == 2) {
-              umma_commit_pair(&empty[stage]);
-              if (kb == p.k_blocks - 1) umma_commit_pair(&acc_full[b]);
-            } else {
-              umma_commit(&empty[stage]);
-              if (kb == p.k_blocks - 1) umma_commit(&acc_full[b]);
-            }
+            __syncwarp();
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }

@@ -188,6 +188,7 @@ class HybridTopKEngine:
         self.text_dtype = text_dtype
         self.kernel_launches = 0      # kernels of libtvbf launched through this engine
         self._ws: torch.Tensor | None = None
+        self._pinned: dict = {}
 
     # ------------------------------------------------------------------------------------ utils
     def _stream(self) -> int:
@@ -350,10 +351,26 @@ class HybridTopKEngine:
         t["row_begin"] = row_begin
         return t
 
-    @staticmethod
-    def to_host(t: dict) -> TopK:
-        """D2H of a result table (synchronises)."""
-        host = {n: t[n].cpu().numpy() for n in ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")}
+    def to_host(self, t: dict, copy: bool = True) -> TopK:
+        """D2H of a result table into cached pinned buffers (synchronises).  With ``copy=False`` the
+        returned arrays alias the pinned buffers and are valid until the next ``to_host`` of the
+        same shape on this engine."""
+        names = ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")
+        host = {}
+        with torch.cuda.device(self.device):
+            for n in names:
+                src = t[n]
+                key = (n, tuple(src.shape), src.dtype)
+                buf = self._pinned.get(key)
+                if buf is None:
+                    if len(self._pinned) > 64:
+                        self._pinned.clear()
+                    buf = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                    self._pinned[key] = buf
+                buf.copy_(src, non_blocking=True)
+                host[n] = buf
+            torch.cuda.current_stream(self.device).synchronize()
+        host = {n: (v.numpy().copy() if copy else v.numpy()) for n, v in host.items()}
         return TopK(indices=host["indices"], counts=host["counts"], hybrid=host["hybrid"], genre=host["genre"],
                     text=host["text"], metadata=host["metadata"], row_begin=int(t.get("row_begin", 0)),
                     flagged_rows=int(host["stats"][0]), rescored_pairs=int(host["stats"][1]))
