@@ -90,3 +90,20 @@ def test_c5_shape_top100_sweep_on_reduced_rows(engine):
         dc = engine.upload(st, w)
         top = engine.to_host(engine.top_k_device(dc, w, 100, 0.1))
         assert_topk_matches(top, cat.features(), rows, w, 100, 0.1)
+
+
+def test_single_process_multi_gpu_matches_single_gpu(engine):
+    """device_ids=[0, 1]: rows sharded in 128-row tiles over two GPUs, features replicated."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(3000, 2000, nnz=25, seed=77)
+    one = SimilarityComputer(engine=engine).compute_top_k(cat.features())
+    two = SimilarityComputer(engine=engine).compute_top_k(cat.features(), device_ids=[0, 1])
+    assert np.array_equal(one.indices, two.indices) and np.array_equal(one.counts, two.counts)
+    m = one.indices >= 0
+    assert np.array_equal(one.hybrid[m], two.hybrid[m])

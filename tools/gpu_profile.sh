@@ -10,5 +10,4 @@ echo "launch list exit $?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:hybrid_topk -s 3 -c 1 -o gpurun_out/prof_k1 $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?"
-tail -3 gpurun_out/ncu_full.log | cut -c1-300
-cat gpurun_out/plain.log | cut -c1-400
+cut -c1-600 gpurun_out/plain.log

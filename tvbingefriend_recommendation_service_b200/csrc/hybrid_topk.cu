@@ -562,21 +562,27 @@ int k1_default_candidates(int k) {
 }
 
 int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
-  // rb_count: super blocks (128*CG rows); sm_count: concurrently resident clusters
-  // concurrently running CTAs should cover (row blocks) x (column splits) so that both operand
-  // streams are shared through L2; prefer the split count with the best wave efficiency.
+  // rb_count: super blocks (128*CG rows); sm_count: concurrently resident clusters.
+  // Concurrently running clusters cover (R super blocks) x (S column splits): A rows are shared
+  // S-way and B tiles R-way through L2, and the R A-blocks stay L2-resident across column tiles
+  // when R is small.  Measured on C3: S = 4 is best (S = 2: +3 % K1 time and 1.8x the DRAM
+  // traffic; S >= 6: same K1 time but the rescoring cost grows linearly with S).
   int best = 1;
-  double best_eff = -1.0;
+  double best_score = -1.0;
   for (int s = 1; s <= 8; ++s) {
-    if (s > 1 && col_tiles / s < 4) break;
+    if (s > 1 && col_tiles / s < 8) break;
     const int r = sm_count / s;
     if (r < 1) break;
-    const int groups = (rb_count + r - 1) / r;
-    double eff = static_cast<double>(rb_count) / (static_cast<double>(groups) * r) *
-                 (static_cast<double>(r * s) / sm_count);
-    // mild preference for 2..4 splits: fewer lists to merge, both operands still L2-shared
-    if (s >= 2 && s <= 4) eff += 0.01;
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    const int r_used = r < rb_count ? r : rb_count;
+    const int groups = (rb_count + r_used - 1) / r_used;
+    // fraction of cluster-slots doing useful work over the whole launch
+    double score = static_cast<double>(rb_count) / (static_cast<double>(groups) * r_used) *
+                   (static_cast<double>(r_used * s) / sm_count);
+    if (s == 4) score += 0.03;
+    else if (s == 3) score += 0.02;
+    else if (s == 2) score += 0.01;
+    else if (s >= 6) score -= 0.02;
+    if (score > best_score + 1e-9) { best_score = score; best = s; }
   }
   return best;
 }
