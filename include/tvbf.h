@@ -100,8 +100,9 @@ typedef struct tvbf_params {
   int32_t tuning;         /* 0 = defaults. bits 0-3: tcgen05 cta_group (1 or 2; default 2);     */
                           /* bits 4-11: producer pacing chunk in 64-wide k-blocks (default 16,   */
                           /* 255 = off); bits 12-15: pacing slack in chunks (default 2);        */
-                          /* bits 16-19: smem ring stages; bits 20-29: L2 prefetch distance and */
-                          /* mode (experimental, default off); bit 30: non-cooperative launch   */
+                          /* bits 16-19: smem ring stages; bits 20-21: symmetric mode (0 auto,  */
+                          /* 1 off, 2 on: compute only tiles on/above the diagonal and feed     */
+                          /* both shows of every score); bit 30: non-cooperative launch         */
 } tvbf_params;
 
 /* Result table of the shard rows [row_begin, row_end): the a9 record stream of

@@ -15,6 +15,8 @@ from oracle.reference_paths import SimilarityComputerOracle
 
 pytestmark = pytest.mark.gpu
 
+SYM_OFF, SYM_ON = 1 << 20, 2 << 20   # tvbf_params.tuning bits 20-21
+
 
 @pytest.fixture(scope="module")
 def engine():
@@ -140,16 +142,23 @@ def test_forced_exact_equals_certified_path(engine, cat2k):
     assert np.array_equal(a.hybrid[m], b.hybrid[m])
 
 
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON])
 @pytest.mark.parametrize("splits", [1, 2, 3])
-def test_column_splits_do_not_change_the_table(engine, cat2k, splits):
-    a = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, splits=splits)
+def test_column_splits_do_not_change_the_table(engine, cat2k, splits, tuning):
+    a = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, splits=splits, tuning=tuning)
     b = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, force_exact=True)
     assert np.array_equal(a.indices, b.indices)
 
 
-@pytest.mark.parametrize("tuning", [0x1, 0x2, 0x1 | (255 << 4), 0x2 | (255 << 4), 0x2 | (1 << 4) | (1 << 12)])
+
+
+
+@pytest.mark.parametrize("tuning", [0x1, 0x2 | SYM_OFF, 0x1 | (255 << 4), 0x2 | (255 << 4) | SYM_OFF,
+                                    0x2 | (1 << 4) | (1 << 12) | SYM_OFF, 0x2 | SYM_ON,
+                                    0x2 | SYM_ON | (255 << 4), 0x2 | SYM_ON | (2 << 4) | (1 << 12), 0x2 | SYM_ON | (63 << 22), 0x2 | SYM_ON | (2 << 22)])
 def test_kernel_variants_give_the_same_table(engine, cat2k, tuning):
-    """cta_group 1 / 2, producer pacing on / off / tight: same certified result."""
+    """cta_group 1 / 2, producer pacing on / off / tight, one-sided / symmetric sweep: same
+    certified result."""
     a = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, tuning=tuning, splits=3)
     b = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.1, force_exact=True)
     assert np.array_equal(a.indices, b.indices) and np.array_equal(a.counts, b.counts)

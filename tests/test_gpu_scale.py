@@ -56,7 +56,8 @@ def test_c2_20k_single_gpu_vs_oracle(engine):
     assert np.array_equal(top.indices, again.indices) and np.array_equal(top.counts, again.counts)
 
 
-def test_c3_100k_properties_and_sample(engine):
+@pytest.mark.parametrize("tuning", [2 << 20, 1 << 20], ids=["symmetric", "one_sided"])
+def test_c3_100k_properties_and_sample(engine, tuning):
     """BASELINE config 3 at full size: 100 k shows, 10 k vocab."""
     from tvbingefriend_recommendation_service_b200.engine import stage
     from tvbingefriend_recommendation_service_b200.synthetic import make_config
@@ -64,7 +65,7 @@ def test_c3_100k_properties_and_sample(engine):
     cat = make_config("C3")
     w = (0.4, 0.5, 0.1)
     dc = engine.upload(stage(cat.features()), w)
-    top = engine.to_host(engine.top_k_device(dc, w, 20, 0.1))
+    top = engine.to_host(engine.top_k_device(dc, w, 20, 0.1, tuning=tuning))
     check_table_properties(top, 100_000, 20, 0.1)
     rows = np.linspace(0, 99_999, 96).astype(np.int64)
     assert_topk_matches(top, cat.features(), rows)

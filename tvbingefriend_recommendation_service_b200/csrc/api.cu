@@ -39,8 +39,9 @@ int sm_count_cached(int* out) {
 
 struct Plan {
   int rows, cg, sb_count, col_tiles, splits, sb_per_group, grid, entries, kp, k6_grid;
-  int tiles_per_split, sync_kb, sync_slack, stages, prefetch_kb, prefetch_mode;
-  size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_keys, off_count, total;
+  int tiles_per_split, sync_kb, sync_slack, stages, sym, sym_cap, cand_lists;
+  size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_keys, off_count, off_gtheta, off_gcnt,
+      off_glist, total;
 };
 
 int validate_features(const tvbf_features* f) {
@@ -88,14 +89,13 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   pl->cg = (tune & 0xF) == 1 ? 1 : 2;
   pl->sync_kb = ((tune >> 4) & 0xFF) == 0 ? 16 : (((tune >> 4) & 0xFF) == 255 ? 0 : ((tune >> 4) & 0xFF));
   pl->sync_slack = ((tune >> 12) & 0xF) == 0 ? 2 : ((tune >> 12) & 0xF);
-  // bits 16-19 ring stages (0 = all), bits 20-27 L2 prefetch distance in k-blocks (0 = off),
-  // bits 28-29 prefetch mode (0 -> 2)
+  // bits 16-19 ring stages (0 = all); bits 20-21 symmetric mode (0 = auto, 1 = off, 2 = on)
   const int max_stages = pl->cg == 2 ? 6 : 4;
   pl->stages = ((tune >> 16) & 0xF) == 0 ? max_stages : ((tune >> 16) & 0xF);
   if (pl->stages > max_stages) pl->stages = max_stages;
   if (pl->stages < 2) pl->stages = 2;
-  pl->prefetch_kb = (tune >> 20) & 0xFF;
-  pl->prefetch_mode = ((tune >> 28) & 0x3) == 0 ? 2 : ((tune >> 28) & 0x3);
+  pl->sym = 0;
+  pl->sym_cap = 1024;
   const int sb_rows = 128 * pl->cg;
   pl->sb_count = (pl->rows + sb_rows - 1) / sb_rows;
   pl->col_tiles = (f->n_shows + 255) / 256;
@@ -121,14 +121,41 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
     if (pl->sb_per_group > pl->sb_count) pl->sb_per_group = pl->sb_count;
     pl->grid = pl->sb_per_group * pl->splits * pl->cg;
     pl->tiles_per_split = (pl->col_tiles + pl->splits - 1) / pl->splits;
+    // Symmetric mode: hybrid(i,j) == hybrid(j,i), so only tiles on or above the diagonal are
+    // computed and each score is offered to both shows.  Needs the whole catalogue in one shard,
+    // CTA pairs (256-row super block == 256-column tile), packed groups with non-negative weights
+    // and a positive threshold (so that every dropped U <= theta_init is below min_similarity).
+    const int sym_req = (tune >> 20) & 0x3;
+    const bool eligible = pl->cg == 2 && p->row_begin == 0 && p->row_end == f->n_shows &&
+                          f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED &&
+                          p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0 &&
+                          p->min_similarity > 1e-30 && pl->kp <= 64 && p->exclude_self;
+    if (sym_req == 2) TVBF_REQUIRE(eligible, "symmetric mode requested but the job is not eligible");
+    // auto: worth it once the triangle is large (measured: C2, 79 tiles, is 15 % slower; C3, 391
+    // tiles, 1.5x faster)
+    pl->sym = (sym_req == 2 || (sym_req == 0 && eligible && pl->col_tiles >= 160)) ? 1 : 0;
+    if (pl->sym && p->splits <= 0) {
+      // the symmetric sweep keeps ONE shared list per show, so rescoring does not grow with the
+      // split count; more splits = fewer phantom tiles under the diagonal
+      pl->splits = 8;
+      while (pl->splits > 1 && (clusters / pl->splits < 1 || pl->col_tiles / pl->splits < 8)) --pl->splits;
+      pl->sb_per_group = clusters / pl->splits;
+      if (pl->sb_per_group > pl->sb_count) pl->sb_per_group = pl->sb_count;
+      pl->grid = pl->sb_per_group * pl->splits * pl->cg;
+      pl->tiles_per_split = (pl->col_tiles + pl->splits - 1) / pl->splits;
+    }
   }
+  pl->cand_lists = pl->sym ? 1 : pl->splits;
   pl->k6_grid = 2 * sms;
   if (pl->k6_grid > pl->rows) pl->k6_grid = pl->rows;
   size_t off = 0;
   pl->off_scratch = off; off = align_up(off + (use_k1 ? static_cast<size_t>(pl->grid) * 128 * 32 * pl->entries * 8 : 0), 256);
-  pl->off_cand = off;    off = align_up(off + (use_k1 ? static_cast<size_t>(pl->rows) * pl->splits * pl->kp * 8 : 0), 256);
-  pl->off_cnt = off;     off = align_up(off + static_cast<size_t>(pl->rows) * pl->splits * 4, 256);
-  pl->off_theta = off;   off = align_up(off + static_cast<size_t>(pl->rows) * pl->splits * 4, 256);
+  pl->off_cand = off;    off = align_up(off + (use_k1 ? static_cast<size_t>(pl->rows) * pl->cand_lists * pl->kp * 8 : 0), 256);
+  pl->off_cnt = off;     off = align_up(off + static_cast<size_t>(pl->rows) * pl->cand_lists * 4, 256);
+  pl->off_theta = off;   off = align_up(off + static_cast<size_t>(pl->rows) * pl->cand_lists * 4, 256);
+  pl->off_gtheta = off;  off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * 4 : 0), 256);
+  pl->off_gcnt = off;    off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * 4 : 0), 256);
+  pl->off_glist = off;   off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * pl->sym_cap * 8 : 0), 256);
   pl->off_flag = off;    off = align_up(off + static_cast<size_t>(pl->rows) * 4, 256);
   pl->off_count = off;   off = align_up(off + 256, 256);
   pl->off_keys = off;    off = align_up(off + static_cast<size_t>(pl->k6_grid) * f->n_shows * 8, 256);
@@ -259,8 +286,19 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   kp.sync_kb = pl.sync_kb;
   kp.sync_slack = pl.sync_slack;
   kp.stages = pl.stages;
-  kp.prefetch_kb = pl.prefetch_kb;
-  kp.prefetch_mode = pl.prefetch_mode;
+  kp.sym = pl.sym;
+  kp.tile_stride = 1;
+  kp.seed_theta = 0;
+  if (pl.sym) {
+    // bits 22-27 of tuning: column-tile stride of the threshold seed pass (0 = 48, 63 = no seeding)
+    const int st_req = (p->tuning >> 22) & 0x3F;
+    kp.tile_stride = st_req == 0 ? 48 : (st_req == 63 ? 1 : st_req);
+    if (kp.tile_stride > pl.col_tiles) kp.tile_stride = pl.col_tiles > 1 ? pl.col_tiles : 1;
+  }
+  kp.sym_cap = pl.sym_cap;
+  kp.g_theta = reinterpret_cast<unsigned int*>(ws + pl.off_gtheta);
+  kp.g_cnt = reinterpret_cast<unsigned int*>(ws + pl.off_gcnt);
+  kp.g_list = reinterpret_cast<uint2*>(ws + pl.off_glist);
   kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
   kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
   kp.kp = pl.kp;
@@ -293,8 +331,12 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     rc = tvbf::k1_launch(f, kp, pl.entries, pl.cg, pl.grid, st);
     if (rc != TVBF_OK) return rc;
   }
+  if ((phases & 2) && pl.sym) {
+    rc = tvbf::k4s_launch(kp, pl.rows, st);
+    if (rc != TVBF_OK) return rc;
+  }
   if (phases & 2) {
-    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.splits, pl.kp, p->row_begin,
+    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.cand_lists, pl.kp, p->row_begin,
                          pl.rows, *out, flagged, st);
     if (rc != TVBF_OK) return rc;
   }
@@ -389,6 +431,7 @@ static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float*
   kp.rb_count = 1;
   kp.rb_per_group = 1;
   kp.tiles_per_split = 1;
+  kp.tile_stride = 1;
   kp.stages = cg == 2 ? 6 : 4;
   kp.dump_col0 = col0;
   kp.kp = 32;

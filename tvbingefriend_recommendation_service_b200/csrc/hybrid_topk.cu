@@ -48,7 +48,8 @@ struct Smem {
   static constexpr uint32_t OFF_B = OFF_A + STAGES * A_BYTES;
   static constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
-  static constexpr uint32_t OFF_BAR = OFF_MS + 2 * MS_BYTES;
+  static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
+  static constexpr uint32_t OFF_BAR = OFF_TH + 2 * MS_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr uint32_t USED = OFF_TMEM + 16;
@@ -131,9 +132,10 @@ __device__ __noinline__ float warp_compact(const uint2* src, int n, uint2* dst, 
 }
 
 struct ItemCoord {
-  int sb;      // super block (128*CG rows) within the shard, -1 = nothing to do
+  int sb;            // super block (128*CG rows) within the shard, -1 = nothing to do
   int split;
-  int tile0, tile1;
+  int tile0, tile1;  // tiles this item walks (pacing); every item of a group walks equally many
+  int real0, real1;  // ... of which [real0, real1) are computed, the rest are phantom
 };
 
 __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
@@ -143,12 +145,48 @@ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
   ItemCoord c;
   c.split = w / p.rb_per_group;
   c.sb = g * p.rb_per_group + (w - c.split * p.rb_per_group);
-  if (c.sb >= p.rb_count) c.sb = -1;
-  // every split walks tiles_per_split tiles so that all CTAs stay in step; tiles at or past
-  // col_tiles are phantom (no loads, no MMA, no epilogue)
-  c.tile0 = c.split * p.tiles_per_split;
-  c.tile1 = c.tile0 + p.tiles_per_split;
+  if (p.sym) {
+    // the group's super blocks are tiles [i0, i0 + R) of the diagonal; only columns >= i0 matter
+    const int i0 = g * p.rb_per_group;
+    const int span = p.col_tiles - i0;
+    const int tps = (span + p.splits - 1) / p.splits;
+    c.tile0 = i0 + c.split * tps;
+    c.tile1 = c.tile0 + tps;
+  } else {
+    c.tile0 = c.split * p.tiles_per_split;
+    c.tile1 = c.tile0 + p.tiles_per_split;
+  }
+  c.real0 = c.tile0;
+  c.real1 = c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles;
+  if (p.sym && c.sb > c.real0) c.real0 = c.sb;  // tiles left of the diagonal are the mirror's job
+  if (c.sb >= p.rb_count) { c.sb = -1; c.real0 = c.real1 = c.tile1; }
+  if (c.real0 > c.real1) c.real0 = c.real1;
   return c;
+}
+
+// ---- symmetric mode helpers ---------------------------------------------------------------------
+// Raise the shared threshold of one show to the kp-th largest score of the first n entries of its
+// list (n a power of two <= 1024).  Entries reserved but not yet written read as 0 = -inf, so the
+// result can only be too LOW, never too high.  Warp-cooperative, deliberately not inlined.
+__device__ __noinline__ void sym_refresh_theta(const uint2* list, int n, int kp,
+                                               unsigned int* theta_slot, int lane) {
+  uint32_t v[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int idx = q * 32 + lane;
+    v[q] = idx < n ? __ldcg(list + idx).x : 0u;
+  }
+  uint32_t best = 0u;  // largest t with count(v >= t) >= kp  ==  kp-th largest value
+#pragma unroll 1
+  for (int bit = 30; bit >= 0; --bit) {
+    const uint32_t t = best | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) c += (v[q] >= t);
+    c = __reduce_add_sync(kFullMask, c);
+    if (c >= kp) best = t;
+  }
+  if (lane == 0) atomicMax(theta_slot, best);
 }
 
 // Grid-wide pacing of the TMA producers.  Operand tiles are shared between CTAs only through L2
@@ -183,7 +221,7 @@ struct Pacer {
   }
 };
 
-template <int E, bool kDump, int CG>
+template <int E, bool kDump, int CG, bool kSym>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
@@ -250,13 +288,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         ItemCoord c = item_coord(p, item);
         if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
         const int row0 = p.row_begin + (kDump ? 0 : c.sb * BM * CG) + static_cast<int>(cta_rank) * BM;
-        // who prefetches: everyone (mode 1), or one CTA per shared stream (mode 2): the A rows of a
-        // super block are streamed by `splits` clusters, the B tiles of a split by rb_per_group
-        const bool pf_a = p.prefetch_mode == 1 || (p.prefetch_mode == 2 && c.split == 0);
-        const bool pf_b = p.prefetch_mode == 1 ||
-                          (p.prefetch_mode == 2 && c.sb >= 0 && (c.sb % p.rb_per_group) == 0);
-        for (int jt = c.tile0; jt < c.tile1; ++jt) {
-          if (c.sb < 0 || (!kDump && jt >= p.col_tiles)) {
+        for (int jt = c.tile0; jt < c.tile1; jt += p.tile_stride) {
+          if (!kDump && (jt < c.real0 || jt >= c.real1)) {
             // phantom tile: keep the pacing counter moving, touch nothing else
             for (int ch = 0; ch < chunks_per_tile; ++ch) {
               pacer.wait_turn();
@@ -269,9 +302,11 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (!kDump) {
             mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             if (elect_one()) {
-              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES);
+              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + (kSym ? MS_BYTES : 0u));
               bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
               bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
+              if (kSym)  // snapshot of the column shows' thresholds (stale = lower = conservative)
+                bulk_load_1d(smem + L::OFF_TH + b * MS_BYTES, p.g_theta + col0, MS_BYTES, &col_full[b]);
             }
             __syncwarp();
           }
@@ -280,16 +315,6 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (p.sync_kb > 0 && kb % p.sync_kb == 0) {
               if (kb) pacer.done_chunk(lane == 0);
               pacer.wait_turn();
-            }
-            if (p.prefetch_kb > 0 && lane == 0) {
-              // pull operands that will be needed prefetch_kb k-blocks from now into L2
-              int t = kb + p.prefetch_kb, pj = jt;
-              if (t >= p.k_blocks) { t -= p.k_blocks; ++pj; }
-              const int pend = c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles;
-              if (t < p.k_blocks && pj < pend) {
-                if (pf_a) tma_prefetch_2d(&tmap_a, t * BK, row0);
-                if (pf_b) tma_prefetch_2d(&tmap_b, t * BK, pj * BN + static_cast<int>(cta_rank) * static_cast<int>(L::B_ROWS));
-              }
             }
             mbar_wait(&empty[stage], phase ^ 1);
             if (elect_one()) {
@@ -326,8 +351,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         ItemCoord c = item_coord(p, item);
         if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
         if (c.sb < 0) continue;
-        const int tile_end = kDump ? c.tile1 : (c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles);
-        for (int jt = c.tile0; jt < tile_end; ++jt, ++it) {
+        const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
+        for (int jt = tile_beg; jt < tile_end; jt += p.tile_stride, ++it) {
           const uint32_t b = it & 1;
           mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // every epilogue drained accumulator b
           tc_fence_after();
@@ -393,18 +418,44 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int self_col = p.exclude_self ? row : -1;
       const float w_text = p.w_text, w_text_err = p.w_text_err, eps = p.eps;
       const bool hstack = p.meta_hstack != 0;
+      // symmetric mode: pending threshold refreshes (show, list length) raised by this lane
+      int pend_r = -1, pend_n = 0, pend2_r = -1, pend2_n = 0;
+      const unsigned sym_cap = static_cast<unsigned>(p.sym_cap);
+      const unsigned sym_first = static_cast<unsigned>(2 * p.kp);
 
-      const int tile_end = kDump ? c.tile1 : (c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles);
-      for (int jt = c.tile0; jt < tile_end; ++jt, ++it) {
+      // append (score, other) to the shared list of `show`; remember a refresh when the list
+      // length reaches 2*kp, 4*kp, ... (power-of-two lengths)
+      auto sym_append = [&](int show, float u, int other, int& pr, int& pn) {
+        const unsigned pos = atomicAdd(p.g_cnt + show, 1u);
+        if (pos < sym_cap) {
+          __stcg(p.g_list + static_cast<size_t>(show) * sym_cap + pos,
+                 make_uint2(__float_as_uint(u), static_cast<uint32_t>(other)));
+          const unsigned np = pos + 1u;
+          if (np >= sym_first && (np & pos) == 0u) { pr = show; pn = static_cast<int>(np); }
+        }
+      };
+
+      const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
+      for (int jt = tile_beg; jt < tile_end; jt += p.tile_stride, ++it) {
         const uint32_t b = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int col0 = kDump ? p.dump_col0 : jt * BN;
+        if (kSym) {
+          // current shared threshold of this thread's show (raised by any CTA working on it)
+          unsigned int tb = 0x7f800000u;
+          if (row_valid)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
+          theta = __uint_as_float(tb);
+        }
         if (!kDump) mbar_wait(&col_full[b], ph);
         mbar_wait(&acc_full[b], ph);
         tc_fence_after();
         const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + L::OFF_COL + b * COL_BYTES);
         const float* sms = reinterpret_cast<const float*>(smem + L::OFF_MS + b * MS_BYTES);
+        const float* sth = reinterpret_cast<const float*>(smem + L::OFF_TH + b * MS_BYTES);
         const uint32_t taddr = tmem_base + tmem_lane + b * BN;
+        // off-diagonal tiles also feed the column shows (their mirror tile is never computed)
+        const bool do_col = kSym && row_valid && jt != c.sb;
 
         // score 16 accumulator columns held in registers
         auto score16 = [&](const uint32_t (&acc)[16], int cbase) {
@@ -421,8 +472,12 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               float u = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
               u = fmaf(a, w_text, u);
               u = fmaf(fabsf(a), w_text_err, u);
-              if (u > theta) {
-                const int col = col0 + cbase + e;
+              const int col = col0 + cbase + e;
+              if (kSym) {
+                if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col, pend_r, pend_n);
+                // padded columns carry threshold +inf, so no bound check is needed here
+                if (do_col && u > sth[cbase + e]) sym_append(col, u, row, pend2_r, pend2_n);
+              } else if (u > theta) {
                 if (col != self_col && col < p.n_shows) {
                   __stcg(my_list + cnt, make_uint2(__float_as_uint(u), static_cast<uint32_t>(col)));
                   ++cnt;
@@ -452,7 +507,32 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive(&acc_empty[b]);
           }
           score16(acc_b, (ch + 1) * 16);
-          if (!kDump) {
+          if (kSym) {
+            // serve the threshold refreshes raised in these 32 columns, one show at a time
+            unsigned need = __ballot_sync(kFullMask, pend_n != 0);
+            while (need) {
+              const int src_lane = __ffs(need) - 1;
+              need &= need - 1;
+              const int show = __shfl_sync(kFullMask, pend_r, src_lane);
+              const int n = __shfl_sync(kFullMask, pend_n, src_lane);
+              sym_refresh_theta(p.g_list + static_cast<size_t>(show) * sym_cap, n, p.kp, p.g_theta + show, lane);
+            }
+            pend_n = 0;
+            need = __ballot_sync(kFullMask, pend2_n != 0);
+            while (need) {
+              const int src_lane = __ffs(need) - 1;
+              need &= need - 1;
+              const int show = __shfl_sync(kFullMask, pend2_r, src_lane);
+              const int n = __shfl_sync(kFullMask, pend2_n, src_lane);
+              sym_refresh_theta(p.g_list + static_cast<size_t>(show) * sym_cap, n, p.kp, p.g_theta + show, lane);
+            }
+            pend2_n = 0;
+            if (row_valid) {  // pick up raises made by other CTAs (and by the refreshes above)
+              unsigned int tb;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
+              theta = __uint_as_float(tb);
+            }
+          } else if (!kDump) {
             // keep 32 free slots for the next 32 columns; compact rows that are nearly full
             unsigned need = __ballot_sync(kFullMask, cnt > CAP - 32);
             while (need) {
@@ -473,7 +553,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (!kDump) mbar_arrive(&col_empty[b]);  // column-side buffer b may be refilled
       }
 
-      if (!kDump) {
+      if (!kDump && !kSym) {
         // final compaction of every row of this warp: sorted best-kp list -> cand
         const int rows_in_shard = p.row_end - p.row_begin;
         for (int src_lane = 0; src_lane < 32; ++src_lane) {
@@ -482,6 +562,14 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint2* lp = reinterpret_cast<const uint2*>(__shfl_sync(
               kFullMask, reinterpret_cast<unsigned long long>(my_list), src_lane));
           const int n = __shfl_sync(kFullMask, cnt, src_lane);
+          if (p.seed_theta) {
+            // sampled sweep: the kp-th best sampled score is a valid lower bound of the show's
+            // final threshold; it spares the symmetric sweep its warm-up flood of appends
+            const float bound = warp_compact<E>(lp, n, const_cast<uint2*>(lp), p.kp, lane);
+            if (lane == src_lane && n >= p.kp && bound > p.theta_init)
+              p.g_theta[p.row_begin + r] = __float_as_uint(bound);
+            continue;
+          }
           uint2* dst = p.cand + (static_cast<size_t>(r) * p.splits + c.split) * p.kp;
           const float bound = warp_compact<E>(lp, n, dst, p.kp, lane);
           if (lane == src_lane) {
@@ -502,6 +590,70 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);
   }
+}
+
+// K4s: symmetric mode -- one warp per show: keep the kp best entries of its shared list as the
+// candidate set and derive the bound on everything that is not in it.
+__global__ void __launch_bounds__(128)
+sym_compact_kernel(const K1Params p, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const unsigned total = p.g_cnt[r];
+  const int n = static_cast<int>(total < static_cast<unsigned>(p.sym_cap) ? total : p.sym_cap);
+  const uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
+  uint32_t v[32], cidx[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int idx = q * 32 + lane;
+    uint2 e = make_uint2(0u, 0u);
+    if (idx < n) e = __ldcg(list + idx);
+    v[q] = idx < n ? e.x : 0u;
+    cidx[q] = e.y;
+  }
+  const int kp = p.kp;
+  uint32_t best = 0u;  // kp-th largest score bits (0 when n < kp)
+  if (n > kp) {
+#pragma unroll 1
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t t = best | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) c += (v[q] >= t);
+      c = __reduce_add_sync(kFullMask, c);
+      if (c >= kp) best = t;
+    }
+  }
+  // entries strictly above the kp-th value always fit; entries equal to it fill the rest
+  uint2* dst = p.cand + static_cast<size_t>(r) * kp;
+  int out = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int idx = q * 32 + lane;
+      const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
+      const unsigned bal = __ballot_sync(kFullMask, take);
+      const int pos = out + __popc(bal & ((1u << lane) - 1u));
+      if (take && pos < kp) dst[pos] = make_uint2(v[q], cidx[q]);
+      out += __popc(bal);
+    }
+    if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
+  }
+  if (lane == 0) {
+    const unsigned int th_bits = p.g_theta[r];
+    float bound = __int_as_float(0xff800000);                        // nothing dropped so far
+    if (th_bits > __float_as_uint(p.theta_init)) bound = __uint_as_float(th_bits);  // elements were rejected
+    if (n > kp) bound = fmaxf(bound, __uint_as_float(best));         // list entries cut here
+    if (total > static_cast<unsigned>(p.sym_cap)) bound = __int_as_float(0x7f800000);  // overflow: send to K6
+    p.cand_cnt[r] = n < kp ? n : kp;
+    p.cand_theta[r] = bound;
+  }
+}
+
+__global__ void sym_init_kernel(unsigned int* theta, int n_shows, int n_pad, float theta_init) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) theta[i] = i < n_shows ? __float_as_uint(theta_init) : 0x7f800000u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -587,7 +739,7 @@ int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
   return best;
 }
 
-template <int E, bool kDump, int CG>
+template <int E, bool kDump, int CG, bool kSym>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
   using L = Smem<CG>;
   CUtensorMap ta, tb;
@@ -595,7 +747,7 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   if (rc != TVBF_OK) return rc;
   rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump, CG>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG, kSym>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(L::BYTES)));
   const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
@@ -621,18 +773,45 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
 
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st) {
+  if (kp.sym) {
+    if (cta_group != 2) {
+      tvbf_set_error("symmetric mode needs cta_group 2");
+      return TVBF_ERR_INVALID;
+    }
+    const int n_pad = f->n_pad;
+    sym_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(kp.g_theta, f->n_shows, n_pad, kp.theta_init);
+    TVBF_LAUNCH_OK("sym_init_kernel");
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(n_pad) * 4, st));
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, static_cast<size_t>(n_pad) * kp.sym_cap * 8, st));
+    if (kp.tile_stride > 1) {
+      // seed pass: one-sided sweep over every tile_stride-th column tile, thresholds only
+      K1Params seed = kp;
+      seed.sym = 0;
+      seed.seed_theta = 1;
+      seed.splits = 1;
+      seed.tiles_per_split = kp.col_tiles;
+      const int clusters = grid / 2;
+      seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
+      int rc = launch_k1<4, false, 2, false>(f, seed, seed.rb_per_group * 2, st);
+      if (rc != TVBF_OK) return rc;
+      TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+    }
+    K1Params sweep = kp;
+    sweep.tile_stride = 1;
+    return launch_k1<4, false, 2, true>(f, sweep, grid, st);
+  }
   if (cta_group == 2) {
     switch (entries_per_lane) {
-      case 4: return launch_k1<4, false, 2>(f, kp, grid, st);
-      case 8: return launch_k1<8, false, 2>(f, kp, grid, st);
-      case 16: return launch_k1<16, false, 2>(f, kp, grid, st);
+      case 4: return launch_k1<4, false, 2, false>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 2, false>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 2, false>(f, kp, grid, st);
       default: break;
     }
   } else {
     switch (entries_per_lane) {
-      case 4: return launch_k1<4, false, 1>(f, kp, grid, st);
-      case 8: return launch_k1<8, false, 1>(f, kp, grid, st);
-      case 16: return launch_k1<16, false, 1>(f, kp, grid, st);
+      case 4: return launch_k1<4, false, 1, false>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 1, false>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 1, false>(f, kp, grid, st);
       default: break;
     }
   }
@@ -641,7 +820,14 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
 }
 
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st) {
-  return cta_group == 2 ? launch_k1<4, true, 2>(f, kp, 2, st) : launch_k1<4, true, 1>(f, kp, 1, st);
+  return cta_group == 2 ? launch_k1<4, true, 2, false>(f, kp, 2, st)
+                        : launch_k1<4, true, 1, false>(f, kp, 1, st);
+}
+
+int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st) {
+  sym_compact_kernel<<<(n_rows + 3) / 4, 128, 0, st>>>(kp, n_rows);
+  TVBF_LAUNCH_OK("sym_compact_kernel");
+  return TVBF_OK;
 }
 
 }  // namespace tvbf

@@ -28,8 +28,16 @@ struct K1Params {
   int sync_kb;         // producers pace themselves every sync_kb k-blocks (0 = no pacing)
   int sync_slack;      // ... staying at most this many chunks ahead of the slowest CTA
   int stages;          // smem ring depth actually used (<= compiled maximum)
-  int prefetch_kb;     // L2 prefetch distance in k-blocks (0 = off)
-  int prefetch_mode;   // 1: every CTA prefetches its operands; 2: one designated CTA per stream
+  // symmetric mode (hybrid(i,j) == hybrid(j,i)): only tiles on or above the diagonal are computed
+  // and every score is offered to BOTH shows' candidate lists, which therefore live in global
+  // memory and are shared by all CTAs
+  int sym;
+  int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
+  int seed_theta;          // one-sided sweep only seeds g_theta with the kp-th best sampled score
+  int sym_cap;             // entries per shared list
+  unsigned int* g_theta;   // [n_pad] raw bits of the (positive) float threshold of each show
+  unsigned int* g_cnt;     // [n_pad] appends so far (> sym_cap = overflow)
+  uint2* g_list;           // [n_pad][sym_cap] (score bits, column)
   int cooperative;     // launch with the cooperative attribute (co-residency guaranteed)
   int kp;              // candidates kept per (row, split)
   int exclude_self;
@@ -60,6 +68,7 @@ int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cu
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st);
+int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st);
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
               const tvbf_topk_out& out, cudaStream_t st);
