@@ -171,6 +171,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--splits", type=int, default=0)
+    ap.add_argument("--one-sided", action="store_true", help="disable the symmetric sweep at N > 1")
     ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
     args = ap.parse_args()
 
@@ -195,7 +196,8 @@ def main() -> None:
     import torch.distributed as dist
 
     from tvbingefriend_recommendation_service_b200.engine import HybridTopKEngine, stage
-    from tvbingefriend_recommendation_service_b200.sharding import empty_tables, gather_tables, row_shard
+    from tvbingefriend_recommendation_service_b200.multi_gpu import top_k_device_distributed
+    from tvbingefriend_recommendation_service_b200.sharding import row_shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
@@ -215,21 +217,20 @@ def main() -> None:
     peaks = _peaks()
 
     def step_device(timing: dict | None = None):
-        """prep + top-k of this rank's rows (+ gather); optionally brackets K1 with events."""
+        """prep + top-k (+ candidate exchange and gather when N > 1); optionally brackets K1."""
         dc = eng.prepare(raw, weights)
-        if re_ <= rb:
-            return gather_tables(empty_tables(k, eng.device), n, k) if world > 1 else None
-        if timing is None:
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, tuning=args.tuning)
-        else:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=1, tuning=args.tuning)
-            e1.record()
-            eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, phases=6, out=t, tuning=args.tuning)
-            timing.setdefault("k1", []).append((e0, e1))
         if world > 1:
-            t = gather_tables(t, n, k)
+            return top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
+                                            symmetric=None if not args.one_sided else False,
+                                            k1_events=None if timing is None else timing.setdefault("k1x", []))
+        if timing is None:
+            return eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=1, tuning=args.tuning)
+        e1.record()
+        eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=6, out=t, tuning=args.tuning)
+        timing.setdefault("k1", []).append((e0, e1))
         return t
 
     def sync():
@@ -259,6 +260,7 @@ def main() -> None:
     launches = eng.kernel_launches - launches0
     total_ms = ev0.elapsed_time(ev1)
     k1_ms = [a.elapsed_time(b) for a, b in timing.get("k1", [])]
+    k1_ms += [sum(a.elapsed_time(b) for a, b in step) for step in timing.get("k1x", [])]
     clocks = sampler.stop() if rank == 0 else None
     t_ms = torch.tensor([total_ms, float(np.mean(k1_ms)) if k1_ms else 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -270,12 +272,11 @@ def main() -> None:
     def step_e2e():
         raw2 = eng.h2d(st)
         dc = eng.prepare(raw2, weights)
-        if re_ > rb:
-            t = eng.top_k_device(dc, weights, k, 0.1, True, row_begin=rb, row_end=re_, splits=args.splits, tuning=args.tuning)
-        else:
-            t = empty_tables(k, eng.device)
         if world > 1:
-            t = gather_tables(t, n, k)
+            t = top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
+                                         symmetric=None if not args.one_sided else False)
+        else:
+            t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
         return eng.to_host(t, copy=False) if rank == 0 else None
 
     step_e2e()
@@ -298,8 +299,9 @@ def main() -> None:
             dist.destroy_process_group()
         return
 
-    rows_k1 = re_ - rb
-    flops = 2.0 * rows_k1 * n * cfg["vocab"]           # algorithmic: text contraction of this rank's rows
+    # algorithmic work of this GPU's share of the text contraction, counted as the reference
+    # computes it (all N x N pairs); the symmetric sweep executes about half of it
+    flops = 2.0 * n * n * cfg["vocab"] / world
     achieved = flops / (k1_ms_mean * 1e-3) / 1e12 if k1_ms_mean > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     line = {

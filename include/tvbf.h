@@ -154,6 +154,32 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
 size_t tvbf_topk_workspace_bytes(const tvbf_features* f, const tvbf_params* p);
 int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_topk_out* out,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* ---- the same job tile-sharded over several GPUs (symmetric sweep).  hybrid(i,j) == hybrid(j,i),
+ *      so GPU `rank` of `world` computes only the tiles on/above the diagonal of the 256-row super
+ *      blocks dealt to it and feeds BOTH shows of every score; it ends with partial candidate lists
+ *      for ALL shows.  Call sequence per GPU, with one small collective (done by the caller)
+ *      between the calls:
+ *        tvbf_sym_seed       theta[n_pad]                   -> all_reduce(MAX, uint32) of theta
+ *        tvbf_sym_sweep      cand[n_shows][L], cnt, bound   -> all_gather of the three arrays
+ *        tvbf_rescore_lists  rows [row_begin,row_end) of p  -> gather of the result tables
+ *      L = tvbf_sym_list_len(); eligibility (packed groups, non-negative weights, positive
+ *      min_similarity, k <= 48): tvbf_sym_eligible().  row_begin/row_end of p are ignored by the
+ *      first two calls. */
+int tvbf_sym_eligible(const tvbf_features* f, const tvbf_params* p);
+int32_t tvbf_sym_list_len(const tvbf_features* f, const tvbf_params* p);
+size_t tvbf_sym_workspace_bytes(const tvbf_features* f, const tvbf_params* p, int32_t world);
+int tvbf_sym_seed(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                  uint32_t* theta, void* workspace, size_t workspace_bytes, void* stream);
+int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                   uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* fp64 rescoring + certificate + exact repair of rows [p->row_begin, p->row_end) from `lists`
+ * gathered candidate tables laid out [lists][n_shows][L]. */
+int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void* cand_all,
+                       const int32_t* cnt_all, const float* bound_all, int32_t lists,
+                       const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* exact fp64 scoring of explicit source rows against all columns + exact top-K
  * (replaces get_recommendations_from_matrix, content_based_service.py:161-236, for any n). */
 size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed);

@@ -108,3 +108,36 @@ def test_single_process_multi_gpu_matches_single_gpu(engine):
     assert np.array_equal(one.indices, two.indices) and np.array_equal(one.counts, two.counts)
     m = one.indices >= 0
     assert np.array_equal(one.hybrid[m], two.hybrid[m])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world):
+    """The three-phase multi-GPU protocol (seed -> MAX-reduce -> sweep -> gather -> rescore) with the
+    ranks run one after the other on a single GPU; must give exactly the single-GPU table."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.engine import TopK, stage
+    from tvbingefriend_recommendation_service_b200.sharding import row_shard
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(6000, 1024, nnz=20, seed=31)
+    w, k, ms = (0.4, 0.5, 0.1), 20, 0.1
+    dc = engine.upload(stage(cat.features()), w)
+    assert engine.sym_eligible(dc, w, k, ms)
+    thetas = [engine.sym_seed(dc, w, k, ms, r, world) for r in range(world)]
+    theta = torch.stack(thetas).amax(dim=0)
+    parts = [engine.sym_sweep(dc, w, k, ms, r, world, theta.clone()) for r in range(world)]
+    cand_all = torch.stack([p[0] for p in parts])
+    cnt_all = torch.stack([p[1] for p in parts])
+    bound_all = torch.stack([p[2] for p in parts])
+    tabs = []
+    for r in range(world):
+        b, e = row_shard(6000, world, r)
+        tabs.append(engine.to_host(engine.sym_rescore(dc, w, k, ms, cand_all, cnt_all, bound_all, b, e)))
+    got = TopK(*(np.concatenate([getattr(t, f) for t in tabs]) for f in
+                 ("indices", "counts", "hybrid", "genre", "text", "metadata")))
+    ref = engine.to_host(engine.top_k_device(dc, w, k, ms, force_exact=True))
+    assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.counts, ref.counts)
+    m = ref.indices >= 0
+    assert np.array_equal(got.hybrid[m], ref.hybrid[m])
+    assert_topk_matches(got, cat.features(), np.arange(0, 6000, 97), w, k, ms)

@@ -74,6 +74,15 @@ SIGNATURES = {
     "tvbf_topk_workspace_bytes": (c_size_t, [C.POINTER(Features), C.POINTER(Params)]),
     "tvbf_hybrid_topk": (C.c_int, [C.POINTER(Features), C.POINTER(Params), C.POINTER(TopKOut),
                                    c_void_p, c_size_t, c_void_p]),
+    "tvbf_sym_eligible": (C.c_int, [C.POINTER(Features), C.POINTER(Params)]),
+    "tvbf_sym_list_len": (c_int32, [C.POINTER(Features), C.POINTER(Params)]),
+    "tvbf_sym_workspace_bytes": (c_size_t, [C.POINTER(Features), C.POINTER(Params), c_int32]),
+    "tvbf_sym_seed": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, c_int32, c_void_p, c_void_p,
+                                c_size_t, c_void_p]),
+    "tvbf_sym_sweep": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, c_int32, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tvbf_rescore_lists": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_void_p, c_void_p, c_int32,
+                                     C.POINTER(TopKOut), c_void_p, c_size_t, c_void_p]),
     "tvbf_exact_workspace_bytes": (c_size_t, [C.POINTER(Features), c_int32]),
     "tvbf_exact_rows": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_int32,
                                   C.POINTER(TopKOut), c_void_p, c_size_t, c_void_p]),

@@ -182,6 +182,91 @@ double default_text_rel_err(int dtype) {
   return (2.0 * u + u * u) * 1.01 + 1.0 / 262144.0;
 }
 
+// Everything the candidate kernel needs besides the launch geometry: pointers into the workspace,
+// the fp32 weights of the epilogue and the slack terms of the upper bound U.
+int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl, uint8_t* ws,
+                   tvbf::K1Params* out_kp) {
+  const int s = f->text_scale_log2;
+  const double inv_scale2 = std::ldexp(1.0, -2 * s);
+  const double rel = p->text_rel_err > 0 ? p->text_rel_err : default_text_rel_err(f->text_dtype);
+  // folded groups live inside the accumulator already weighted; their error is bounded
+  // absolutely (Cauchy-Schwarz on unit rows): |err| <= rel * weight
+  double folded_w = 0.0;
+  if (f->genre_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->genre_weight);
+  if (f->meta_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->metadata_weight);
+  const bool any_folded = folded_w > 0.0;
+  const double wsum = std::fabs(p->genre_weight) + std::fabs(p->text_weight) + std::fabs(p->metadata_weight);
+  if (any_folded) {
+    TVBF_REQUIRE(p->text_weight > 0.0, "folded feature groups need text_weight > 0");
+    TVBF_REQUIRE(p->genre_weight >= 0.0 && p->metadata_weight >= 0.0,
+                 "folded feature groups need non-negative weights");
+  }
+
+  tvbf::K1Params& kp = *out_kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.col_side = static_cast<const TvbfColSide*>(f->col_side);
+  kp.meta_scale = f->meta_scale;
+  kp.scratch = reinterpret_cast<uint2*>(ws + pl.off_scratch);
+  kp.cand = reinterpret_cast<uint2*>(ws + pl.off_cand);
+  kp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
+  kp.cand_theta = reinterpret_cast<float*>(ws + pl.off_theta);
+  kp.n_shows = f->n_shows;
+  kp.row_begin = p->row_begin;
+  kp.row_end = p->row_end;
+  kp.k_blocks = f->k_pad / 64;
+  kp.col_tiles = pl.col_tiles;
+  kp.splits = pl.splits;
+  kp.rb_count = pl.sb_count;
+  kp.rb_per_group = pl.sb_per_group;
+  kp.tiles_per_split = pl.tiles_per_split;
+  kp.sync_kb = pl.sync_kb;
+  kp.sync_slack = pl.sync_slack;
+  kp.stages = pl.stages;
+  kp.sym = pl.sym;
+  kp.sb_world = 1;
+  kp.sb_rank = 0;
+  kp.tile_stride = 1;
+  kp.seed_theta = 0;
+  if (pl.sym) {
+    // bits 22-27 of tuning: column-tile stride of the threshold seed pass (0 = 48, 63 = no seeding)
+    const int st_req = (p->tuning >> 22) & 0x3F;
+    kp.tile_stride = st_req == 0 ? 48 : (st_req == 63 ? 1 : st_req);
+    if (kp.tile_stride > pl.col_tiles) kp.tile_stride = pl.col_tiles > 1 ? pl.col_tiles : 1;
+  }
+  kp.sym_cap = pl.sym_cap;
+  kp.g_theta = reinterpret_cast<unsigned int*>(ws + pl.off_gtheta);
+  kp.g_cnt = reinterpret_cast<unsigned int*>(ws + pl.off_gcnt);
+  kp.g_list = reinterpret_cast<uint2*>(ws + pl.off_glist);
+  kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
+  kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
+  kp.kp = pl.kp;
+  kp.exclude_self = p->exclude_self;
+  if (any_folded) {
+    // operand columns were scaled by 2^s * sqrt(w_group / text_weight): acc * text_weight * 2^-2s
+    // is the whole folded part of the hybrid; bound the error absolutely.
+    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
+    kp.w_text_err = 0.0f;
+    kp.eps = static_cast<float>(rel * (std::fabs(p->text_weight) + folded_w) + 4e-6 * (wsum + 1.0));
+  } else {
+    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
+    kp.w_text_err = static_cast<float>(std::fabs(p->text_weight) * inv_scale2 * rel);
+    kp.eps = static_cast<float>(4e-6 * (wsum + 1.0));
+  }
+  kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
+  kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight) : 0.0f;
+  kp.meta_hstack = f->meta_kind == TVBF_META_HSTACK ? 1 : 0;
+  {
+    // strictly below min_similarity in fp32 so that U >= min_similarity always passes "U > theta"
+    const double ms = p->min_similarity;
+    float th = static_cast<float>(ms);
+    if (!(ms > -3.0e38)) th = -3.0e38f;
+    th = std::nextafterf(th, -INFINITY);
+    if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
+    kp.theta_init = th;
+  }
+  return TVBF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -250,82 +335,9 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     return TVBF_OK;
   }
 
-  const int s = f->text_scale_log2;
-  const double inv_scale2 = std::ldexp(1.0, -2 * s);
-  const double rel = p->text_rel_err > 0 ? p->text_rel_err : default_text_rel_err(f->text_dtype);
-  // folded groups live inside the accumulator already weighted; their error is bounded
-  // absolutely (Cauchy-Schwarz on unit rows): |err| <= rel * weight
-  double folded_w = 0.0;
-  if (f->genre_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->genre_weight);
-  if (f->meta_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->metadata_weight);
-  const bool any_folded = folded_w > 0.0;
-  const double wsum = std::fabs(p->genre_weight) + std::fabs(p->text_weight) + std::fabs(p->metadata_weight);
-  if (any_folded) {
-    TVBF_REQUIRE(p->text_weight > 0.0, "folded feature groups need text_weight > 0");
-    TVBF_REQUIRE(p->genre_weight >= 0.0 && p->metadata_weight >= 0.0,
-                 "folded feature groups need non-negative weights");
-  }
-
   tvbf::K1Params kp;
-  memset(&kp, 0, sizeof(kp));
-  kp.col_side = static_cast<const TvbfColSide*>(f->col_side);
-  kp.meta_scale = f->meta_scale;
-  kp.scratch = reinterpret_cast<uint2*>(ws + pl.off_scratch);
-  kp.cand = reinterpret_cast<uint2*>(ws + pl.off_cand);
-  kp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
-  kp.cand_theta = reinterpret_cast<float*>(ws + pl.off_theta);
-  kp.n_shows = f->n_shows;
-  kp.row_begin = p->row_begin;
-  kp.row_end = p->row_end;
-  kp.k_blocks = f->k_pad / 64;
-  kp.col_tiles = pl.col_tiles;
-  kp.splits = pl.splits;
-  kp.rb_count = pl.sb_count;
-  kp.rb_per_group = pl.sb_per_group;
-  kp.tiles_per_split = pl.tiles_per_split;
-  kp.sync_kb = pl.sync_kb;
-  kp.sync_slack = pl.sync_slack;
-  kp.stages = pl.stages;
-  kp.sym = pl.sym;
-  kp.tile_stride = 1;
-  kp.seed_theta = 0;
-  if (pl.sym) {
-    // bits 22-27 of tuning: column-tile stride of the threshold seed pass (0 = 48, 63 = no seeding)
-    const int st_req = (p->tuning >> 22) & 0x3F;
-    kp.tile_stride = st_req == 0 ? 48 : (st_req == 63 ? 1 : st_req);
-    if (kp.tile_stride > pl.col_tiles) kp.tile_stride = pl.col_tiles > 1 ? pl.col_tiles : 1;
-  }
-  kp.sym_cap = pl.sym_cap;
-  kp.g_theta = reinterpret_cast<unsigned int*>(ws + pl.off_gtheta);
-  kp.g_cnt = reinterpret_cast<unsigned int*>(ws + pl.off_gcnt);
-  kp.g_list = reinterpret_cast<uint2*>(ws + pl.off_glist);
-  kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
-  kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
-  kp.kp = pl.kp;
-  kp.exclude_self = p->exclude_self;
-  if (any_folded) {
-    // operand columns were scaled by 2^s * sqrt(w_group / text_weight): acc * text_weight * 2^-2s
-    // is the whole folded part of the hybrid; bound the error absolutely.
-    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
-    kp.w_text_err = 0.0f;
-    kp.eps = static_cast<float>(rel * (std::fabs(p->text_weight) + folded_w) + 4e-6 * (wsum + 1.0));
-  } else {
-    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
-    kp.w_text_err = static_cast<float>(std::fabs(p->text_weight) * inv_scale2 * rel);
-    kp.eps = static_cast<float>(4e-6 * (wsum + 1.0));
-  }
-  kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
-  kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight) : 0.0f;
-  kp.meta_hstack = f->meta_kind == TVBF_META_HSTACK ? 1 : 0;
-  {
-    // strictly below min_similarity in fp32 so that U >= min_similarity always passes "U > theta"
-    const double ms = p->min_similarity;
-    float th = static_cast<float>(ms);
-    if (!(ms > -3.0e38)) th = -3.0e38f;
-    th = std::nextafterf(th, -INFINITY);
-    if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
-    kp.theta_init = th;
-  }
+  rc = fill_k1_params(f, p, pl, ws, &kp);
+  if (rc != TVBF_OK) return rc;
   if (phases & 1) {
     TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
     rc = tvbf::k1_launch(f, kp, pl.entries, pl.cg, pl.grid, st);
@@ -336,8 +348,9 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (rc != TVBF_OK) return rc;
   }
   if (phases & 2) {
-    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.cand_lists, pl.kp, p->row_begin,
-                         pl.rows, *out, flagged, st);
+    const tvbf::CandLayout lay{0, pl.cand_lists, 1};
+    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.cand_lists, lay, pl.kp,
+                         p->row_begin, pl.rows, *out, flagged, st);
     if (rc != TVBF_OK) return rc;
   }
   if ((phases & 4) && !p->skip_fallback) {
@@ -345,6 +358,189 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (rc != TVBF_OK) return rc;
   }
   return TVBF_OK;
+}
+
+// ---- symmetric sweep over several GPUs ---------------------------------------------------------
+// Tile sharding instead of row sharding: GPU `rank` of `world` owns the 256-row super blocks dealt
+// to it in zigzag order and sweeps their tiles on/above the diagonal, feeding the candidate lists of
+// BOTH shows of every score, so it ends up with partial lists for ALL shows.  Three calls with one
+// small collective between each (done by the caller, e.g. NCCL through torch.distributed):
+//   tvbf_sym_seed   -> all_reduce(MAX) of theta[n_pad] (uint32)
+//   tvbf_sym_sweep  -> all_gather of cand / cand_cnt / cand_bound
+//   tvbf_rescore_lists (own row shard) -> gather of the result tables
+namespace {
+
+struct SymPlan {
+  Plan pl;            // geometry of a full-catalogue symmetric job
+  int local_sb;       // super blocks owned by this rank
+  size_t off_prog, off_scratch, off_gcnt, off_glist, off_flag, off_keys, total;
+};
+
+int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int world, SymPlan* sp) {
+  TVBF_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+  tvbf_params q = *p;
+  q.row_begin = 0;
+  q.row_end = f->n_shows;
+  q.tuning = (q.tuning & ~(0x3 << 20)) | (2 << 20);   // symmetric mode on (or fail if ineligible)
+  q.tuning = (q.tuning & ~0xF) | 2;                   // CTA pairs
+  int rc = validate_params(f, &q);
+  if (rc != TVBF_OK) return rc;
+  rc = make_plan(f, &q, &sp->pl);
+  if (rc != TVBF_OK) return rc;
+  Plan& pl = sp->pl;
+  int sms = 0;
+  rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  const int clusters = sms / 2;
+  sp->local_sb = tvbf::k1_local_super_blocks(pl.sb_count, world, rank);
+  pl.sb_per_group = clusters / pl.splits;
+  if (pl.sb_per_group > sp->local_sb) pl.sb_per_group = sp->local_sb > 0 ? sp->local_sb : 1;
+  pl.grid = pl.sb_per_group * pl.splits * 2;
+  const int k6_grid = 2 * sms;
+  size_t off = 0;
+  sp->off_prog = off;    off = align_up(off + 256, 256);
+  sp->off_scratch = off; off = align_up(off + static_cast<size_t>(sms) * 128 * 32 * 4 * 8, 256);
+  sp->off_gcnt = off;    off = align_up(off + static_cast<size_t>(f->n_pad) * 4, 256);
+  sp->off_glist = off;   off = align_up(off + static_cast<size_t>(f->n_pad) * pl.sym_cap * 8, 256);
+  sp->off_flag = off;    off = align_up(off + static_cast<size_t>(f->n_shows) * 4, 256);
+  sp->off_keys = off;    off = align_up(off + static_cast<size_t>(k6_grid) * f->n_shows * 8, 256);
+  sp->total = off;
+  return TVBF_OK;
+}
+
+int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan& sp, int rank, int world,
+                    uint8_t* ws, uint32_t* theta, tvbf::K1Params* kp) {
+  tvbf_params q = *p;
+  q.row_begin = 0;
+  q.row_end = f->n_shows;
+  int rc = fill_k1_params(f, &q, sp.pl, ws, kp);
+  if (rc != TVBF_OK) return rc;
+  kp->scratch = reinterpret_cast<uint2*>(ws + sp.off_scratch);
+  kp->progress = reinterpret_cast<unsigned int*>(ws + sp.off_prog);
+  kp->g_theta = theta;
+  kp->g_cnt = reinterpret_cast<unsigned int*>(ws + sp.off_gcnt);
+  kp->g_list = reinterpret_cast<uint2*>(ws + sp.off_glist);
+  kp->cand = nullptr;
+  kp->cand_cnt = nullptr;
+  kp->cand_theta = nullptr;
+  kp->rb_count = sp.local_sb;
+  kp->rb_per_group = sp.pl.sb_per_group;
+  kp->sb_world = world;
+  kp->sb_rank = rank;
+  return TVBF_OK;
+}
+
+}  // namespace
+
+int tvbf_sym_eligible(const tvbf_features* f, const tvbf_params* p) {
+  if (validate_features(f) != TVBF_OK || p == nullptr) return 0;
+  SymPlan sp;
+  return make_sym_plan(f, p, 0, 1, &sp) == TVBF_OK ? 1 : 0;
+}
+
+int32_t tvbf_sym_list_len(const tvbf_features* f, const tvbf_params* p) {
+  SymPlan sp;
+  if (validate_features(f) != TVBF_OK || make_sym_plan(f, p, 0, 1, &sp) != TVBF_OK) return 0;
+  return sp.pl.kp;
+}
+
+size_t tvbf_sym_workspace_bytes(const tvbf_features* f, const tvbf_params* p, int32_t world) {
+  SymPlan sp;
+  if (validate_features(f) != TVBF_OK || make_sym_plan(f, p, 0, world, &sp) != TVBF_OK) return 0;
+  return sp.total;
+}
+
+int tvbf_sym_seed(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                  uint32_t* theta, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(theta && workspace, "tvbf_sym_seed: NULL buffer");
+  SymPlan sp;
+  rc = make_sym_plan(f, p, rank, world, &sp);
+  if (rc != TVBF_OK) return rc;
+  if (workspace_bytes < sp.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, sp.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  tvbf::K1Params kp;
+  rc = fill_sym_params(f, p, sp, rank, world, ws, theta, &kp);
+  if (rc != TVBF_OK) return rc;
+  kp.sym_phase = 1;
+  TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+  return tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
+}
+
+int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                   uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(theta && cand && cand_cnt && cand_bound && workspace, "tvbf_sym_sweep: NULL buffer");
+  SymPlan sp;
+  rc = make_sym_plan(f, p, rank, world, &sp);
+  if (rc != TVBF_OK) return rc;
+  if (workspace_bytes < sp.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, sp.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  tvbf::K1Params kp;
+  rc = fill_sym_params(f, p, sp, rank, world, ws, theta, &kp);
+  if (rc != TVBF_OK) return rc;
+  kp.sym_phase = 2;
+  kp.cand = static_cast<uint2*>(cand);
+  kp.cand_cnt = cand_cnt;
+  kp.cand_theta = cand_bound;
+  TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+  if (sp.local_sb > 0) {
+    rc = tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
+    if (rc != TVBF_OK) return rc;
+  } else {
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(f->n_pad) * 4, st));
+  }
+  return tvbf::k4s_launch(kp, f->n_shows, st);
+}
+
+int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void* cand_all,
+                       const int32_t* cnt_all, const float* bound_all, int32_t lists,
+                       const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  rc = validate_params(f, p);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(cand_all && cnt_all && bound_all && lists >= 1, "tvbf_rescore_lists: bad candidate tables");
+  TVBF_REQUIRE(out && out->indices && out->counts && out->hybrid && out->genre && out->text &&
+                   out->metadata && out->stats,
+               "output table has NULL members");
+  SymPlan sp;
+  rc = make_sym_plan(f, p, 0, lists, &sp);
+  if (rc != TVBF_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < sp.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, sp.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* flagged = reinterpret_cast<int*>(ws + sp.off_flag);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + sp.off_keys);
+  TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
+  const tvbf::ScoreParams scp = score_params(f, p);
+  const int rows = p->row_end - p->row_begin;
+  // gathered layout: [lists][n_shows][kp]
+  const tvbf::CandLayout lay{p->row_begin, 1, f->n_shows};
+  rc = tvbf::k5_launch(scp, static_cast<const uint2*>(cand_all), cnt_all, bound_all, lists, lay, sp.pl.kp,
+                       p->row_begin, rows, *out, flagged, st);
+  if (rc != TVBF_OK) return rc;
+  int sms = 0;
+  rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  int k6_grid = 2 * sms;
+  if (k6_grid > rows) k6_grid = rows;
+  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, k6_grid, *out, st);
 }
 
 size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed) {
@@ -432,6 +628,7 @@ static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float*
   kp.rb_per_group = 1;
   kp.tiles_per_split = 1;
   kp.tile_stride = 1;
+  kp.sb_world = 1;
   kp.stages = cg == 2 ? 6 : 4;
   kp.dump_col0 = col0;
   kp.kp = 32;

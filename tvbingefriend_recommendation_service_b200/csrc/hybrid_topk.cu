@@ -138,17 +138,24 @@ struct ItemCoord {
   int real0, real1;  // ... of which [real0, real1) are computed, the rest are phantom
 };
 
+// Super blocks are dealt to the GPUs in zigzag order (0..W-1, W-1..0, ...) so that in symmetric
+// mode, where block G costs (T - G) tiles, every GPU gets the same work to within one block.
+__host__ __device__ __forceinline__ int global_super_block(int local, int world, int rank) {
+  return local * world + ((local & 1) ? (world - 1 - rank) : rank);
+}
+
 __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
   const int per_group = p.rb_per_group * p.splits;
   const int g = item / per_group;
   const int w = item - g * per_group;
   ItemCoord c;
   c.split = w / p.rb_per_group;
-  c.sb = g * p.rb_per_group + (w - c.split * p.rb_per_group);
+  const int local = g * p.rb_per_group + (w - c.split * p.rb_per_group);
+  c.sb = global_super_block(local, p.sb_world, p.sb_rank);
   if (p.sym) {
-    // the group's super blocks are tiles [i0, i0 + R) of the diagonal; only columns >= i0 matter
-    const int i0 = g * p.rb_per_group;
-    const int span = p.col_tiles - i0;
+    // the group's super blocks lie at or right of tile i0 on the diagonal; only columns >= i0 matter
+    const int i0 = g * p.rb_per_group * p.sb_world;
+    const int span = p.col_tiles > i0 ? p.col_tiles - i0 : 0;
     const int tps = (span + p.splits - 1) / p.splits;
     c.tile0 = i0 + c.split * tps;
     c.tile1 = c.tile0 + tps;
@@ -159,7 +166,7 @@ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
   c.real0 = c.tile0;
   c.real1 = c.tile1 < p.col_tiles ? c.tile1 : p.col_tiles;
   if (p.sym && c.sb > c.real0) c.real0 = c.sb;  // tiles left of the diagonal are the mirror's job
-  if (c.sb >= p.rb_count) { c.sb = -1; c.real0 = c.real1 = c.tile1; }
+  if (local >= p.rb_count) { c.sb = -1; c.real0 = c.real1 = c.tile1; }
   if (c.real0 > c.real1) c.real0 = c.real1;
   return c;
 }
@@ -697,6 +704,12 @@ static int make_operand_map(const tvbf_features* f, int box_rows, CUtensorMap* o
   return TVBF_OK;
 }
 
+int k1_local_super_blocks(int total_super_blocks, int world, int rank) {
+  int n = 0;
+  while (global_super_block(n, world, rank) < total_super_blocks) ++n;
+  return n;
+}
+
 int k1_entries_per_lane(int k) {
   if (k <= 48) return 4;
   if (k <= 160) return 8;
@@ -779,23 +792,27 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
       return TVBF_ERR_INVALID;
     }
     const int n_pad = f->n_pad;
-    sym_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(kp.g_theta, f->n_shows, n_pad, kp.theta_init);
-    TVBF_LAUNCH_OK("sym_init_kernel");
+    if (kp.sym_phase != 2) {
+      sym_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(kp.g_theta, f->n_shows, n_pad, kp.theta_init);
+      TVBF_LAUNCH_OK("sym_init_kernel");
+      if (kp.tile_stride > 1) {
+        // seed pass: one-sided sweep over every tile_stride-th column tile, thresholds only
+        K1Params seed = kp;
+        seed.sym = 0;
+        seed.seed_theta = 1;
+        seed.splits = 1;
+        seed.tiles_per_split = kp.col_tiles;
+        const int clusters = grid / 2;
+        seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
+        if (seed.rb_per_group < 1) seed.rb_per_group = 1;
+        int rc = launch_k1<4, false, 2, false>(f, seed, seed.rb_per_group * 2, st);
+        if (rc != TVBF_OK) return rc;
+        TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+      }
+      if (kp.sym_phase == 1) return TVBF_OK;
+    }
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(n_pad) * 4, st));
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, static_cast<size_t>(n_pad) * kp.sym_cap * 8, st));
-    if (kp.tile_stride > 1) {
-      // seed pass: one-sided sweep over every tile_stride-th column tile, thresholds only
-      K1Params seed = kp;
-      seed.sym = 0;
-      seed.seed_theta = 1;
-      seed.splits = 1;
-      seed.tiles_per_split = kp.col_tiles;
-      const int clusters = grid / 2;
-      seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
-      int rc = launch_k1<4, false, 2, false>(f, seed, seed.rb_per_group * 2, st);
-      if (rc != TVBF_OK) return rc;
-      TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
-    }
     K1Params sweep = kp;
     sweep.tile_stride = 1;
     return launch_k1<4, false, 2, true>(f, sweep, grid, st);

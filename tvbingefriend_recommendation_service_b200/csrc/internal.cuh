@@ -32,8 +32,11 @@ struct K1Params {
   // and every score is offered to BOTH shows' candidate lists, which therefore live in global
   // memory and are shared by all CTAs
   int sym;
+  int sb_world;            // super blocks are dealt to `sb_world` GPUs in zigzag order ...
+  int sb_rank;             // ... and this launch owns those of `sb_rank` (1 / 0 on a single GPU)
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
   int seed_theta;          // one-sided sweep only seeds g_theta with the kp-th best sampled score
+  int sym_phase;           // 0: init + seed + sweep in one call; 1: init + seed only; 2: sweep only
   int sym_cap;             // entries per shared list
   unsigned int* g_theta;   // [n_pad] raw bits of the (positive) float threshold of each show
   unsigned int* g_cnt;     // [n_pad] appends so far (> sym_cap = overflow)
@@ -65,9 +68,14 @@ int k1_choose_splits(int rb_count, int col_tiles, int sm_count);
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st);
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st);
+// candidate list s of shard row r lives in slot  slot_base + r * row_stride + s * list_stride
+struct CandLayout {
+  long long slot_base, row_stride, list_stride;
+};
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
-              const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
+              const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st);
+int k1_local_super_blocks(int total_super_blocks, int world, int rank);
 int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st);
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,

@@ -114,8 +114,8 @@ constexpr int K5_WARPS = 4;
 __global__ void __launch_bounds__(K5_WARPS * 32)
 rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
                const int* __restrict__ cand_cnt, const float* __restrict__ cand_theta, int splits,
-               int kp, int row_begin, int n_rows, tvbf_topk_out out, int* flagged_rows,
-               int max_cand) {
+               const CandLayout lay, int kp, int row_begin, int n_rows, tvbf_topk_out out,
+               int* flagged_rows, int max_cand) {
   extern __shared__ __align__(16) uint8_t k5_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * K5_WARPS + warp;
@@ -133,7 +133,7 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   int total = 0;
   float theta = __int_as_float(0xff800000);
   for (int s = 0; s < splits; ++s) {
-    const size_t slot = static_cast<size_t>(r) * splits + s;
+    const size_t slot = static_cast<size_t>(lay.slot_base + r * lay.row_stride + s * lay.list_stride);
     const int n = cand_cnt[slot];
     theta = fmaxf(theta, cand_theta[slot]);
     for (int e = lane; e < n; e += 32) sj[total + e] = static_cast<int>(cand[slot * kp + e].y);
@@ -371,7 +371,7 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
 // host-side launchers used by api.cu
 // ---------------------------------------------------------------------------------------------
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
-              const float* cand_theta, int splits, int kp, int row_begin, int n_rows,
+              const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st) {
   const int max_cand = splits * kp;
   const size_t smem = static_cast<size_t>(K5_WARPS) * max_cand * 40;
@@ -382,7 +382,7 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
   TVBF_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
   const int grid = (n_rows + K5_WARPS - 1) / K5_WARPS;
-  rescore_kernel<<<grid, K5_WARPS * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, kp,
+  rescore_kernel<<<grid, K5_WARPS * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, lay, kp,
                                                     row_begin, n_rows, out, flagged_rows, max_cand);
   TVBF_LAUNCH_OK("rescore_kernel");
   return TVBF_OK;

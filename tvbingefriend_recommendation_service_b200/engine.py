@@ -381,6 +381,115 @@ class HybridTopKEngine:
         cat = self.upload(stage(features, metadata_mode), weights)
         return self.to_host(self.top_k_device(cat, weights, k, min_similarity, exclude_self, **kw))
 
+    # ------------------------------------------------------------------------------------ several GPUs
+    def _params(self, cat: DeviceCatalogue, weights, k, min_similarity, exclude_self=True, row_begin=0,
+                row_end=None, splits=0, tuning=0) -> Params:
+        gw, tw, mw = (float(w) for w in weights)
+        return Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=float(min_similarity),
+                      k=int(k), exclude_self=int(bool(exclude_self)), row_begin=int(row_begin),
+                      row_end=int(cat.n_shows if row_end is None else row_end), splits=int(splits), candidates=0,
+                      force_exact=0, skip_fallback=0, text_rel_err=0.0, phases=0, tuning=int(tuning))
+
+    def sym_eligible(self, cat: DeviceCatalogue, weights, k, min_similarity) -> bool:
+        """Can this job use the symmetric (tile-sharded) sweep?  (packed groups, non-negative
+        weights, positive threshold, k <= 48)"""
+        if cat.folded:
+            return False
+        p = self._params(cat, weights, k, min_similarity)
+        with torch.cuda.device(self.device):
+            return bool(self.lib.tvbf_sym_eligible(C.byref(cat.c), C.byref(p)))
+
+    def sym_seed(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
+                 splits: int = 0, tuning: int = 0) -> torch.Tensor:
+        """Phase 1 of the tile-sharded symmetric job: thresholds of this rank's shows seeded from a
+        sampled sweep; returns theta int32[n_pad] (raw bits of positive floats), to be MAX-reduced
+        over the ranks."""
+        p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world)
+            if nbytes == 0:
+                check(-1, "tvbf_sym_workspace_bytes")
+            ws = self._workspace(nbytes)
+            theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
+            check(self.lib.tvbf_sym_seed(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), self._stream()), "tvbf_sym_seed")
+            self.kernel_launches += 2
+        return theta
+
+    def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
+                  theta: torch.Tensor, splits: int = 0, tuning: int = 0):
+        """Phase 2: sweep this rank's tiles; returns (cand int32[N, L, 2], cnt int32[N], bound f32[N]),
+        partial candidate lists for ALL shows, to be all-gathered."""
+        p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
+        dev, n = self.device, cat.n_shows
+        with torch.cuda.device(dev):
+            ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
+            L = int(self.lib.tvbf_sym_list_len(C.byref(cat.c), C.byref(p)))
+            cand = torch.empty((n, L, 2), dtype=torch.int32, device=dev)
+            cnt = torch.empty((n,), dtype=torch.int32, device=dev)
+            bound = torch.empty((n,), dtype=torch.float32, device=dev)
+            check(self.lib.tvbf_sym_sweep(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), cand.data_ptr(),
+                                          cnt.data_ptr(), bound.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+                  "tvbf_sym_sweep")
+            self.kernel_launches += 2
+        return cand, cnt, bound
+
+    def sym_rescore(self, cat: DeviceCatalogue, weights, k, min_similarity, cand_all: torch.Tensor,
+                    cnt_all: torch.Tensor, bound_all: torch.Tensor, row_begin: int, row_end: int,
+                    splits: int = 0, tuning: int = 0) -> dict:
+        """Phase 3: fp64 rescoring + certificate + exact repair of rows [row_begin, row_end) from the
+        gathered candidate tables ([world, N, L, 2] / [world, N])."""
+        dev, rows, world = self.device, row_end - row_begin, int(cand_all.shape[0])
+        with torch.cuda.device(dev):
+            t = {
+                "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
+                "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
+                "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
+                "row_begin": row_begin,
+            }
+            if rows > 0:
+                p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end,
+                                 splits=splits, tuning=tuning)
+                ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
+                cout = TopKOut(**{name: t[name].data_ptr() for name in
+                                  ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+                check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(), cnt_all.data_ptr(),
+                                                  bound_all.data_ptr(), world, C.byref(cout), ws.data_ptr(),
+                                                  ws.numel(), self._stream()), "tvbf_rescore_lists")
+                self.kernel_launches += 2
+        return t
+
+    def top_k_device_sym_sharded(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
+                                 all_reduce_max, all_gather, row_range, splits: int = 0, tuning: int = 0,
+                                 k1_events: list | None = None) -> dict:
+        """This GPU's part of the tile-sharded symmetric job: the three phases with the two
+        collectives between them passed in as callables (``all_reduce_max(int32 tensor)`` in place,
+        ``all_gather(tensor) -> tensor with a leading [world] dimension``)."""
+        def mark():
+            if k1_events is None:
+                return None
+            ev = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.device(self.device):
+                ev.record()
+            return ev
+
+        e0 = mark()
+        theta = self.sym_seed(cat, weights, k, min_similarity, rank, world, splits, tuning)
+        e1 = mark()
+        all_reduce_max(theta)            # raw bits of positive floats order like integers
+        e2 = mark()
+        cand, cnt, bound = self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning)
+        e3 = mark()
+        if k1_events is not None:
+            k1_events.append(((e0, e1), (e2, e3)))
+        cand_all, cnt_all, bound_all = all_gather(cand), all_gather(cnt), all_gather(bound)
+        b, e = row_range
+        return self.sym_rescore(cat, weights, k, min_similarity, cand_all, cnt_all, bound_all, b, e, splits, tuning)
+
     # ------------------------------------------------------------------------------------ exact
     def exact_rows(self, cat: DeviceCatalogue, rows, weights=(0.4, 0.5, 0.1), k: int = 10,
                    min_similarity: float = 0.0, exclude_self: bool = True) -> TopK:
