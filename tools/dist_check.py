@@ -27,8 +27,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cat = make_catalogue(5000, 3000, nnz=30, seed=123)
     eng = HybridTopKEngine(local)
-    full = compute_top_k_distributed(cat.features(), engine=eng)
+    full = compute_top_k_distributed(cat.features(), engine=eng, symmetric=False)
+    sym = compute_top_k_distributed(cat.features(), engine=eng, symmetric=True)
     if dist.get_rank() == 0:
+        assert np.array_equal(full.indices, sym.indices), "tile-sharded symmetric sweep: indices differ"
+        assert np.array_equal(full.counts, sym.counts)
+        m = full.indices >= 0
+        assert np.array_equal(full.hybrid[m], sym.hybrid[m])
         single = eng.compute_top_k(cat.features())
         assert np.array_equal(full.indices, single.indices), "indices differ"
         assert np.array_equal(full.counts, single.counts), "counts differ"

@@ -30,6 +30,7 @@ constexpr uint32_t A_BYTES = BM * BK * 2;
 constexpr uint32_t COL_BYTES = BN * sizeof(TvbfColSide);
 constexpr uint32_t MS_BYTES = BN * sizeof(float);
 constexpr int NUM_THREADS = 192;
+constexpr int SYMQ = 8;     // pending appends a thread can hold between two flushes
 // warps 0-3: epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4: TMA producer; warp 5: MMA
 // issuer.  The SM's issue arbiter favours higher warp ids, so the two single-thread roles, which
 // share schedulers with epilogue warps 0 and 1, are never starved by the epilogue's ALU stream.
@@ -49,7 +50,9 @@ struct Smem {
   static constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
   static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
-  static constexpr uint32_t OFF_BAR = OFF_TH + 2 * MS_BYTES;
+  // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][128] words
+  static constexpr uint32_t OFF_Q = OFF_TH + 2 * MS_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * 128 * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr uint32_t USED = OFF_TMEM + 16;
@@ -430,16 +433,55 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const unsigned sym_cap = static_cast<unsigned>(p.sym_cap);
       const unsigned sym_first = static_cast<unsigned>(2 * p.kp);
 
-      // append (score, other) to the shared list of `show`; remember a refresh when the list
-      // length reaches 2*kp, 4*kp, ... (power-of-two lengths)
-      auto sym_append = [&](int show, float u, int other, int& pr, int& pn) {
-        const unsigned pos = atomicAdd(p.g_cnt + show, 1u);
+      // Shared-list appends need the slot returned by an atomicAdd; done on the spot that round trip
+      // (~700 cycles) would stall the warp once per append.  Appends are therefore queued in shared
+      // memory (per-thread FIFO) and flushed every 64 columns with the atomics of a whole batch in
+      // flight together.  A later append only delays a candidate, it never loses one.
+      uint32_t* q_show = reinterpret_cast<uint32_t*>(smem + L::OFF_Q) + (warp * 32 + lane);
+      uint32_t* q_score = q_show + SYMQ * 128;
+      uint32_t* q_other = q_score + SYMQ * 128;
+      int qn = 0;
+      auto sym_commit = [&](int show, uint32_t ubits, uint32_t other, unsigned pos) {
         if (pos < sym_cap) {
-          __stcg(p.g_list + static_cast<size_t>(show) * sym_cap + pos,
-                 make_uint2(__float_as_uint(u), static_cast<uint32_t>(other)));
+          __stcg(p.g_list + static_cast<size_t>(show) * sym_cap + pos, make_uint2(ubits, other));
           const unsigned np = pos + 1u;
-          if (np >= sym_first && (np & pos) == 0u) { pr = show; pn = static_cast<int>(np); }
+          // refresh the show's threshold when its list reaches 2*kp, 4*kp, ... entries
+          if (np >= sym_first && (np & pos) == 0u) {
+            if (pend_n == 0) { pend_r = show; pend_n = static_cast<int>(np); }
+            else { pend2_r = show; pend2_n = static_cast<int>(np); }
+          }
         }
+      };
+      auto sym_append = [&](int show, float u, int other) {
+        if (qn < SYMQ) {
+          q_show[qn * 128] = static_cast<uint32_t>(show);
+          q_score[qn * 128] = __float_as_uint(u);
+          q_other[qn * 128] = static_cast<uint32_t>(other);
+          ++qn;
+        } else {  // queue full (rare): pay the round trip now
+          sym_commit(show, __float_as_uint(u), static_cast<uint32_t>(other), atomicAdd(p.g_cnt + show, 1u));
+        }
+      };
+      auto sym_flush = [&]() {
+        const int maxn = __reduce_max_sync(kFullMask, qn);
+        for (int base = 0; base < maxn; base += 4) {
+          unsigned pos[4];
+          uint32_t sh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sh[j] = 0u;
+            pos[j] = 0xFFFFFFFFu;
+            if (base + j < qn) {
+              sh[j] = q_show[(base + j) * 128];
+              pos[j] = atomicAdd(p.g_cnt + sh[j], 1u);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (base + j < qn)
+              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * 128], q_other[(base + j) * 128], pos[j]);
+        }
+        qn = 0;
       };
 
       const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
@@ -481,9 +523,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               u = fmaf(fabsf(a), w_text_err, u);
               const int col = col0 + cbase + e;
               if (kSym) {
-                if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col, pend_r, pend_n);
+                if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col);
                 // padded columns carry threshold +inf, so no bound check is needed here
-                if (do_col && u > sth[cbase + e]) sym_append(col, u, row, pend2_r, pend2_n);
+                if (do_col && u > sth[cbase + e]) sym_append(col, u, row);
               } else if (u > theta) {
                 if (col != self_col && col < p.n_shows) {
                   __stcg(my_list + cnt, make_uint2(__float_as_uint(u), static_cast<uint32_t>(col)));
@@ -514,8 +556,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive(&acc_empty[b]);
           }
           score16(acc_b, (ch + 1) * 16);
-          if (kSym) {
-            // serve the threshold refreshes raised in these 32 columns, one show at a time
+          if (kSym && ((ch & 2) != 0 || ch + 2 >= BN / 16)) {
+            // every 64 columns: flush the queued appends, then serve the threshold refreshes they
+            // raised, one show at a time
+            sym_flush();
             unsigned need = __ballot_sync(kFullMask, pend_n != 0);
             while (need) {
               const int src_lane = __ffs(need) - 1;
@@ -539,7 +583,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
               theta = __uint_as_float(tb);
             }
-          } else if (!kDump) {
+          } else if (!kDump && !kSym) {
             // keep 32 free slots for the next 32 columns; compact rows that are nearly full
             unsigned need = __ballot_sync(kFullMask, cnt > CAP - 32);
             while (need) {
