@@ -146,8 +146,7 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
     }
   }
   pl->cand_lists = pl->sym ? 1 : pl->splits;
-  pl->k6_grid = 2 * sms;
-  if (pl->k6_grid > pl->rows) pl->k6_grid = pl->rows;
+  pl->k6_grid = sms;
   size_t off = 0;
   pl->off_scratch = off; off = align_up(off + (use_k1 ? static_cast<size_t>(pl->grid) * 128 * 32 * pl->entries * 8 : 0), 256);
   pl->off_cand = off;    off = align_up(off + (use_k1 ? static_cast<size_t>(pl->rows) * pl->cand_lists * pl->kp * 8 : 0), 256);
@@ -158,7 +157,7 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   pl->off_glist = off;   off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * pl->sym_cap * 8 : 0), 256);
   pl->off_flag = off;    off = align_up(off + static_cast<size_t>(pl->rows) * 4, 256);
   pl->off_count = off;   off = align_up(off + 256, 256);
-  pl->off_keys = off;    off = align_up(off + static_cast<size_t>(pl->k6_grid) * f->n_shows * 8, 256);
+  pl->off_keys = off;    off = align_up(off + tvbf::k6_scratch_bytes(f->n_shows, sms), 256);
   pl->total = off;
   return TVBF_OK;
 }
@@ -396,14 +395,13 @@ int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int wo
   pl.sb_per_group = clusters / pl.splits;
   if (pl.sb_per_group > sp->local_sb) pl.sb_per_group = sp->local_sb > 0 ? sp->local_sb : 1;
   pl.grid = pl.sb_per_group * pl.splits * 2;
-  const int k6_grid = 2 * sms;
   size_t off = 0;
   sp->off_prog = off;    off = align_up(off + 256, 256);
   sp->off_scratch = off; off = align_up(off + static_cast<size_t>(sms) * 128 * 32 * 4 * 8, 256);
   sp->off_gcnt = off;    off = align_up(off + static_cast<size_t>(f->n_pad) * 4, 256);
   sp->off_glist = off;   off = align_up(off + static_cast<size_t>(f->n_pad) * pl.sym_cap * 8, 256);
   sp->off_flag = off;    off = align_up(off + static_cast<size_t>(f->n_shows) * 4, 256);
-  sp->off_keys = off;    off = align_up(off + static_cast<size_t>(k6_grid) * f->n_shows * 8, 256);
+  sp->off_keys = off;    off = align_up(off + tvbf::k6_scratch_bytes(f->n_shows, sms), 256);
   sp->total = off;
   return TVBF_OK;
 }
@@ -538,18 +536,14 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   int sms = 0;
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
-  int k6_grid = 2 * sms;
-  if (k6_grid > rows) k6_grid = rows;
-  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, k6_grid, *out, st);
+  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, sms, *out, st);
 }
 
 size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed) {
   if (f == nullptr || n_rows_listed <= 0) return 0;
   int sms = 0;
   if (sm_count_cached(&sms) != TVBF_OK) return 0;
-  int grid = 2 * sms;
-  if (grid > n_rows_listed) grid = n_rows_listed;
-  return align_up(static_cast<size_t>(grid) * f->n_shows * 8, 256);
+  return align_up(tvbf::k6_scratch_bytes(f->n_shows, sms), 256);
 }
 
 int tvbf_exact_rows(const tvbf_features* f, const tvbf_params* p, const int32_t* rows,
@@ -570,11 +564,9 @@ int tvbf_exact_rows(const tvbf_features* f, const tvbf_params* p, const int32_t*
   int sms = 0;
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
-  int grid = 2 * sms;
-  if (grid > n_rows_listed) grid = n_rows_listed;
   const tvbf::ScoreParams sp = score_params(f, p);
   return tvbf::k6_launch(sp, rows, n_rows_listed, nullptr, 0, 0,
-                         static_cast<unsigned long long*>(workspace), grid, *out,
+                         static_cast<unsigned long long*>(workspace), sms, *out,
                          static_cast<cudaStream_t>(stream));
 }
 

@@ -29,13 +29,20 @@ constexpr int UMMA_K = 16;
 constexpr uint32_t A_BYTES = BM * BK * 2;
 constexpr uint32_t COL_BYTES = BN * sizeof(TvbfColSide);
 constexpr uint32_t MS_BYTES = BN * sizeof(float);
-constexpr int NUM_THREADS = 192;
-constexpr int SYMQ = 8;     // pending appends a thread can hold between two flushes
-// warps 0-3: epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4: TMA producer; warp 5: MMA
-// issuer.  The SM's issue arbiter favours higher warp ids, so the two single-thread roles, which
-// share schedulers with epilogue warps 0 and 1, are never starved by the epilogue's ALU stream.
-constexpr int PRODUCER_WARP = 4;
-constexpr int MMA_WARP = 5;
+constexpr int SYMQ = 4;     // pending appends a thread can hold between two flushes
+// warps 0..EPI-1: epilogue (warp w may touch TMEM lanes 32*(w%4)..+31); then the TMA producer and
+// the MMA issuer.  The SM's issue arbiter favours higher warp ids, so the two single-lane roles,
+// which share schedulers with epilogue warps, are never starved by the epilogue's ALU stream.
+// One-sided sweep: 4 epilogue warps (thread t owns accumulator row t and its private list).
+// Symmetric sweep: 8 epilogue warps, two per lane quarter, each scoring half of the tile's columns
+// -- its epilogue does twice the compares plus the shared-list traffic and, with one warp per
+// scheduler, was latency-bound (tensor pipe 74 % active); two warps per scheduler hide it.
+template <bool kSym> struct Roles {
+  static constexpr int EPI = kSym ? 8 : 4;
+  static constexpr int PRODUCER = EPI;
+  static constexpr int MMA = EPI + 1;
+  static constexpr int THREADS = 32 * (EPI + 2);
+};
 
 // Shared-memory plan.  CG = CTAs cooperating on one MMA (tcgen05 cta_group): with CG = 2 the pair
 // computes a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the B tile, so the
@@ -50,9 +57,9 @@ struct Smem {
   static constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
   static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
-  // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][128] words
+  // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][256] words
   static constexpr uint32_t OFF_Q = OFF_TH + 2 * MS_BYTES;
-  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * 128 * 4;
+  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * 256 * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr uint32_t USED = OFF_TMEM + 16;
@@ -232,12 +239,14 @@ struct Pacer {
 };
 
 template <int E, bool kDump, int CG, bool kSym>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Roles<kSym>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
                    const uint32_t idesc) {
   using L = Smem<CG>;
   constexpr int STAGES = L::STAGES;
+  constexpr int EPI = Roles<kSym>::EPI, PRODUCER_WARP = Roles<kSym>::PRODUCER, MMA_WARP = Roles<kSym>::MMA;
+  constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
   const uint32_t nstages = static_cast<uint32_t>(p.stages);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles; done as an OFFSET so the compiler still knows
@@ -268,9 +277,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 128 * CG);
+      mbar_init(&acc_empty[b], 32 * EPI * CG);
       mbar_init(&col_full[b], 1);
-      mbar_init(&col_empty[b], 128);
+      mbar_init(&col_empty[b], 32 * EPI);
     }
     fence_barrier_init();
   }
@@ -438,8 +447,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // memory (per-thread FIFO) and flushed every 64 columns with the atomics of a whole batch in
       // flight together.  A later append only delays a candidate, it never loses one.
       uint32_t* q_show = reinterpret_cast<uint32_t*>(smem + L::OFF_Q) + (warp * 32 + lane);
-      uint32_t* q_score = q_show + SYMQ * 128;
-      uint32_t* q_other = q_score + SYMQ * 128;
+      uint32_t* q_score = q_show + SYMQ * 256;
+      uint32_t* q_other = q_score + SYMQ * 256;
       int qn = 0;
       auto sym_commit = [&](int show, uint32_t ubits, uint32_t other, unsigned pos) {
         if (pos < sym_cap) {
@@ -454,9 +463,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       };
       auto sym_append = [&](int show, float u, int other) {
         if (qn < SYMQ) {
-          q_show[qn * 128] = static_cast<uint32_t>(show);
-          q_score[qn * 128] = __float_as_uint(u);
-          q_other[qn * 128] = static_cast<uint32_t>(other);
+          q_show[qn * 256] = static_cast<uint32_t>(show);
+          q_score[qn * 256] = __float_as_uint(u);
+          q_other[qn * 256] = static_cast<uint32_t>(other);
           ++qn;
         } else {  // queue full (rare): pay the round trip now
           sym_commit(show, __float_as_uint(u), static_cast<uint32_t>(other), atomicAdd(p.g_cnt + show, 1u));
@@ -472,14 +481,14 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             sh[j] = 0u;
             pos[j] = 0xFFFFFFFFu;
             if (base + j < qn) {
-              sh[j] = q_show[(base + j) * 128];
+              sh[j] = q_show[(base + j) * 256];
               pos[j] = atomicAdd(p.g_cnt + sh[j], 1u);
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (base + j < qn)
-              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * 128], q_other[(base + j) * 128], pos[j]);
+              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * 256], q_other[(base + j) * 256], pos[j]);
         }
         qn = 0;
       };
@@ -540,14 +549,15 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // is in flight while the current one is scored.  The loop is kept rolled on purpose: the
         // whole body (~700 instructions) stays resident in the instruction cache.
         uint32_t acc_a[16], acc_b[16];
-        tmem_ld_32x16(taddr, acc_a);
+        const int ch0 = (warp >> 2) * (COLS_PER_WARP / 16), ch1 = ch0 + COLS_PER_WARP / 16;
+        tmem_ld_32x16(taddr + ch0 * 16, acc_a);
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 16; ch += 2) {
+        for (int ch = ch0; ch < ch1; ch += 2) {
           tmem_ld_wait();
           tmem_ld_32x16(taddr + (ch + 1) * 16, acc_b);
           score16(acc_a, ch * 16);
           tmem_ld_wait();
-          if (ch + 2 < BN / 16) {
+          if (ch + 2 < ch1) {
             tmem_ld_32x16(taddr + (ch + 2) * 16, acc_a);
           } else {
             // every accumulator column of this tile is in registers: hand the TMEM buffer back
@@ -556,7 +566,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive(&acc_empty[b]);
           }
           score16(acc_b, (ch + 1) * 16);
-          if (kSym && ((ch & 2) != 0 || ch + 2 >= BN / 16)) {
+          if (kSym && ((ch & 2) != 0 || ch + 2 >= ch1)) {
             // every 64 columns: flush the queued appends, then serve the threshold refreshes they
             // raised, one show at a time
             sym_flush();
@@ -811,7 +821,7 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(Roles<kSym>::THREADS);
   cfg.dynamicSmemBytes = L::BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

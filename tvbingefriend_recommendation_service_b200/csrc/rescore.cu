@@ -240,30 +240,131 @@ struct SelectParams {
   double min_similarity;
 };
 
+// block-wide selection state (static shared memory)
+struct SelectSmem {
+  unsigned int hist[256];
+  unsigned long long prefix;
+  int rank, valid, above, taken;
+  int warp_tot[32];
+  unsigned long long win_key[K6_MAXK];
+  int win_j[K6_MAXK];
+};
+
+// Exact top-k of one source row from its N order-preserving keys (0 = invalid): radix select of the
+// count-th largest key, everything above it, then the LOWEST column indices among keys equal to
+// it, finally ordered by (score desc, column asc).  Called by all threads of the block.
+template <class Scorer>
+__device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, int n, int k,
+                                int valid, int i, size_t orow, const Scorer& scorer,
+                                const tvbf_topk_out& out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int count = valid < k ? valid : k;
+  const size_t obase = orow * static_cast<size_t>(k);
+  __syncthreads();
+  if (tid == 0) { sm.above = 0; sm.taken = 0; sm.prefix = 0ull; sm.rank = count; }
+  __syncthreads();
+  if (count > 0) {
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int b = tid; b < 256; b += nthr) sm.hist[b] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = sm.prefix;
+      const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+#pragma unroll 4
+      for (int j = tid; j < n; j += nthr) {
+        const unsigned long long key = __ldcg(keys + j);
+        if (key != 0ull && (key & hi_mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rank = sm.rank;  // rank-th largest among keys matching the prefix
+        int d = 255;
+        for (; d > 0; --d) {
+          const int c = static_cast<int>(sm.hist[d]);
+          if (rank <= c) break;
+          rank -= c;
+        }
+        sm.prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+        sm.rank = rank;
+      }
+      __syncthreads();
+    }
+    const unsigned long long vstar = sm.prefix;  // count-th largest key
+#pragma unroll 4
+    for (int j = tid; j < n; j += nthr) {
+      const unsigned long long key = __ldcg(keys + j);
+      if (key > vstar) {
+        const int pos = atomicAdd(&sm.above, 1);
+        sm.win_key[pos] = key;
+        sm.win_j[pos] = j;
+      }
+    }
+    __syncthreads();
+    const int above = sm.above;
+    const int need = count - above;  // >= 1 : lowest column indices among keys == v*
+    const int nwarps = nthr >> 5;
+    for (int base = 0; base < n; base += nthr) {
+      const int j = base + tid;
+      const bool flag = j < n && keys[j] == vstar;
+      const unsigned bal = __ballot_sync(kFullMask, flag);
+      if (lane == 0) sm.warp_tot[warp] = __popc(bal);
+      __syncthreads();
+      int before = sm.taken;
+      for (int w = 0; w < warp; ++w) before += sm.warp_tot[w];
+      int chunk_total = 0;
+      for (int w = 0; w < nwarps; ++w) chunk_total += sm.warp_tot[w];
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      if (flag && pos < need) {
+        sm.win_key[above + pos] = vstar;
+        sm.win_j[above + pos] = j;
+      }
+      __syncthreads();
+      if (tid == 0) sm.taken += chunk_total;
+      __syncthreads();
+      if (sm.taken >= need) break;
+    }
+    __syncthreads();
+    for (int e = tid; e < count; e += nthr) {
+      const unsigned long long ke = sm.win_key[e];
+      const int je = sm.win_j[e];
+      int rank = 0;
+      for (int o = 0; o < count; ++o)
+        rank += (sm.win_key[o] > ke) || (sm.win_key[o] == ke && sm.win_j[o] < je);
+      const Scores s = scorer(i, je);
+      out.indices[obase + rank] = je;
+      out.hybrid[obase + rank] = f64_from_orderable(ke);
+      out.genre[obase + rank] = s.g;
+      out.text[obase + rank] = s.t;
+      out.metadata[obase + rank] = s.m;
+    }
+  }
+  for (int e = count + tid; e < k; e += nthr) {
+    out.indices[obase + e] = -1;
+    out.hybrid[obase + e] = NAN;
+    out.genre[obase + e] = NAN;
+    out.text[obase + e] = NAN;
+    out.metadata[obase + e] = NAN;
+  }
+  if (tid == 0) out.counts[orow] = count;
+  __syncthreads();
+}
+
+// generic form: one source row per CTA pass, any scorer (used for the N x N matrix variant)
 template <class Scorer>
 __global__ void __launch_bounds__(K6_THREADS)
 exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __restrict__ rows,
                   int n_listed, const int* __restrict__ count_ptr, int row_begin,
                   int rows_are_local, unsigned long long* __restrict__ key_scratch,
                   tvbf_topk_out out) {
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned long long s_prefix;
-  __shared__ int s_rank, s_valid, s_above, s_taken, s_warp_tot[K6_THREADS / 32];
-  __shared__ unsigned long long win_key[K6_MAXK];
-  __shared__ int win_j[K6_MAXK];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ SelectSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int n = sel.n;
   const int listed = count_ptr ? *count_ptr : n_listed;
   unsigned long long* keys = key_scratch + static_cast<size_t>(blockIdx.x) * n;
-  const int k = sel.k;
-
   for (int t = blockIdx.x; t < listed; t += gridDim.x) {
     const int r = rows[t];
     const int i = rows_are_local ? row_begin + r : r;
     const int orow = rows_are_local ? r : t;
-    // ---- 1. exact scores of row i against every column -> order-preserving keys (0 = invalid)
-    if (tid == 0) { s_valid = 0; s_above = 0; s_taken = 0; }
+    if (tid == 0) sm.valid = 0;
     __syncthreads();
     int my_valid = 0;
     for (int j = tid; j < n; j += K6_THREADS) {
@@ -274,96 +375,168 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(kFullMask, my_valid, o);
-    if (lane == 0 && my_valid) atomicAdd(&s_valid, my_valid);
+    if (lane == 0 && my_valid) atomicAdd(&sm.valid, my_valid);
     __syncthreads();
-    const int count = s_valid < k ? s_valid : k;
-    const size_t obase = static_cast<size_t>(orow) * k;
-    if (count > 0) {
-      // ---- 2. radix select: value of the count-th largest key
-      if (tid == 0) { s_prefix = 0ull; s_rank = count; }
-      for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int b = tid; b < 256; b += K6_THREADS) hist[b] = 0u;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-        for (int j = tid; j < n; j += K6_THREADS) {
-          const unsigned long long key = keys[j];
-          if (key != 0ull && (key & hi_mask) == prefix)
-            atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-          int rank = s_rank;  // rank-th largest among keys matching the prefix
-          int d = 255;
-          for (; d > 0; --d) {
-            const int c = static_cast<int>(hist[d]);
-            if (rank <= c) break;
-            rank -= c;
+    select_and_emit(sm, keys, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
+  }
+}
+
+// Feature form, batched: a CTA takes up to K6B_MAXB source rows at once so that the CSR of the
+// catalogue (the dominant traffic: ~12 B per text nnz, 56 MB at C3) is streamed once per BATCH
+// instead of once per row.  mask[c] (one byte per vocabulary column, shared memory) has bit r set
+// when batch row r uses column c; a column show's entries are tested against it and only hits are
+// looked up in the batch rows.  Sums run over ascending column index, exactly like text_dot.
+constexpr int K6B_THREADS = 1024;
+constexpr int K6B_MAXB = 8;
+
+__device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, int64_t e, int c) {
+  // value of column c in the sorted row segment [b, e); the caller knows it is present
+  while (b < e) {
+    const int64_t mid = (b + e) >> 1;
+    const int cm = f.text_indices[mid];
+    if (cm == c) return f.text_values[mid];
+    if (cm < c) b = mid + 1; else e = mid;
+  }
+  return 0.0;
+}
+
+__global__ void __launch_bounds__(K6B_THREADS, 1)
+exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
+                          const int* __restrict__ count_ptr, int row_begin, int rows_are_local,
+                          unsigned long long* __restrict__ key_scratch, tvbf_topk_out out) {
+  extern __shared__ unsigned int mask_words[];  // vocab bytes, 4 per word
+  __shared__ SelectSmem sm;
+  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB];
+  __shared__ long long s_b[K6B_MAXB], s_e[K6B_MAXB];
+  const tvbf_features& f = sp.f;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = f.n_shows;
+  const int listed = count_ptr ? *count_ptr : n_listed;
+  if (listed <= 0) return;
+  int B = (listed + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  B = B < 1 ? 1 : (B > K6B_MAXB ? K6B_MAXB : B);
+  const int n_batches = (listed + B - 1) / B;
+  const int words = (f.vocab + 3) / 4;
+  const unsigned char* mask = reinterpret_cast<const unsigned char*>(mask_words);
+  unsigned long long* keys0 = key_scratch + static_cast<size_t>(blockIdx.x) * K6B_MAXB * n;
+
+  for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int nb = (listed - batch * B) < B ? (listed - batch * B) : B;
+    __syncthreads();
+    for (int w = tid; w < words; w += K6B_THREADS) mask_words[w] = 0u;
+    if (tid < K6B_MAXB) {
+      s_valid[tid] = 0;
+      if (tid < nb) {
+        const int r = rows[batch * B + tid];
+        const int i = rows_are_local ? row_begin + r : r;
+        s_row[tid] = i;
+        s_b[tid] = f.text_indptr[i];
+        s_e[tid] = f.text_indptr[i + 1];
+      } else {
+        s_row[tid] = -1; s_b[tid] = 0; s_e[tid] = 0;
+      }
+    }
+    __syncthreads();
+    for (int r = 0; r < nb; ++r)
+      for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
+        const int c = f.text_indices[e];
+        atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
+      }
+    __syncthreads();
+
+    int my_valid[K6B_MAXB];
+#pragma unroll
+    for (int r = 0; r < K6B_MAXB; ++r) my_valid[r] = 0;
+    const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
+    const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+    for (int j = tid; j < n; j += K6B_THREADS) {
+      double acc[K6B_MAXB];
+#pragma unroll
+      for (int r = 0; r < K6B_MAXB; ++r) acc[r] = 0.0;
+      const int64_t bj = f.text_indptr[j], ej = f.text_indptr[j + 1];
+      // four entries per step: the index loads and mask probes of a step are independent, so
+      // their latencies overlap; hits (rare) are resolved in ascending column order
+      for (int64_t e = bj; e < ej; e += 4) {
+        int c[4];
+        unsigned m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = (e + u < ej) ? f.text_indices[e + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) m[u] = c[u] >= 0 ? mask[c[u]] : 0u;
+        if (m[0] | m[1] | m[2] | m[3]) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (m[u]) {
+              const double v = f.text_values[e + u];
+#pragma unroll
+              for (int r = 0; r < K6B_MAXB; ++r)
+                if (m[u] & (1u << r)) acc[r] += csr_lookup(f, s_b[r], s_e[r], c[u]) * v;
+            }
           }
-          s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
-          s_rank = rank;
-        }
-        __syncthreads();
-      }
-      const unsigned long long vstar = s_prefix;  // count-th largest key
-      // ---- 3a. everything strictly above v*
-      for (int j = tid; j < n; j += K6_THREADS) {
-        const unsigned long long key = keys[j];
-        if (key > vstar) {
-          const int pos = atomicAdd(&s_above, 1);
-          win_key[pos] = key;
-          win_j[pos] = j;
         }
       }
-      __syncthreads();
-      const int above = s_above;
-      const int need = count - above;  // >= 1 : lowest column indices among keys == v*
-      // ---- 3b. ordered take of the ties
-      for (int base = 0; base < n; base += K6_THREADS) {
-        const int j = base + tid;
-        const bool flag = j < n && keys[j] == vstar;
-        const unsigned bal = __ballot_sync(kFullMask, flag);
-        if (lane == 0) s_warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int before = s_taken;
-        for (int w = 0; w < warp; ++w) before += s_warp_tot[w];
-        int chunk_total = 0;
-        for (int w = 0; w < K6_THREADS / 32; ++w) chunk_total += s_warp_tot[w];
-        const int pos = before + __popc(bal & ((1u << lane) - 1u));
-        if (flag && pos < need) {
-          win_key[above + pos] = vstar;
-          win_j[above + pos] = j;
-        }
-        __syncthreads();
-        if (tid == 0) s_taken += chunk_total;
-        __syncthreads();
-        if (s_taken >= need) break;
+      // genre / metadata parts: same expressions as genre_score() / meta_score(), with the
+      // column show's factors computed once for the whole batch
+      TvbfColSide cj;
+      int gnj = 0, mnj = 0;
+      double g_rj = 0.0, m_rj = 0.0;
+      if (packed) {
+        cj = cs[j];
+        gnj = __popcll(cj.genre_bits);
+        mnj = __popc(cj.meta_bits);
+        if (gnj) g_rj = 1.0 / sqrt(static_cast<double>(gnj));
+        if (mnj) m_rj = 1.0 / sqrt(static_cast<double>(mnj));
       }
-      __syncthreads();
-      // ---- 4. order the winners (score desc, column asc) and emit
-      for (int e = tid; e < count; e += K6_THREADS) {
-        const unsigned long long ke = win_key[e];
-        const int je = win_j[e];
-        int rank = 0;
-        for (int o = 0; o < count; ++o)
-          rank += (win_key[o] > ke) || (win_key[o] == ke && win_j[o] < je);
-        const Scores s = scorer(i, je);
-        out.indices[obase + rank] = je;
-        out.hybrid[obase + rank] = f64_from_orderable(ke);
-        out.genre[obase + rank] = s.g;
-        out.text[obase + rank] = s.t;
-        out.metadata[obase + rank] = s.m;
+#pragma unroll
+      for (int r = 0; r < K6B_MAXB; ++r) {
+        if (r < nb) {
+          const int i = s_row[r];
+          double g, mm;
+          if (packed) {
+            const TvbfColSide ci = cs[i];
+            g = 0.0;
+            mm = 0.0;
+            if (f.genre_mode == TVBF_GROUP_PACKED) {
+              const int gni = __popcll(ci.genre_bits);
+              if (gni && gnj)
+                g = static_cast<double>(__popcll(ci.genre_bits & cj.genre_bits)) *
+                    ((1.0 / sqrt(static_cast<double>(gni))) * g_rj);
+            }
+            if (f.meta_mode == TVBF_GROUP_PACKED) {
+              const int eq = __popc(ci.meta_bits & cj.meta_bits);
+              if (f.meta_kind == TVBF_META_MEAN3) {
+                mm = static_cast<double>(eq) / 3.0;
+              } else {
+                const int mni = __popc(ci.meta_bits);
+                if (mni && mnj) mm = static_cast<double>(eq) * ((1.0 / sqrt(static_cast<double>(mni))) * m_rj);
+              }
+            }
+          } else {
+            g = genre_score(f, i, j);
+            mm = meta_score(f, i, j);
+          }
+          const double h = sp.wg * g + sp.wt * acc[r] + sp.wm * mm;
+          const bool ok = (h >= sp.min_similarity) && !(sp.exclude_self && j == i);
+          keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(h) : 0ull;
+          my_valid[r] += ok;
+        }
       }
     }
-    for (int e = count + tid; e < k; e += K6_THREADS) {
-      out.indices[obase + e] = -1;
-      out.hybrid[obase + e] = NAN;
-      out.genre[obase + e] = NAN;
-      out.text[obase + e] = NAN;
-      out.metadata[obase + e] = NAN;
+#pragma unroll
+    for (int r = 0; r < K6B_MAXB; ++r) {
+      int v = my_valid[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+      if (lane == 0 && v) atomicAdd(&s_valid[r], v);
     }
-    if (tid == 0) out.counts[orow] = count;
     __syncthreads();
+    const FeatureScorer scorer{sp};
+    for (int r = 0; r < nb; ++r) {
+      const int t = batch * B + r;
+      const int orow = rows_are_local ? rows[t] : t;
+      select_and_emit(sm, keys0 + static_cast<size_t>(r) * n, n, sp.k, s_valid[r], s_row[r],
+                      static_cast<size_t>(orow), scorer, out);
+    }
   }
 }
 
@@ -388,6 +561,11 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
   return TVBF_OK;
 }
 
+size_t k6_scratch_bytes(int n_shows, int sm_count) {
+  // batched feature kernel: one CTA per SM, up to K6B_MAXB key rows each
+  return static_cast<size_t>(sm_count) * K6B_MAXB * static_cast<size_t>(n_shows) * 8;
+}
+
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
               const tvbf_topk_out& out, cudaStream_t st) {
@@ -395,6 +573,17 @@ int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* c
     tvbf_set_error("exact rows: k=%d exceeds %d", sp.k, K6_MAXK);
     return TVBF_ERR_INVALID;
   }
+  const size_t mask_bytes = (static_cast<size_t>(sp.f.vocab) + 3) / 4 * 4;
+  if (mask_bytes <= 200 * 1024) {
+    TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_batched_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(mask_bytes)));
+    exact_rows_batched_kernel<<<grid, K6B_THREADS, mask_bytes, st>>>(
+        sp, rows, n_listed, count_ptr, row_begin, rows_are_local, key_scratch, out);
+    TVBF_LAUNCH_OK("exact_rows_batched_kernel");
+    return TVBF_OK;
+  }
+  // vocabulary too wide for the shared-memory mask: one row per CTA pass
   FeatureScorer sc{sp};
   SelectParams sel{sp.f.n_shows, sp.k, sp.exclude_self, sp.min_similarity};
   exact_rows_kernel<FeatureScorer><<<grid, K6_THREADS, 0, st>>>(
