@@ -181,13 +181,15 @@ def test_golden_production_loop(engine, name):
         assert sum(len(v) for v in d.values()) == int(z[f"case{c}_total_records"])
 
 
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
 @pytest.mark.parametrize("mode,norm,w", [("hstack", True, (2.0, 3.0, 1.0)), ("mean3", False, (0.5, 0.5, 0.0)),
                                          ("hstack", False, (0.3, 0.6, 0.1))])
-def test_variants_and_weights(engine, cat2k, mode, norm, w):
+def test_variants_and_weights(engine, cat2k, mode, norm, w, tuning):
     from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
 
     top = SimilarityComputer(*w, engine=engine).compute_top_k(cat2k.features(), k=10, min_similarity=0.05,
-                                                               metadata_mode=mode, normalize_weights=norm)
+                                                               metadata_mode=mode, normalize_weights=norm,
+                                                               tuning=tuning)
     assert_topk_matches(top, cat2k.features(), None, w, 10, 0.05, mode, norm)
 
 
@@ -197,17 +199,34 @@ def test_other_k(engine, cat2k, k):
     assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 7), (0.4, 0.5, 0.1), k, 0.0)
 
 
-@pytest.mark.parametrize("n", [1, 2, 127, 129, 300, 513])
-def test_ragged_sizes(engine, n):
+@pytest.mark.parametrize("k", [1, 20, 48])
+def test_other_k_symmetric(engine, cat2k, k):
+    top = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), k, 0.02, tuning=SYM_ON)
+    assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 7), (0.4, 0.5, 0.1), k, 0.02)
+
+
+def test_symmetric_request_on_ineligible_job_is_refused(engine, cat2k):
+    from tvbingefriend_recommendation_service_b200._lib import TvbfError
+
+    with pytest.raises(TvbfError):   # k = 100 needs more candidates per show than the shared lists keep
+        engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 100, 0.1, tuning=SYM_ON)
+    with pytest.raises(TvbfError):   # non-positive threshold
+        engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.0, tuning=SYM_ON)
+
+
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+@pytest.mark.parametrize("n", [1, 2, 127, 129, 300, 513, 1100])
+def test_ragged_sizes(engine, n, tuning):
     from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
 
     cat = make_catalogue(n, 100, nnz=8, n_genres=12, seed=n)
-    top = engine.compute_top_k(cat.features(), (0.4, 0.5, 0.1), 20, 0.1)
+    top = engine.compute_top_k(cat.features(), (0.4, 0.5, 0.1), 20, 0.1, tuning=tuning)
     assert top.indices.shape == (n, 20)
     assert_topk_matches(top, cat.features())
 
 
-def test_degenerate_rows(engine):
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+def test_degenerate_rows(engine, tuning):
     """Empty text, all-zero genres, missing type, exact duplicates and a high threshold."""
     from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
 
@@ -220,21 +239,25 @@ def test_degenerate_rows(engine):
         t.rows[r], t.data[r] = [], []
     f["text_features"] = t.tocsr()
     for ms in (0.1, 0.75, 0.0):
-        top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, ms)
+        # min_similarity <= 0 is not eligible for the symmetric sweep: the library falls back
+        top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, ms, tuning=tuning if ms > 0 else SYM_OFF)
         assert_topk_matches(top, f, None, (0.4, 0.5, 0.1), 20, ms)
-    assert (engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 5.0).counts == 0).all()
+    assert (engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 5.0, tuning=tuning).counts == 0).all()
 
 
-def test_tie_break_is_by_index(engine):
-    """Identical shows: all scores tie exactly; the stated order is ascending column index."""
-    n = 300
+@pytest.mark.parametrize("tuning,n", [(SYM_OFF, 300), (SYM_ON, 300), (SYM_ON, 3000)],
+                         ids=["one_sided", "symmetric", "symmetric_list_overflow"])
+def test_tie_break_is_by_index(engine, tuning, n):
+    """Identical shows: all scores tie exactly; the stated order is ascending column index.
+    (3000 identical shows overflow the shared candidate lists of the symmetric sweep before a
+    threshold refresh can stop the flood: those rows must be repaired by the exact kernel.)"""
     f = {"genre_features": np.ones((n, 3), dtype=np.int64),
          "text_features": sp.csr_matrix(np.tile(np.array([[0.6, 0.8, 0.0]]), (n, 1))),
          "platform_features": np.tile(np.array([[1.0, 0.0]]), (n, 1)),
          "type_features": np.tile(np.array([[True, False]]), (n, 1)),
          "language_features": np.tile(np.array([[1.0, 0.0]]), (n, 1))}
-    top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1)
-    for i in (0, 5, 150, 299):
+    top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1, tuning=tuning)
+    for i in (0, 5, 150, n - 1):
         want = [j for j in range(n) if j != i][:20]
         assert top.indices[i].tolist() == want
     assert np.allclose(top.hybrid, 1.0)
