@@ -78,6 +78,41 @@ def test_c3_100k_properties_and_sample(engine, tuning):
     assert 0 < top.flagged_rows < 20_000
 
 
+def test_c4_250k_full_catalogue(engine):
+    """BASELINE config 4: 250 k shows (full TVmaze-scale catalogue), N x N never materialised."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+    cat = make_config("C4")
+    w = (0.4, 0.5, 0.1)
+    dc = engine.upload(stage(cat.features()), w)
+    top = engine.to_host(engine.top_k_device(dc, w, 20, 0.1))
+    check_table_properties(top, 250_000, 20, 0.1)
+    rows = np.linspace(0, 249_999, 48).astype(np.int64)
+    assert_topk_matches(top, cat.features(), rows)
+
+
+def test_c5_200k_50k_vocab_top100_full_size(engine):
+    """BASELINE config 5 at full size (200 k shows, 50 k vocabulary, top-100), one weight triple of
+    the sweep: 20 GB operand, GEMM K = 50 048, k = 100 candidate lists (one-sided sweep)."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import WEIGHT_SWEEP, make_config
+
+    cat = make_config("C5")
+    w = WEIGHT_SWEEP[1]
+    dc = engine.upload(stage(cat.features()), w)
+    top = engine.to_host(engine.top_k_device(dc, w, 100, 0.1))
+    assert top.indices.shape == (200_000, 100)
+    valid = np.arange(100)[None, :] < top.counts[:, None]
+    assert (top.hybrid[valid] >= 0.1).all() and (np.diff(top.hybrid, axis=1)[valid[:, 1:]] <= 0).all()
+    rows = np.linspace(0, 199_999, 24).astype(np.int64)
+    assert_topk_matches(top, cat.features(), rows, w, 100, 0.1)
+    del dc
+    import torch
+    engine._ws = None
+    torch.cuda.empty_cache()
+
+
 def test_c5_shape_top100_sweep_on_reduced_rows(engine):
     """BASELINE config 5 shape (50 k vocab, top-100, weight sweep) on a 6 k-show slice: stresses
     GEMM K, the k=100 candidate lists and non-default weights."""
