@@ -40,7 +40,7 @@ int sm_count_cached(int* out) {
 struct Plan {
   int rows, cg, sb_count, col_tiles, splits, sb_per_group, grid, entries, kp, k6_grid;
   int tiles_per_split, sync_kb, sync_slack, stages, sym, sym_cap, cand_lists;
-  size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_keys, off_count, off_gtheta, off_gcnt,
+  size_t off_scratch, off_cand, off_cnt, off_theta, off_flag, off_floor, off_keys, off_count, off_gtheta, off_gcnt,
       off_glist, total;
 };
 
@@ -156,6 +156,7 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   pl->off_gcnt = off;    off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * 4 : 0), 256);
   pl->off_glist = off;   off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * pl->sym_cap * 8 : 0), 256);
   pl->off_flag = off;    off = align_up(off + static_cast<size_t>(pl->rows) * 4, 256);
+  pl->off_floor = off;   off = align_up(off + static_cast<size_t>(pl->rows) * 8, 256);
   pl->off_count = off;   off = align_up(off + 256, 256);
   pl->off_keys = off;    off = align_up(off + tvbf::k6_scratch_bytes(f->n_shows, sms), 256);
   pl->total = off;
@@ -319,6 +320,7 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   auto st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
+  double* floors = reinterpret_cast<double*>(ws + pl.off_floor);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + pl.off_keys);
   const int phases = p->phases == 0 ? 7 : p->phases;
   if (phases & 1) TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
@@ -329,7 +331,7 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     // every row through the exact kernel
     iota_kernel<<<(pl.rows + 255) / 256, 256, 0, st>>>(flagged, pl.rows);
     TVBF_LAUNCH_OK("iota_kernel");
-    rc = tvbf::k6_launch(sp, flagged, pl.rows, nullptr, p->row_begin, 1, keys, pl.k6_grid, *out, st);
+    rc = tvbf::k6_launch(sp, flagged, pl.rows, nullptr, nullptr, p->row_begin, 1, keys, pl.k6_grid, *out, st);
     if (rc != TVBF_OK) return rc;
     return TVBF_OK;
   }
@@ -349,11 +351,11 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   if (phases & 2) {
     const tvbf::CandLayout lay{0, pl.cand_lists, 1};
     rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.cand_lists, lay, pl.kp,
-                         p->row_begin, pl.rows, *out, flagged, st);
+                         p->row_begin, pl.rows, *out, flagged, floors, st);
     if (rc != TVBF_OK) return rc;
   }
   if ((phases & 4) && !p->skip_fallback) {
-    rc = tvbf::k6_launch(sp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, pl.k6_grid, *out, st);
+    rc = tvbf::k6_launch(sp, flagged, 0, out->stats + 0, floors, p->row_begin, 1, keys, pl.k6_grid, *out, st);
     if (rc != TVBF_OK) return rc;
   }
   return TVBF_OK;
@@ -372,7 +374,7 @@ namespace {
 struct SymPlan {
   Plan pl;            // geometry of a full-catalogue symmetric job
   int local_sb;       // super blocks owned by this rank
-  size_t off_prog, off_scratch, off_gcnt, off_glist, off_flag, off_keys, total;
+  size_t off_prog, off_scratch, off_gcnt, off_glist, off_flag, off_floor, off_keys, total;
 };
 
 int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int world, SymPlan* sp) {
@@ -408,6 +410,7 @@ int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int wo
   sp->off_gcnt = off;    off = align_up(off + static_cast<size_t>(f->n_pad) * 4, 256);
   sp->off_glist = off;   off = align_up(off + static_cast<size_t>(f->n_pad) * pl.sym_cap * 8, 256);
   sp->off_flag = off;    off = align_up(off + static_cast<size_t>(f->n_shows) * 4, 256);
+  sp->off_floor = off;   off = align_up(off + static_cast<size_t>(f->n_shows) * 8, 256);
   sp->off_keys = off;    off = align_up(off + tvbf::k6_scratch_bytes(f->n_shows, sms), 256);
   sp->total = off;
   return TVBF_OK;
@@ -531,6 +534,7 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   auto st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* flagged = reinterpret_cast<int*>(ws + sp.off_flag);
+  double* floors = reinterpret_cast<double*>(ws + sp.off_floor);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + sp.off_keys);
   TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
   const tvbf::ScoreParams scp = score_params(f, p);
@@ -538,12 +542,12 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   // gathered layout: [lists][n_shows][kp]
   const tvbf::CandLayout lay{p->row_begin, 1, f->n_shows};
   rc = tvbf::k5_launch(scp, static_cast<const uint2*>(cand_all), cnt_all, bound_all, lists, lay, sp.pl.kp,
-                       p->row_begin, rows, *out, flagged, st);
+                       p->row_begin, rows, *out, flagged, floors, st);
   if (rc != TVBF_OK) return rc;
   int sms = 0;
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
-  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, p->row_begin, 1, keys, sms, *out, st);
+  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, floors, p->row_begin, 1, keys, sms, *out, st);
 }
 
 size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed) {
@@ -572,7 +576,7 @@ int tvbf_exact_rows(const tvbf_features* f, const tvbf_params* p, const int32_t*
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
   const tvbf::ScoreParams sp = score_params(f, p);
-  return tvbf::k6_launch(sp, rows, n_rows_listed, nullptr, 0, 0,
+  return tvbf::k6_launch(sp, rows, n_rows_listed, nullptr, nullptr, 0, 0,
                          static_cast<unsigned long long*>(workspace), sms, *out,
                          static_cast<cudaStream_t>(stream));
 }

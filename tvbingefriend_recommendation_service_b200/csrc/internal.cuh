@@ -74,13 +74,13 @@ struct CandLayout {
 };
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
-              const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st);
+              const tvbf_topk_out& out, int* flagged_rows, double* flagged_floor, cudaStream_t st);
 int k1_local_super_blocks(int total_super_blocks, int world, int rank);
 int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st);
 size_t k6_scratch_bytes(int n_shows, int sm_count);
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
-              int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
-              const tvbf_topk_out& out, cudaStream_t st);
+              const double* floors, int row_begin, int rows_are_local, unsigned long long* key_scratch,
+              int grid, const tvbf_topk_out& out, cudaStream_t st);
 
 int k6_launch_matrix(const double* h, const double* g, const double* t, const double* m, int n,
                      int k, int exclude_self, double min_similarity, const int* rows, int n_listed,

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(K5_WARPS * 32)
 rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
                const int* __restrict__ cand_cnt, const float* __restrict__ cand_theta, int splits,
                const CandLayout lay, int kp, int row_begin, int n_rows, tvbf_topk_out out,
-               int* flagged_rows, int max_cand) {
+               int* flagged_rows, double* flagged_floor, int max_cand) {
   extern __shared__ __align__(16) uint8_t k5_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * K5_WARPS + warp;
@@ -193,6 +193,9 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
     if (!safe) {
       const int pos = atomicAdd(&out.stats[0], 1);
       flagged_rows[pos] = r;
+      // the k-th best exact score among the candidates is a lower bound of the true k-th best:
+      // the exact kernel only needs to keep columns that reach it
+      flagged_floor[pos] = bound;
     }
   }
 }
@@ -253,9 +256,10 @@ struct SelectSmem {
 // Exact top-k of one source row from its N order-preserving keys (0 = invalid): radix select of the
 // count-th largest key, everything above it, then the LOWEST column indices among keys equal to
 // it, finally ordered by (score desc, column asc).  Called by all threads of the block.
+// `keys` has n entries in ascending column order; entry e is column jmap[e] (or e when jmap is null).
 template <class Scorer>
-__device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, int n, int k,
-                                int valid, int i, size_t orow, const Scorer& scorer,
+__device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, const int* jmap, int n,
+                                int k, int valid, int i, size_t orow, const Scorer& scorer,
                                 const tvbf_topk_out& out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
   const int count = valid < k ? valid : k;
@@ -271,7 +275,7 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
       const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
 #pragma unroll 4
       for (int j = tid; j < n; j += nthr) {
-        const unsigned long long key = __ldcg(keys + j);
+        const unsigned long long key = keys[j];  // generic: global scratch or shared memory
         if (key != 0ull && (key & hi_mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 0xFFu], 1u);
       }
       __syncthreads();
@@ -291,11 +295,11 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
     const unsigned long long vstar = sm.prefix;  // count-th largest key
 #pragma unroll 4
     for (int j = tid; j < n; j += nthr) {
-      const unsigned long long key = __ldcg(keys + j);
+      const unsigned long long key = keys[j];
       if (key > vstar) {
         const int pos = atomicAdd(&sm.above, 1);
         sm.win_key[pos] = key;
-        sm.win_j[pos] = j;
+        sm.win_j[pos] = jmap ? jmap[j] : j;
       }
     }
     __syncthreads();
@@ -315,7 +319,7 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
       const int pos = before + __popc(bal & ((1u << lane) - 1u));
       if (flag && pos < need) {
         sm.win_key[above + pos] = vstar;
-        sm.win_j[above + pos] = j;
+        sm.win_j[above + pos] = jmap ? jmap[j] : j;
       }
       __syncthreads();
       if (tid == 0) sm.taken += chunk_total;
@@ -377,7 +381,7 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(kFullMask, my_valid, o);
     if (lane == 0 && my_valid) atomicAdd(&sm.valid, my_valid);
     __syncthreads();
-    select_and_emit(sm, keys, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
+    select_and_emit(sm, keys, nullptr, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
   }
 }
 
@@ -388,6 +392,8 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
 // looked up in the batch rows.  Sums run over ascending column index, exactly like text_dot.
 constexpr int K6B_THREADS = 1024;
 constexpr int K6B_MAXB = 8;
+constexpr int K6B_SMALL = 4096;   // survivors that are selected from shared memory
+constexpr int K6B_ROWNNZ = 192;   // text entries of a batch row staged in shared memory
 
 __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, int64_t e, int c) {
   // value of column c in the sorted row segment [b, e); the caller knows it is present
@@ -402,12 +408,22 @@ __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, 
 
 __global__ void __launch_bounds__(K6B_THREADS, 1)
 exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
-                          const int* __restrict__ count_ptr, int row_begin, int rows_are_local,
+                          const int* __restrict__ count_ptr, const double* __restrict__ floors,
+                          int row_begin, int rows_are_local, int mask_bytes,
                           unsigned long long* __restrict__ key_scratch, tvbf_topk_out out) {
-  extern __shared__ unsigned int mask_words[];  // vocab bytes, 4 per word
+  // dynamic smem: [mask: vocab bytes][small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
+  extern __shared__ __align__(16) unsigned int mask_words[];
   __shared__ SelectSmem sm;
-  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB];
+  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB], s_scan[K6B_THREADS / 32], s_base;
   __shared__ long long s_b[K6B_MAXB], s_e[K6B_MAXB];
+  __shared__ double s_floor[K6B_MAXB];
+  // the batch rows' own (column, value) lists, staged so that a mask hit is resolved by a binary
+  // search in shared memory (rows with more than K6B_ROWNNZ entries are searched in global memory)
+  __shared__ int s_cols[K6B_MAXB][K6B_ROWNNZ];
+  __shared__ double s_vals[K6B_MAXB][K6B_ROWNNZ];
+  unsigned long long* small_key =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(mask_words) + mask_bytes);
+  int* small_j = reinterpret_cast<int*>(small_key + K6B_SMALL);
   const tvbf_features& f = sp.f;
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = f.n_shows;
@@ -432,16 +448,25 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
         s_row[tid] = i;
         s_b[tid] = f.text_indptr[i];
         s_e[tid] = f.text_indptr[i + 1];
+        s_floor[tid] = floors ? floors[batch * B + tid] : -INFINITY;
       } else {
-        s_row[tid] = -1; s_b[tid] = 0; s_e[tid] = 0;
+        s_row[tid] = -1; s_b[tid] = 0; s_e[tid] = 0; s_floor[tid] = INFINITY;
       }
     }
     __syncthreads();
-    for (int r = 0; r < nb; ++r)
+    bool any_text = false;
+    for (int r = 0; r < nb; ++r) {
+      any_text |= s_e[r] > s_b[r];
+      const bool staged = (s_e[r] - s_b[r]) <= K6B_ROWNNZ;
       for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
         const int c = f.text_indices[e];
         atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
+        if (staged) {
+          s_cols[r][e - s_b[r]] = c;
+          s_vals[r][e - s_b[r]] = f.text_values[e];
+        }
       }
+    }
     __syncthreads();
 
     int my_valid[K6B_MAXB];
@@ -453,7 +478,8 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
       double acc[K6B_MAXB];
 #pragma unroll
       for (int r = 0; r < K6B_MAXB; ++r) acc[r] = 0.0;
-      const int64_t bj = f.text_indptr[j], ej = f.text_indptr[j + 1];
+      // a batch of shows without any text (a common reason for a tie plateau) never touches the CSR
+      const int64_t bj = any_text ? f.text_indptr[j] : 0, ej = any_text ? f.text_indptr[j + 1] : 0;
       // four entries per step: the index loads and mask probes of a step are independent, so
       // their latencies overlap; hits (rare) are resolved in ascending column order
       for (int64_t e = bj; e < ej; e += 4) {
@@ -470,7 +496,23 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
               const double v = f.text_values[e + u];
 #pragma unroll
               for (int r = 0; r < K6B_MAXB; ++r)
-                if (m[u] & (1u << r)) acc[r] += csr_lookup(f, s_b[r], s_e[r], c[u]) * v;
+                if (m[u] & (1u << r)) {
+                  const int len = static_cast<int>(s_e[r] - s_b[r]);
+                  double xv;
+                  if (len <= K6B_ROWNNZ) {
+                    int lo = 0, hi = len;
+                    xv = 0.0;
+                    while (lo < hi) {
+                      const int mid = (lo + hi) >> 1;
+                      const int cm = s_cols[r][mid];
+                      if (cm == c[u]) { xv = s_vals[r][mid]; break; }
+                      if (cm < c[u]) lo = mid + 1; else hi = mid;
+                    }
+                  } else {
+                    xv = csr_lookup(f, s_b[r], s_e[r], c[u]);
+                  }
+                  acc[r] += xv * v;
+                }
             }
           }
         }
@@ -516,7 +558,9 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
             mm = meta_score(f, i, j);
           }
           const double h = sp.wg * g + sp.wt * acc[r] + sp.wm * mm;
-          const bool ok = (h >= sp.min_similarity) && !(sp.exclude_self && j == i);
+          // only columns that reach the row's floor (a lower bound of its k-th best score) can
+          // matter; everything else is written as "invalid"
+          const bool ok = (h >= sp.min_similarity) && (h >= s_floor[r]) && !(sp.exclude_self && j == i);
           keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(h) : 0ull;
           my_valid[r] += ok;
         }
@@ -534,8 +578,43 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
     for (int r = 0; r < nb; ++r) {
       const int t = batch * B + r;
       const int orow = rows_are_local ? rows[t] : t;
-      select_and_emit(sm, keys0 + static_cast<size_t>(r) * n, n, sp.k, s_valid[r], s_row[r],
-                      static_cast<size_t>(orow), scorer, out);
+      const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
+      const int survivors = s_valid[r];
+      if (survivors <= K6B_SMALL) {
+        // few survivors: one ordered compaction pass over the dense keys, then select from smem
+        // (instead of ~10 passes over N keys)
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        for (int base = 0; base < n; base += K6B_THREADS) {
+          const int j = base + tid;
+          const unsigned long long key = j < n ? __ldcg(keys_r + j) : 0ull;
+          const bool flag = key != 0ull;
+          const unsigned bal = __ballot_sync(kFullMask, flag);
+          if (lane == 0) s_scan[tid >> 5] = __popc(bal);
+          __syncthreads();
+          int before = s_base;
+          for (int w = 0; w < (tid >> 5); ++w) before += s_scan[w];
+          if (flag) {
+            const int pos = before + __popc(bal & ((1u << lane) - 1u));
+            small_key[pos] = key;
+            small_j[pos] = j;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < K6B_THREADS / 32; ++w) tot += s_scan[w];
+            s_base += tot;
+          }
+          __syncthreads();
+          if (s_base >= survivors) break;
+        }
+        __syncthreads();
+        select_and_emit(sm, small_key, small_j, survivors, sp.k, survivors, s_row[r],
+                        static_cast<size_t>(orow), scorer, out);
+      } else {
+        select_and_emit(sm, keys_r, nullptr, n, sp.k, survivors, s_row[r], static_cast<size_t>(orow),
+                        scorer, out);
+      }
     }
   }
 }
@@ -545,7 +624,7 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
 // ---------------------------------------------------------------------------------------------
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
-              const tvbf_topk_out& out, int* flagged_rows, cudaStream_t st) {
+              const tvbf_topk_out& out, int* flagged_rows, double* flagged_floor, cudaStream_t st) {
   const int max_cand = splits * kp;
   const size_t smem = static_cast<size_t>(K5_WARPS) * max_cand * 40;
   if (smem > 200 * 1024) {
@@ -556,7 +635,8 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
                                     static_cast<int>(smem)));
   const int grid = (n_rows + K5_WARPS - 1) / K5_WARPS;
   rescore_kernel<<<grid, K5_WARPS * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, lay, kp,
-                                                    row_begin, n_rows, out, flagged_rows, max_cand);
+                                                    row_begin, n_rows, out, flagged_rows, flagged_floor,
+                                                    max_cand);
   TVBF_LAUNCH_OK("rescore_kernel");
   return TVBF_OK;
 }
@@ -567,19 +647,21 @@ size_t k6_scratch_bytes(int n_shows, int sm_count) {
 }
 
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
-              int row_begin, int rows_are_local, unsigned long long* key_scratch, int grid,
-              const tvbf_topk_out& out, cudaStream_t st) {
+              const double* floors, int row_begin, int rows_are_local, unsigned long long* key_scratch,
+              int grid, const tvbf_topk_out& out, cudaStream_t st) {
   if (sp.k > K6_MAXK) {
     tvbf_set_error("exact rows: k=%d exceeds %d", sp.k, K6_MAXK);
     return TVBF_ERR_INVALID;
   }
-  const size_t mask_bytes = (static_cast<size_t>(sp.f.vocab) + 3) / 4 * 4;
-  if (mask_bytes <= 200 * 1024) {
+  const size_t mask_bytes = (static_cast<size_t>(sp.f.vocab) + 15) / 16 * 16;
+  const size_t smem = mask_bytes + static_cast<size_t>(K6B_SMALL) * 12;
+  if (smem <= 200 * 1024) {
     TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_batched_kernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(mask_bytes)));
-    exact_rows_batched_kernel<<<grid, K6B_THREADS, mask_bytes, st>>>(
-        sp, rows, n_listed, count_ptr, row_begin, rows_are_local, key_scratch, out);
+                                      static_cast<int>(smem)));
+    exact_rows_batched_kernel<<<grid, K6B_THREADS, smem, st>>>(
+        sp, rows, n_listed, count_ptr, floors, row_begin, rows_are_local, static_cast<int>(mask_bytes),
+        key_scratch, out);
     TVBF_LAUNCH_OK("exact_rows_batched_kernel");
     return TVBF_OK;
   }
