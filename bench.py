@@ -312,6 +312,13 @@ def main() -> None:
     else:
         exec_tiles = tiles * tiles
     exec_flops = 2.0 * exec_tiles * 256 * 256 * k_pad / world
+    traffic = None
+    try:   # DRAM bytes per K1 launch from the committed ncu capture of this configuration
+        tj = json.loads((ROOT / "profiles" / "k1_traffic.json").read_text())
+        if world == 1 and not args.n_shows:
+            traffic = tj[args.config]["symmetric" if used_sym else "one_sided"]["bytes"]
+    except Exception:
+        traffic = None
     achieved = flops / (k1_ms_mean * 1e-3) / 1e12 if k1_ms_mean > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     line = {
@@ -320,8 +327,8 @@ def main() -> None:
         "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05) candidate pass, f64 for every reported score",
         "data": "synthetic", "config": bench_config(args, cfg),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
-                     "kernel": "hybrid_topk_kernel (K1)", "kernel_ms": k1_ms_mean,
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": "hybrid_topk_kernel (K1: threshold seed pass + sweep)", "kernel_ms": k1_ms_mean,
                      "flops_per_launch": flops, "peak_kind": f"bf16 sustained, {peaks['source']}",
                      "peak_burst": peaks["bf16_tflops"], "frac_of_burst": achieved / peaks["bf16_tflops"],
                      "symmetric_sweep": bool(used_sym), "executed_flops_per_launch": exec_flops,

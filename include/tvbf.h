@@ -120,6 +120,8 @@ typedef struct tvbf_topk_out {
 
 int tvbf_version(void);
 const char* tvbf_last_error(void);
+/* cumulative number of CUDA kernels this library has launched in this process */
+uint64_t tvbf_kernel_launches(void);
 /* sm count and compute capability of the current device; TVBF_ERR_UNSUPPORTED unless 10.x */
 int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

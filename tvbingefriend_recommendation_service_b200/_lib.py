@@ -61,6 +61,7 @@ class TopKOut(C.Structure):
 SIGNATURES = {
     "tvbf_version": (C.c_int, []),
     "tvbf_last_error": (C.c_char_p, []),
+    "tvbf_kernel_launches": (C.c_uint64, []),
     "tvbf_device_info": (C.c_int, [C.POINTER(c_int32)] * 3),
     "tvbf_prep_csr_normalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "tvbf_prep_csr_to_operand": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,

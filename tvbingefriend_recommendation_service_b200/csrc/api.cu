@@ -2,10 +2,14 @@
 // sequence K1 (tcgen05 candidate pass) -> K5 (fp64 rescore + certificate) -> K6 (exact repair).
 #include "internal.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 
 static thread_local char g_last_error[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void tvbf_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void tvbf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -274,6 +278,8 @@ extern "C" {
 int tvbf_version(void) { return TVBF_VERSION; }
 
 const char* tvbf_last_error(void) { return g_last_error; }
+
+uint64_t tvbf_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;

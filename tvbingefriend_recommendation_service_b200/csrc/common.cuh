@@ -15,6 +15,7 @@
 // error plumbing (no exceptions cross the C ABI)
 // ---------------------------------------------------------------------------------------------
 void tvbf_set_error(const char* fmt, ...);
+void tvbf_count_launch(void);  // every kernel launch of the library is counted (tvbf_kernel_launches)
 
 #define TVBF_CUDA_OK(expr)                                                              \
   do {                                                                                  \
@@ -41,6 +42,7 @@ void tvbf_set_error(const char* fmt, ...);
       tvbf_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));          \
       return TVBF_ERR_CUDA;                                                             \
     }                                                                                   \
+    tvbf_count_launch();                                                                \
   } while (0)
 
 // Column-side record the epilogue reads once per score (16 bytes -> one LDS.128).

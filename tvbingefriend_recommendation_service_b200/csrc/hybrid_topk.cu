@@ -835,6 +835,7 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   TVBF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, kp, idesc));
+  tvbf_count_launch();
   return TVBF_OK;
 }
 

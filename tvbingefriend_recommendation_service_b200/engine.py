@@ -186,9 +186,15 @@ class HybridTopKEngine:
         if text_dtype not in _DTYPES:
             raise ValueError(f"text_dtype must be one of {list(_DTYPES)}")
         self.text_dtype = text_dtype
-        self.kernel_launches = 0      # kernels of libtvbf launched through this engine
+        self._launch_base = int(self.lib.tvbf_kernel_launches())
         self._ws: torch.Tensor | None = None
         self._pinned: dict = {}
+
+    @property
+    def kernel_launches(self) -> int:
+        """CUDA kernels libtvbf has launched since this engine was created (counted inside the
+        library at every launch)."""
+        return int(self.lib.tvbf_kernel_launches()) - self._launch_base
 
     # ------------------------------------------------------------------------------------ utils
     def _stream(self) -> int:
@@ -243,7 +249,6 @@ class HybridTopKEngine:
             check(lib.tvbf_prep_csr_to_operand(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n,
                                                operand.data_ptr(), k_pad, 0, scale, code, stream),
                   "tvbf_prep_csr_to_operand")
-            self.kernel_launches += 2
 
             f = Features()
             f.n_shows, f.n_pad, f.k_pad, f.text_dtype = n, n_pad, k_pad, code
@@ -271,7 +276,6 @@ class HybridTopKEngine:
                 check(lib.tvbf_prep_dense_to_operand(g_norm.data_ptr(), n, g_norm.shape[1], operand.data_ptr(),
                                                      k_pad, col, scale * float(np.sqrt(ratio)), code, stream),
                       "tvbf_prep_dense_to_operand")
-                self.kernel_launches += 2
                 keep.append(g_norm)
                 col += g_norm.shape[1]
                 folded = True
@@ -281,7 +285,6 @@ class HybridTopKEngine:
                 g8 = raw["genre"]
                 check(lib.tvbf_prep_genre_bits(g8.data_ptr(), n, g8.shape[1], col_side.data_ptr(), stream),
                       "tvbf_prep_genre_bits")
-                self.kernel_launches += 1
                 f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(g8.shape[1])
             else:
                 f.genre_mode, f.genre_dim = _lib.GROUP_FOLDED, int(st.genre.shape[1])
@@ -292,7 +295,6 @@ class HybridTopKEngine:
                                              m8[2].data_ptr(), m8[2].shape[1], n, n_pad, f.meta_kind,
                                              col_side.data_ptr(), meta_scale.data_ptr(), stream),
                       "tvbf_prep_meta_ids")
-                self.kernel_launches += 1
                 f.meta_mode = _lib.GROUP_PACKED
             else:
                 f.meta_mode = _lib.GROUP_FOLDED
@@ -343,11 +345,6 @@ class HybridTopKEngine:
                               ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
             check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(cout), ws.data_ptr(),
                                             ws.numel(), self._stream()), "tvbf_hybrid_topk")
-            ph = 7 if phases == 0 else phases
-            if force_exact:
-                self.kernel_launches += 2
-            else:
-                self.kernel_launches += bin(ph & (3 if skip_fallback else 7)).count("1")
         t["row_begin"] = row_begin
         return t
 
@@ -413,7 +410,6 @@ class HybridTopKEngine:
             theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
             check(self.lib.tvbf_sym_seed(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
                                          ws.numel(), self._stream()), "tvbf_sym_seed")
-            self.kernel_launches += 2
         return theta
 
     def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
@@ -431,7 +427,6 @@ class HybridTopKEngine:
             check(self.lib.tvbf_sym_sweep(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), cand.data_ptr(),
                                           cnt.data_ptr(), bound.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
                   "tvbf_sym_sweep")
-            self.kernel_launches += 2
         return cand, cnt, bound
 
     def sym_rescore(self, cat: DeviceCatalogue, weights, k, min_similarity, cand_all: torch.Tensor,
@@ -460,7 +455,6 @@ class HybridTopKEngine:
                 check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(), cnt_all.data_ptr(),
                                                   bound_all.data_ptr(), world, C.byref(cout), ws.data_ptr(),
                                                   ws.numel(), self._stream()), "tvbf_rescore_lists")
-                self.kernel_launches += 2
         return t
 
     def top_k_device_sym_sharded(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
@@ -520,7 +514,6 @@ class HybridTopKEngine:
             ws = self._workspace(nbytes)
             check(self.lib.tvbf_exact_rows(C.byref(cat.c), C.byref(p), rows_d.data_ptr(), r, C.byref(out),
                                            ws.data_ptr(), ws.numel(), self._stream()), "tvbf_exact_rows")
-            self.kernel_launches += 1
         return self.to_host(t)
 
     def matrix_rows_topk(self, hybrid: torch.Tensor, genre: torch.Tensor, text: torch.Tensor,
@@ -551,7 +544,6 @@ class HybridTopKEngine:
                                                  metadata.data_ptr(), n, C.byref(p), rows_d.data_ptr(), r,
                                                  C.byref(out), ws.data_ptr(), ws.numel(), self._stream()),
                   "tvbf_matrix_rows_topk")
-            self.kernel_launches += 1
         return self.to_host(t)
 
     # ------------------------------------------------------------------------------------ matrices
@@ -576,7 +568,6 @@ class HybridTopKEngine:
                 xn = torch.zeros((n, d), dtype=torch.float64, device=dev)
                 check(self.lib.tvbf_csr_to_dense_f64(indptr.data_ptr(), indices.data_ptr(), vals.data_ptr(), n, d,
                                                      xn.data_ptr(), stream), "tvbf_csr_to_dense_f64")
-                self.kernel_launches += 2
             else:
                 a = np.ascontiguousarray(np.asarray(x), dtype=np.float64)
                 if a.ndim != 2:
@@ -586,11 +577,9 @@ class HybridTopKEngine:
                 xn = torch.empty_like(raw)
                 check(self.lib.tvbf_prep_dense_normalize(raw.data_ptr(), n, d, xn.data_ptr(), stream),
                       "tvbf_prep_dense_normalize")
-                self.kernel_launches += 1
             out = torch.empty((n, n), dtype=torch.float64, device=dev)
             check(self.lib.tvbf_cosine_matrix_f64(xn.data_ptr(), n, d, out.data_ptr(), stream),
                   "tvbf_cosine_matrix_f64")
-            self.kernel_launches += 1
         return out
 
     def hybrid_combine(self, g: torch.Tensor, t: torch.Tensor, m: torch.Tensor, wg: float, wt: float,
@@ -601,7 +590,6 @@ class HybridTopKEngine:
             check(self.lib.tvbf_hybrid_combine_f64(g.data_ptr(), t.data_ptr(), m.data_ptr(), float(wg), float(wt),
                                                    float(wm), g.numel(), out.data_ptr(), self._stream()),
                   "tvbf_hybrid_combine_f64")
-            self.kernel_launches += 1
         return out
 
     def matrix_stats(self, mat: torch.Tensor) -> dict:
@@ -612,7 +600,6 @@ class HybridTopKEngine:
             out5 = (C.c_double * 5)()
             check(self.lib.tvbf_matrix_stats_f64(mat.data_ptr(), n, out5, ws.data_ptr(), ws.numel(), self._stream()),
                   "tvbf_matrix_stats_f64")
-            self.kernel_launches += 4 + 2 * 17
         return {"mean": float(out5[0]), "std": float(out5[1]), "min": float(out5[2]),
                 "max": float(out5[3]), "median": float(out5[4])}
 
@@ -624,7 +611,6 @@ class HybridTopKEngine:
             fn = self.lib.tvbf_debug_gemm_tile_pair if pair else self.lib.tvbf_debug_gemm_tile
             check(fn(C.byref(cat.c), int(row0), int(col0), out.data_ptr(), self._stream()),
                   "tvbf_debug_gemm_tile")
-            self.kernel_launches += 1
         return out
 
 
