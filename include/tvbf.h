@@ -215,6 +215,26 @@ size_t tvbf_matrix_stats_workspace_bytes(void);
 int tvbf_matrix_stats_f64(const double* mat, int32_t n, double* out5_host, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- streaming statistics for catalogues whose N x N matrices cannot exist
+ *      (get_similarity_statistics, ml/similarity_computer.py:171-190, as used by
+ *      scripts/compute_similarities.py:119-131).  One symmetric tensor-core sweep accumulates, for
+ *      genre / text / metadata / hybrid over the strict upper triangle: sum and sum of squares
+ *      (fp64), min / max (fp32), the count of exact zeros and a 1024-bin histogram; `accum` is a
+ *      device buffer of tvbf_stats_accum_bytes() holding, in this order:
+ *        double sum[4], sumsq[4]; uint64 zeros[4]; uint64 hist[4][1024]; uint32 min_bits[4],
+ *        max_bits[4]; float hi[4]; int32 n_cand; int32 cand_ij[2][2048][2]; float cand_val[2][2048]
+ *      (cand_*: argmax candidates of text and hybrid, to be rescored exactly with
+ *      tvbf_score_pairs).  Text values come from the fp16 operand (relative error <= 1e-3 per
+ *      element, correlated per vocabulary column): mean / std agree with float64 to ~1e-5
+ *      relative, the median to one bin. */
+size_t tvbf_stats_accum_bytes(void);
+int tvbf_similarity_stats(const tvbf_features* f, const tvbf_params* p, void* accum, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* exact float64 scores of explicit pairs: out4[p] = {hybrid, genre, text, metadata} of
+ * (pairs[2p], pairs[2p+1]). */
+int tvbf_score_pairs(const tvbf_features* f, const tvbf_params* p, const int32_t* pairs,
+                     int32_t n_pairs, double* out4, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------- */
 /* raw tensor-core tile dump: out[i, j] = sum_k operand[row0+i, k] * operand[col0+j, k] for a
  * 128 x 256 tile (fp32), used by the tests to validate descriptors and the error bound. */

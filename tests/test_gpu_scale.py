@@ -176,3 +176,68 @@ def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world):
     m = ref.indices >= 0
     assert np.array_equal(got.hybrid[m], ref.hybrid[m])
     assert_topk_matches(got, cat.features(), np.arange(0, 6000, 97), w, k, ms)
+
+
+@pytest.mark.parametrize("mode,norm,w", [("hstack", True, (0.4, 0.5, 0.1)), ("mean3", False, (0.3, 0.6, 0.1))])
+def test_streaming_statistics_match_the_full_matrices(engine, mode, norm, w):
+    """get_similarity_statistics for all four matrices from one streaming sweep (no N x N) against
+    the reference arithmetic on the materialised float64 matrices (oracle), N = 3000."""
+    from oracle.reference_paths import ProductionRows, SimilarityComputerOracle
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(3000, 2048, nnz=30, seed=17)
+    got = SimilarityComputer(*w, engine=engine).compute_similarity_statistics(
+        cat.features(), metadata_mode=mode, normalize_weights=norm)
+    pr = ProductionRows(cat.features(), *w, metadata_mode=mode, normalize_weights=norm)
+    mats = {k: np.zeros((3000, 3000)) for k in ("hybrid_similarity", "genre_similarity", "text_similarity",
+                                                "metadata_similarity")}
+    for i in range(3000):
+        h, g, t, m = pr.row(i)
+        mats["hybrid_similarity"][i], mats["genre_similarity"][i] = h, g
+        mats["text_similarity"][i], mats["metadata_similarity"][i] = t, m
+    for name, mat in mats.items():
+        ref = SimilarityComputerOracle.get_similarity_statistics(mat)
+        g_ = got[name]
+        # genre / metadata are exact up to fp32 rounding; text (and the hybrid through it) carries the
+        # fp16 rounding of the operand, which is correlated per vocabulary column: ~1e-5 relative on
+        # the mean at N = 3000, shrinking with N
+        tol = 2e-6 if name in ("genre_similarity", "metadata_similarity") else 3e-5
+        assert g_["mean"] == pytest.approx(ref["mean"], rel=tol, abs=1e-9), name
+        assert g_["std"] == pytest.approx(ref["std"], rel=10 * tol, abs=1e-8), name
+        assert g_["min"] == pytest.approx(ref["min"], abs=1e-6), name
+        assert g_["max"] == pytest.approx(ref["max"], rel=1e-6, abs=1e-6), name
+        assert abs(g_["median"] - ref["median"]) <= g_["median_resolution"] * 1.01, (name, g_["median"], ref["median"])
+
+
+def test_streaming_statistics_at_c3_scale(engine):
+    """100 k shows: statistics of 5e9 pairs per matrix in one sweep; sanity against a row sample."""
+    from oracle.reference_paths import ProductionRows
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+    cat = make_config("C3")
+    got = SimilarityComputer(engine=engine).compute_similarity_statistics(cat.features())
+    pr = ProductionRows(cat.features(), metadata_mode="hstack", normalize_weights=True)
+    n = 100_000
+    count = n * (n - 1) / 2
+
+    def exact_mean(xn):
+        """mean over i<j of <x_i, x_j> = (|sum_i x_i|^2 - sum_i |x_i|^2) / 2 / count, float64."""
+        col = np.asarray(xn.sum(axis=0)).ravel()
+        sq = float(xn.multiply(xn).sum()) if hasattr(xn, "multiply") else float((xn * xn).sum())
+        return (float(col @ col) - sq) / 2 / count
+
+    mg, mt, mm = exact_mean(pr.G), exact_mean(pr.T), exact_mean(pr.M[0])
+    assert got["genre_similarity"]["mean"] == pytest.approx(mg, rel=2e-6)
+    assert got["metadata_similarity"]["mean"] == pytest.approx(mm, rel=2e-6)
+    assert got["text_similarity"]["mean"] == pytest.approx(mt, rel=1e-5)
+    assert got["hybrid_similarity"]["mean"] == pytest.approx(pr.gw * mg + pr.tw * mt + pr.mw * mm, rel=1e-5)
+    rows = np.linspace(0, 99_999, 40).astype(np.int64)
+    sample = np.concatenate([np.delete(pr.row(int(i))[0], int(i)) for i in rows])   # hybrid, self removed
+    assert got["hybrid_similarity"]["std"] == pytest.approx(sample.std(), rel=0.1)
+    assert abs(got["hybrid_similarity"]["median"] - np.median(sample)) < 0.02
+    for name in ("genre_similarity", "text_similarity", "metadata_similarity", "hybrid_similarity"):
+        s = got[name]
+        assert 0.0 <= s["min"] <= s["median"] <= s["max"] <= 1.0 + 2e-7 and s["std"] >= 0   # genre/metadata extrema are fp32
+    assert got["text_similarity"]["max"] == pytest.approx(1.0, abs=1e-9)   # planted duplicate shows

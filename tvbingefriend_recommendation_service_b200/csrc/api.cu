@@ -556,6 +556,82 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, floors, p->row_begin, 1, keys, sms, *out, st);
 }
 
+// ---- streaming statistics of the four similarity matrices (no N x N) --------------------------
+size_t tvbf_stats_accum_bytes(void) { return sizeof(tvbf::StatsAccum); }
+
+int tvbf_similarity_stats(const tvbf_features* f, const tvbf_params* p, void* accum, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(p && accum && workspace, "tvbf_similarity_stats: NULL argument");
+  TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED,
+               "streaming statistics need binary genre / one-hot metadata features");
+  TVBF_REQUIRE(p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0,
+               "streaming statistics need non-negative weights");
+  tvbf_params q = *p;
+  q.row_begin = 0;
+  q.row_end = f->n_shows;
+  q.k = 20;
+  q.min_similarity = 0.5;
+  q.exclude_self = 1;
+  q.splits = 0;
+  q.tuning = (p->tuning & (1 << 30)) | 2 | (1 << 20);   // CTA pairs, plan as a one-sided job
+  Plan pl;
+  rc = make_plan(f, &q, &pl);
+  if (rc != TVBF_OK) return rc;
+  if (workspace_bytes < pl.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  int sms = 0;
+  rc = sm_count_cached(&sms);
+  if (rc != TVBF_OK) return rc;
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  tvbf::K1Params kp;
+  rc = fill_k1_params(f, &q, pl, ws, &kp);
+  if (rc != TVBF_OK) return rc;
+  // symmetric schedule, 8 splits, one ring stage given up for the shared-memory histogram
+  const int clusters = sms / 2;
+  kp.sym = 1;
+  kp.splits = 8;
+  while (kp.splits > 1 && (clusters / kp.splits < 1 || pl.col_tiles / kp.splits < 8)) --kp.splits;
+  kp.rb_count = pl.sb_count;
+  kp.rb_per_group = clusters / kp.splits;
+  if (kp.rb_per_group > pl.sb_count) kp.rb_per_group = pl.sb_count;
+  kp.tiles_per_split = (pl.col_tiles + kp.splits - 1) / kp.splits;
+  kp.stages = 5;
+  kp.stats = static_cast<tvbf::StatsAccum*>(accum);
+  kp.inv_scale2 = static_cast<float>(std::ldexp(1.0, -2 * f->text_scale_log2));
+  kp.w_text_plain = static_cast<float>(p->text_weight);
+  kp.w_genre = static_cast<float>(p->genre_weight);
+  kp.w_meta = static_cast<float>(p->metadata_weight);
+  static thread_local tvbf::StatsAccum init;   // 80 KB: keep it off the stack
+  memset(&init, 0, sizeof(init));
+  const double wsum = p->genre_weight + p->text_weight + p->metadata_weight;
+  for (int qi = 0; qi < 4; ++qi) {
+    init.min_bits[qi] = 0x7f800000u;
+    init.max_bits[qi] = 0u;
+    init.hi[qi] = static_cast<float>((qi == 3 ? (wsum > 0 ? wsum : 1.0) : 1.0) * 1.002);
+  }
+  for (int qi = 0; qi < 2; ++qi)
+    for (int c = 0; c < tvbf::kStatsCand; ++c) { init.cand_val[qi][c] = -1.0f; init.cand_ij[qi][c][0] = -1; init.cand_ij[qi][c][1] = -1; }
+  // staged through pageable host memory: small (80 KB) and synchronous with respect to the host
+  TVBF_CUDA_OK(cudaMemcpyAsync(accum, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  TVBF_CUDA_OK(cudaStreamSynchronize(st));
+  TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+  return tvbf::k1_launch_stats(f, kp, kp.rb_per_group * kp.splits * 2, st);
+}
+
+int tvbf_score_pairs(const tvbf_features* f, const tvbf_params* p, const int32_t* pairs,
+                     int32_t n_pairs, double* out4, void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(p && pairs && out4 && n_pairs > 0, "tvbf_score_pairs: bad arguments");
+  const tvbf::ScoreParams sp = score_params(f, p);
+  return tvbf::score_pairs_launch(sp, pairs, n_pairs, out4, static_cast<cudaStream_t>(stream));
+}
+
 size_t tvbf_exact_workspace_bytes(const tvbf_features* f, int32_t n_rows_listed) {
   if (f == nullptr || n_rows_listed <= 0) return 0;
   int sms = 0;

@@ -238,12 +238,15 @@ struct Pacer {
   }
 };
 
-template <int E, bool kDump, int CG, bool kSym>
-__global__ void __launch_bounds__(Roles<kSym>::THREADS, 1)
+// kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep
+template <int E, bool kDump, int CG, int kMode>
+__global__ void __launch_bounds__(Roles<(kMode != 0)>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
                    const uint32_t idesc) {
   using L = Smem<CG>;
+  constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 epilogue warps
+  constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
   constexpr int STAGES = L::STAGES;
   constexpr int EPI = Roles<kSym>::EPI, PRODUCER_WARP = Roles<kSym>::PRODUCER, MMA_WARP = Roles<kSym>::MMA;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
@@ -321,10 +324,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (!kDump) {
             mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             if (elect_one()) {
-              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + (kSym ? MS_BYTES : 0u));
+              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? MS_BYTES : 0u));
               bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
               bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
-              if (kSym)  // snapshot of the column shows' thresholds (stale = lower = conservative)
+              if (kSym && !kStats)  // snapshot of the column shows' thresholds (stale = lower = conservative)
                 bulk_load_1d(smem + L::OFF_TH + b * MS_BYTES, p.g_theta + col0, MS_BYTES, &col_full[b]);
             }
             __syncwarp();
@@ -412,6 +415,18 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int CAP = 32 * E;
     uint2* my_list = p.scratch + (static_cast<size_t>(blockIdx.x) * BM + row_in_tile) * CAP;
     uint32_t it = 0;
+    // ---- statistics sweep state (kStats): per-thread fp64 sums, extrema, argmax of text / hybrid,
+    // and a CTA-wide histogram in the shared memory of the (unused) last ring stage
+    double st_sum[4] = {0, 0, 0, 0}, st_sq[4] = {0, 0, 0, 0};
+    float st_min[4] = {3e38f, 3e38f, 3e38f, 3e38f}, st_max[4] = {-1.f, -1.f, -1.f, -1.f};
+    unsigned long long st_zero[4] = {0, 0, 0, 0};
+    int st_arg_i[2] = {-1, -1}, st_arg_j[2] = {-1, -1};
+    float st_arg_v[2] = {-1.f, -1.f};
+    unsigned int* shist = reinterpret_cast<unsigned int*>(smem + L::OFF_A + (STAGES - 1) * A_BYTES);
+    if (kStats) {
+      for (int b = threadIdx.x; b < 4 * kStatsBins; b += 32 * EPI) shist[b] = 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+    }
     for (int item = cluster_id; item < n_items; item += num_clusters) {
       ItemCoord c = item_coord(p, item);
       if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
@@ -430,6 +445,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         rn_wg = rs.genre_rnorm * p.w_genre;
         // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories)
         ci_wm = p.meta_scale[row] * p.w_meta * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
+        if (kStats) {  // plain cosines here; the weights enter only the hybrid
+          rn_wg = rs.genre_rnorm;
+          ci_wm = p.meta_scale[row] * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
+        }
       }
       float theta = row_valid ? p.theta_init : __int_as_float(0x7f800000);  // +inf: never append
       int cnt = 0;
@@ -498,7 +517,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t b = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int col0 = kDump ? p.dump_col0 : jt * BN;
-        if (kSym) {
+        if (kSym && !kStats) {
           // current shared threshold of this thread's show (raised by any CTA working on it)
           unsigned int tb = 0x7f800000u;
           if (row_valid)
@@ -515,6 +534,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // off-diagonal tiles also feed the column shows (their mirror tile is never computed)
         const bool do_col = kSym && row_valid && jt != c.sb;
 
+        float tile_sum[4] = {0.f, 0.f, 0.f, 0.f}, tile_sq[4] = {0.f, 0.f, 0.f, 0.f};
+        float stat_scale[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) stat_scale[q] = kStats ? static_cast<float>(kStatsBins) / p.stats->hi[q] : 0.f;
         // score 16 accumulator columns held in registers
         auto score16 = [&](const uint32_t (&acc)[16], int cbase) {
 #pragma unroll
@@ -531,7 +554,31 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               u = fmaf(a, w_text, u);
               u = fmaf(fabsf(a), w_text_err, u);
               const int col = col0 + cbase + e;
-              if (kSym) {
+              if (kStats) {
+                if (row_valid && col > row && col < p.n_shows) {   // strict upper triangle
+                  float v[4];
+                  v[0] = gdot * rn_wg;
+                  v[1] = a * p.inv_scale2;
+                  v[2] = mdot * ci_wm;
+                  v[3] = fmaf(p.w_genre, v[0], fmaf(p.w_text_plain, v[1], p.w_meta * v[2]));
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    tile_sum[q] += v[q];
+                    tile_sq[q] = fmaf(v[q], v[q], tile_sq[q]);
+                    st_min[q] = fminf(st_min[q], v[q]);
+                    st_max[q] = fmaxf(st_max[q], v[q]);
+                    if (v[q] == 0.0f) {
+                      ++st_zero[q];
+                    } else {
+                      int bin = static_cast<int>(v[q] * stat_scale[q]);
+                      bin = bin < 0 ? 0 : (bin >= kStatsBins ? kStatsBins - 1 : bin);
+                      atomicAdd(&shist[q * kStatsBins + bin], 1u);
+                    }
+                  }
+                  if (v[1] > st_arg_v[0]) { st_arg_v[0] = v[1]; st_arg_i[0] = row; st_arg_j[0] = col; }
+                  if (v[3] > st_arg_v[1]) { st_arg_v[1] = v[3]; st_arg_i[1] = row; st_arg_j[1] = col; }
+                }
+              } else if (kSym) {
                 if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col);
                 // padded columns carry threshold +inf, so no bound check is needed here
                 if (do_col && u > sth[cbase + e]) sym_append(col, u, row);
@@ -566,7 +613,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             else mbar_arrive(&acc_empty[b]);
           }
           score16(acc_b, (ch + 1) * 16);
-          if (kSym && ((ch & 2) != 0 || ch + 2 >= ch1)) {
+          if (kSym && !kStats && ((ch & 2) != 0 || ch + 2 >= ch1)) {
             // every 64 columns: flush the queued appends, then serve the threshold refreshes they
             // raised, one show at a time
             sym_flush();
@@ -612,6 +659,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
         if (!kDump) mbar_arrive(&col_empty[b]);  // column-side buffer b may be refilled
+        if (kStats) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { st_sum[q] += tile_sum[q]; st_sq[q] += tile_sq[q]; }
+        }
       }
 
       if (!kDump && !kSym) {
@@ -641,6 +692,55 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       }
+    }
+    if (kStats) {
+      StatsAccum* sa = p.stats;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        double s1 = st_sum[q], s2 = st_sq[q];
+        unsigned long long z = st_zero[q];
+        float mn = st_min[q], mx = st_max[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(kFullMask, s1, o);
+          s2 += __shfl_xor_sync(kFullMask, s2, o);
+          z += __shfl_xor_sync(kFullMask, z, o);
+          mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+          mx = fmaxf(mx, __shfl_xor_sync(kFullMask, mx, o));
+        }
+        if (lane == 0) {
+          atomicAdd(&sa->sum[q], s1);
+          atomicAdd(&sa->sumsq[q], s2);
+          atomicAdd(&sa->zeros[q], z);
+          if (mx >= 0.f) {   // at least one element seen (all values are >= 0)
+            atomicMin(&sa->min_bits[q], __float_as_uint(mn));
+            atomicMax(&sa->max_bits[q], __float_as_uint(mx));
+          }
+        }
+      }
+      // argmax candidates of text (0) and hybrid (1): best of the warp -> one slot per warp
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v = st_arg_v[q];
+        int bi = st_arg_i[q], bj = st_arg_j[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(kFullMask, v, o);
+          const int oi = __shfl_xor_sync(kFullMask, bi, o), oj = __shfl_xor_sync(kFullMask, bj, o);
+          if (ov > v) { v = ov; bi = oi; bj = oj; }
+        }
+        if (lane == 0 && bi >= 0) {
+          const int slot = (blockIdx.x * EPI + warp) % kStatsCand;   // private to this warp (grid <= 256 CTAs)
+          if (v > sa->cand_val[q][slot]) {
+            sa->cand_val[q][slot] = v;
+            sa->cand_ij[q][slot][0] = bi;
+            sa->cand_ij[q][slot][1] = bj;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+      for (int b = threadIdx.x; b < 4 * kStatsBins; b += 32 * EPI)
+        if (shist[b]) atomicAdd(&sa->hist[b / kStatsBins][b % kStatsBins], static_cast<unsigned long long>(shist[b]));
     }
   }
 
@@ -806,7 +906,7 @@ int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
   return best;
 }
 
-template <int E, bool kDump, int CG, bool kSym>
+template <int E, bool kDump, int CG, int kMode>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
   using L = Smem<CG>;
   CUtensorMap ta, tb;
@@ -814,14 +914,14 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   if (rc != TVBF_OK) return rc;
   rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump, CG, kSym>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(L::BYTES)));
   const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(Roles<kSym>::THREADS);
+  cfg.blockDim = dim3(Roles<(kMode != 0)>::THREADS);
   cfg.dynamicSmemBytes = L::BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -860,7 +960,7 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
         const int clusters = grid / 2;
         seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
         if (seed.rb_per_group < 1) seed.rb_per_group = 1;
-        int rc = launch_k1<4, false, 2, false>(f, seed, seed.rb_per_group * 2, st);
+        int rc = launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
         if (rc != TVBF_OK) return rc;
         TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
       }
@@ -870,20 +970,20 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, static_cast<size_t>(n_pad) * kp.sym_cap * 8, st));
     K1Params sweep = kp;
     sweep.tile_stride = 1;
-    return launch_k1<4, false, 2, true>(f, sweep, grid, st);
+    return launch_k1<4, false, 2, 1>(f, sweep, grid, st);
   }
   if (cta_group == 2) {
     switch (entries_per_lane) {
-      case 4: return launch_k1<4, false, 2, false>(f, kp, grid, st);
-      case 8: return launch_k1<8, false, 2, false>(f, kp, grid, st);
-      case 16: return launch_k1<16, false, 2, false>(f, kp, grid, st);
+      case 4: return launch_k1<4, false, 2, 0>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 2, 0>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 2, 0>(f, kp, grid, st);
       default: break;
     }
   } else {
     switch (entries_per_lane) {
-      case 4: return launch_k1<4, false, 1, false>(f, kp, grid, st);
-      case 8: return launch_k1<8, false, 1, false>(f, kp, grid, st);
-      case 16: return launch_k1<16, false, 1, false>(f, kp, grid, st);
+      case 4: return launch_k1<4, false, 1, 0>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 1, 0>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 1, 0>(f, kp, grid, st);
       default: break;
     }
   }
@@ -892,8 +992,12 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
 }
 
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st) {
-  return cta_group == 2 ? launch_k1<4, true, 2, false>(f, kp, 2, st)
-                        : launch_k1<4, true, 1, false>(f, kp, 1, st);
+  return cta_group == 2 ? launch_k1<4, true, 2, 0>(f, kp, 2, st)
+                        : launch_k1<4, true, 1, 0>(f, kp, 1, st);
+}
+
+int k1_launch_stats(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
+  return launch_k1<4, false, 2, 2>(f, kp, grid, st);
 }
 
 int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st) {

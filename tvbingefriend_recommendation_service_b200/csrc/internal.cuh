@@ -5,6 +5,23 @@
 
 namespace tvbf {
 
+// Raw accumulators of the streaming upper-triangle statistics (ml/similarity_computer.py:171-190
+// for catalogues whose N x N matrices cannot exist).  Matrix order: genre, text, metadata, hybrid.
+constexpr int kStatsBins = 1024;
+constexpr int kStatsCand = 2048;
+struct StatsAccum {
+  double sum[4];
+  double sumsq[4];
+  unsigned long long zeros[4];            // elements that are exactly 0 (kept out of the histogram)
+  unsigned long long hist[4][kStatsBins]; // bin b covers [b, b+1) * hi / kStatsBins
+  unsigned int min_bits[4];               // float bits of the smallest / largest element seen
+  unsigned int max_bits[4];
+  float hi[4];                            // histogram range per matrix
+  int n_cand;                             // reserved
+  int cand_ij[2][kStatsCand][2];          // argmax candidates of {text, hybrid}: one slot per epilogue warp
+  float cand_val[2][kStatsCand];
+};
+
 // parameters of the tcgen05 candidate kernel (hybrid_topk.cu)
 struct K1Params {
   const TvbfColSide* col_side;
@@ -32,6 +49,9 @@ struct K1Params {
   // and every score is offered to BOTH shows' candidate lists, which therefore live in global
   // memory and are shared by all CTAs
   int sym;
+  StatsAccum* stats;       // statistics sweep only
+  float inv_scale2;        // 2^-2s: accumulator -> text cosine
+  float w_text_plain;      // text weight without the error inflation (statistics sweep)
   int sb_world;            // super blocks are dealt to `sb_world` GPUs in zigzag order ...
   int sb_rank;             // ... and this launch owns those of `sb_rank` (1 / 0 on a single GPU)
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
@@ -77,6 +97,8 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const tvbf_topk_out& out, int* flagged_rows, double* flagged_floor, cudaStream_t st);
 int k1_local_super_blocks(int total_super_blocks, int world, int rank);
 int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st);
+int k1_launch_stats(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st);
+int score_pairs_launch(const ScoreParams& sp, const int* pairs, int n_pairs, double* out, cudaStream_t st);
 size_t k6_scratch_bytes(int n_shows, int sm_count);
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               const double* floors, int row_begin, int rows_are_local, unsigned long long* key_scratch,

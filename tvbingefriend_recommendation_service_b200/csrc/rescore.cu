@@ -619,6 +619,27 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
   }
 }
 
+// exact fp64 scores of explicit (i, j) pairs: out[p] = {hybrid, genre, text, metadata}
+__global__ void score_pairs_kernel(const ScoreParams sp, const int* __restrict__ pairs, int n_pairs,
+                                   double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  const int i = pairs[2 * t], j = pairs[2 * t + 1];
+  Scores s{0.0, 0.0, 0.0, 0.0};
+  if (i >= 0 && j >= 0 && i < sp.f.n_shows && j < sp.f.n_shows) s = score_pair(sp, i, j);
+  out[4 * t + 0] = s.h;
+  out[4 * t + 1] = s.g;
+  out[4 * t + 2] = s.t;
+  out[4 * t + 3] = s.m;
+}
+
+int score_pairs_launch(const ScoreParams& sp, const int* pairs, int n_pairs, double* out,
+                       cudaStream_t st) {
+  score_pairs_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(sp, pairs, n_pairs, out);
+  TVBF_LAUNCH_OK("score_pairs_kernel");
+  return TVBF_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers used by api.cu
 // ---------------------------------------------------------------------------------------------

@@ -603,6 +603,71 @@ class HybridTopKEngine:
         return {"mean": float(out5[0]), "std": float(out5[1]), "min": float(out5[2]),
                 "max": float(out5[3]), "median": float(out5[4])}
 
+    # ------------------------------------------------------------------------------------ streaming statistics
+    _STATS_DTYPE = np.dtype([("sum", "<f8", 4), ("sumsq", "<f8", 4), ("zeros", "<u8", 4),
+                             ("hist", "<u8", (4, 1024)), ("min_bits", "<u4", 4), ("max_bits", "<u4", 4),
+                             ("hi", "<f4", 4), ("n_cand", "<i4"), ("cand_ij", "<i4", (2, 2048, 2)),
+                             ("cand_val", "<f4", (2, 2048))], align=True)
+
+    def similarity_stats(self, cat: DeviceCatalogue, weights) -> dict:
+        """Upper-triangle statistics of the genre / text / metadata / hybrid similarity matrices
+        (ml/similarity_computer.py:171-190) WITHOUT materialising them: one symmetric tensor-core
+        sweep accumulates sums, extrema, zero counts and 1024-bin histograms on the device; the
+        largest text and hybrid elements are rescored exactly in float64.  mean / std agree with
+        float64 to ~1e-5 relative (the fp16 rounding of the text operand is correlated per vocabulary
+        column; genre / metadata are exact to fp32, so their min / max carry fp32 rounding, +-1.2e-7),
+        median to one histogram bin (range / 1024)."""
+        gw, tw, mw = (float(w) for w in weights)
+        p = self._params(cat, (gw, tw, mw), 20, 0.5)
+        lib, dev = self.lib, self.device
+        n = cat.n_shows
+        with torch.cuda.device(dev):
+            nbytes = int(lib.tvbf_stats_accum_bytes())
+            assert nbytes == self._STATS_DTYPE.itemsize, (nbytes, self._STATS_DTYPE.itemsize)
+            accum = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+            p1 = self._params(cat, (gw, tw, mw), 20, 0.5, tuning=1 << 20)
+            ws = self._workspace(max(int(lib.tvbf_topk_workspace_bytes(C.byref(cat.c), C.byref(p1))), 1 << 20))
+            check(lib.tvbf_similarity_stats(C.byref(cat.c), C.byref(p), accum.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            self._stream()), "tvbf_similarity_stats")
+            raw = np.frombuffer(accum.cpu().numpy().tobytes(), dtype=self._STATS_DTYPE)[0]
+            # exact float64 value of the largest text / hybrid elements
+            pairs = raw["cand_ij"].reshape(-1, 2)
+            keep = pairs[:, 0] >= 0
+            exact_max = {}
+            if keep.any():
+                pk = np.ascontiguousarray(pairs[keep].astype(np.int32))
+                pd = torch.from_numpy(pk).to(dev)
+                out4 = torch.empty((pk.shape[0], 4), dtype=torch.float64, device=dev)
+                check(lib.tvbf_score_pairs(C.byref(cat.c), C.byref(p), pd.data_ptr(), pk.shape[0], out4.data_ptr(),
+                                           self._stream()), "tvbf_score_pairs")
+                o = out4.cpu().numpy()
+                exact_max = {"text_similarity": float(o[:, 2].max()), "hybrid_similarity": float(o[:, 0].max())}
+        count = n * (n - 1) // 2
+        names = ("genre_similarity", "text_similarity", "metadata_similarity", "hybrid_similarity")
+        out = {}
+        for q, name in enumerate(names):
+            mean = float(raw["sum"][q]) / count
+            var = max(0.0, float(raw["sumsq"][q]) / count - mean * mean)
+            zeros = int(raw["zeros"][q])
+            hist = raw["hist"][q].astype(np.int64)
+            width = float(raw["hi"][q]) / 1024.0
+
+            def value_at(rank: int) -> float:
+                if rank < zeros:
+                    return 0.0
+                cum = zeros + np.cumsum(hist)
+                b = int(np.searchsorted(cum, rank, side="right"))
+                before = zeros + int(hist[:b].sum())
+                return (b + (rank - before + 0.5) / max(int(hist[b]), 1)) * width
+
+            vmin = 0.0 if zeros else float(np.frombuffer(np.uint32(raw["min_bits"][q]).tobytes(), np.float32)[0])
+            vmax = float(np.frombuffer(np.uint32(raw["max_bits"][q]).tobytes(), np.float32)[0])
+            out[name] = {"mean": mean, "std": float(np.sqrt(var)), "min": vmin,
+                         "max": exact_max.get(name, vmax),
+                         "median": 0.5 * (value_at((count - 1) // 2) + value_at(count // 2)),
+                         "median_resolution": width}
+        return out
+
     def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int, pair: bool = False) -> torch.Tensor:
         """Raw fp32 accumulators of one tensor-core tile (diagnostics / tests): 128 x 256 through
         cta_group::1, or 256 x 256 through a cta_group::2 CTA pair."""

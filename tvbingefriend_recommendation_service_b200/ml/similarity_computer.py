@@ -95,6 +95,20 @@ class SimilarityComputer:
         mat = torch.from_numpy(np.ascontiguousarray(similarity_matrix, dtype=np.float64)).to(self.engine.device)
         return self.engine.matrix_stats(mat)
 
+    def compute_similarity_statistics(self, features: dict, metadata_mode: str = "hstack",
+                                      normalize_weights: bool = True) -> dict[str, dict[str, float]]:
+        """The four ``get_similarity_statistics`` results of scripts/compute_similarities.py:119-131
+        for catalogues whose N x N matrices cannot exist: one streaming tensor-core sweep (defaults =
+        this class' conventions: hstack metadata, normalised weights).  mean / std / min / max as
+        the reference's, median to ``median_resolution``.  Needs binary genre and one-hot metadata
+        features."""
+        from ..engine import stage
+
+        weights = self._normalized_weights() if normalize_weights else \
+            (self.genre_weight, self.text_weight, self.metadata_weight)
+        cat = self.engine.upload(stage(features, metadata_mode), weights)
+        return self.engine.similarity_stats(cat, weights)
+
     # ---- production variant: no N x N ------------------------------------------------------------
     def compute_top_k(self, features: dict, k: int = 20, min_similarity: float = 0.1,
                       exclude_self: bool = True, metadata_mode: str = "mean3",
