@@ -162,7 +162,8 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
  *      for ALL shows.  Call sequence per GPU, with one small collective (done by the caller)
  *      between the calls:
  *        tvbf_sym_seed       theta[n_pad]                   -> all_reduce(MAX, uint32) of theta
- *        tvbf_sym_sweep      cand[n_shows][L], cnt, bound   -> all_gather of the three arrays
+ *        tvbf_sym_sweep      cand[n_shows][L], cnt, bound   -> all_to_all: GPU r receives every GPU's
+ *                                                              lists of ITS rows (or all_gather)
  *        tvbf_rescore_lists  rows [row_begin,row_end) of p  -> gather of the result tables
  *      L = tvbf_sym_list_len(); eligibility (packed groups, non-negative weights, positive
  *      min_similarity, k <= 48): tvbf_sym_eligible().  row_begin/row_end of p are ignored by the
@@ -176,11 +177,14 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
                    uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
                    void* workspace, size_t workspace_bytes, void* stream);
 /* fp64 rescoring + certificate + exact repair of rows [p->row_begin, p->row_end) from `lists`
- * gathered candidate tables laid out [lists][n_shows][L]. */
+ * candidate tables laid out [lists][table_rows][L] that cover the shows
+ * [table_row0, table_row0 + table_rows): (0, n_shows) after an all_gather, (row_begin, rows) after
+ * an all_to_all.  Of the merged lists only the 2L largest upper bounds are rescored; the rest
+ * joins the row's bound. */
 int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void* cand_all,
                        const int32_t* cnt_all, const float* bound_all, int32_t lists,
-                       const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
-                       void* stream);
+                       int32_t table_row0, int32_t table_rows, const tvbf_topk_out* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* exact fp64 scoring of explicit source rows against all columns + exact top-K
  * (replaces get_recommendations_from_matrix, content_based_service.py:161-236, for any n). */

@@ -168,7 +168,12 @@ def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world):
     tabs = []
     for r in range(world):
         b, e = row_shard(6000, world, r)
-        tabs.append(engine.to_host(engine.sym_rescore(dc, w, k, ms, cand_all, cnt_all, bound_all, b, e)))
+        if r % 2 == 0:   # tables after an all-gather: every rank's lists for all shows
+            t = engine.sym_rescore(dc, w, k, ms, cand_all, cnt_all, bound_all, b, e)
+        else:            # tables after the all-to-all: every rank's lists for this rank's rows only
+            t = engine.sym_rescore(dc, w, k, ms, cand_all[:, b:e].contiguous(), cnt_all[:, b:e].contiguous(),
+                                   bound_all[:, b:e].contiguous(), b, e, table_row0=b)
+        tabs.append(engine.to_host(t))
     got = TopK(*(np.concatenate([getattr(t, f) for t in tabs]) for f in
                  ("indices", "counts", "hybrid", "genre", "text", "metadata")))
     ref = engine.to_host(engine.top_k_device(dc, w, k, ms, force_exact=True))

@@ -520,13 +520,16 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
 
 int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void* cand_all,
                        const int32_t* cnt_all, const float* bound_all, int32_t lists,
-                       const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
-                       void* stream) {
+                       int32_t table_row0, int32_t table_rows, const tvbf_topk_out* out,
+                       void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_features(f);
   if (rc != TVBF_OK) return rc;
   rc = validate_params(f, p);
   if (rc != TVBF_OK) return rc;
   TVBF_REQUIRE(cand_all && cnt_all && bound_all && lists >= 1, "tvbf_rescore_lists: bad candidate tables");
+  TVBF_REQUIRE(table_row0 >= 0 && table_row0 <= p->row_begin &&
+                   static_cast<int64_t>(table_row0) + table_rows >= p->row_end,
+               "tvbf_rescore_lists: the candidate tables do not cover rows [row_begin, row_end)");
   TVBF_REQUIRE(out && out->indices && out->counts && out->hybrid && out->genre && out->text &&
                    out->metadata && out->stats,
                "output table has NULL members");
@@ -545,8 +548,8 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   TVBF_CUDA_OK(cudaMemsetAsync(out->stats, 0, 8 * sizeof(int32_t), st));
   const tvbf::ScoreParams scp = score_params(f, p);
   const int rows = p->row_end - p->row_begin;
-  // gathered layout: [lists][n_shows][kp]
-  const tvbf::CandLayout lay{p->row_begin, 1, f->n_shows};
+  // table layout: [lists][table_rows][kp]
+  const tvbf::CandLayout lay{p->row_begin - table_row0, 1, table_rows};
   rc = tvbf::k5_launch(scp, static_cast<const uint2*>(cand_all), cnt_all, bound_all, lists, lay, sp.pl.kp,
                        p->row_begin, rows, *out, flagged, floors, st);
   if (rc != TVBF_OK) return rc;

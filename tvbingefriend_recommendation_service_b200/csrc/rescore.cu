@@ -115,31 +115,75 @@ __global__ void __launch_bounds__(K5_WARPS * 32)
 rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
                const int* __restrict__ cand_cnt, const float* __restrict__ cand_theta, int splits,
                const CandLayout lay, int kp, int row_begin, int n_rows, tvbf_topk_out out,
-               int* flagged_rows, double* flagged_floor, int max_cand) {
+               int* flagged_rows, double* flagged_floor, int max_cand, int keep) {
   extern __shared__ __align__(16) uint8_t k5_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * K5_WARPS + warp;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= n_rows) return;
   const int i = row_begin + r;
-  uint8_t* base = k5_smem + static_cast<size_t>(warp) * max_cand * 40;
+  uint8_t* base = k5_smem + static_cast<size_t>(warp) * max_cand * 48;
   double* sh = reinterpret_cast<double*>(base);
   double* sg = sh + max_cand;
   double* st = sg + max_cand;
   double* sm = st + max_cand;
   int* sj = reinterpret_cast<int*>(sm + max_cand);
+  uint32_t* su = reinterpret_cast<uint32_t*>(sj + max_cand);
   __shared__ double s_kth[K5_WARPS];
 
-  // gather the candidate columns of all splits
+  // gather the candidate columns (and their upper bounds U) of all lists
   int total = 0;
   float theta = __int_as_float(0xff800000);
   for (int s = 0; s < splits; ++s) {
     const size_t slot = static_cast<size_t>(lay.slot_base + r * lay.row_stride + s * lay.list_stride);
     const int n = cand_cnt[slot];
     theta = fmaxf(theta, cand_theta[slot]);
-    for (int e = lane; e < n; e += 32) sj[total + e] = static_cast<int>(cand[slot * kp + e].y);
+    for (int e = lane; e < n; e += 32) {
+      const uint2 c = cand[slot * kp + e];
+      su[total + e] = c.x;
+      sj[total + e] = static_cast<int>(c.y);
+    }
     total += n;
   }
   __syncwarp();
+  // Several lists (column splits, or the partial lists of several GPUs): only the `keep` largest
+  // upper bounds are worth an exact score -- what a single merged list would have kept.  Everything
+  // cut here has exact score <= U <= the keep-th largest U, which joins the row's bound theta.
+  // (U bits of positive floats order like unsigned integers.)
+  if (total > keep) {
+    uint32_t best = 0u;
+#pragma unroll 1
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t t = best | (1u << bit);
+      int c = 0;
+      for (int e = lane; e < total; e += 32) c += (su[e] >= t);
+      c = __reduce_add_sync(kFullMask, c);
+      if (c >= keep) best = t;
+    }
+    int above = 0;
+    for (int e = lane; e < total; e += 32) above += (su[e] > best);
+    above = __reduce_add_sync(kFullMask, above);
+    const int quota = keep - above;   // entries equal to the keep-th value that still fit
+    int out_n = 0, eq_seen = 0;
+    for (int c0 = 0; c0 < total; c0 += 32) {   // ordered in-place compaction (writes trail reads)
+      const int e = c0 + lane;
+      const uint32_t u = e < total ? su[e] : 0u;
+      const int j = e < total ? sj[e] : 0;
+      const unsigned lt = (1u << lane) - 1u;
+      const unsigned bal_eq = __ballot_sync(kFullMask, e < total && u == best);
+      const bool take = e < total && (u > best || (u == best && eq_seen + __popc(bal_eq & lt) < quota));
+      const unsigned bal = __ballot_sync(kFullMask, take);
+      if (take) {
+        su[out_n + __popc(bal & lt)] = u;
+        sj[out_n + __popc(bal & lt)] = j;
+      }
+      out_n += __popc(bal);
+      eq_seen += __popc(bal_eq);
+      __syncwarp();
+    }
+    total = out_n;
+    theta = fmaxf(theta, __uint_as_float(best));
+    __syncwarp();
+  }
   // exact scores
   int valid = 0;
   for (int e = lane; e < total; e += 32) {
@@ -647,17 +691,19 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, double* flagged_floor, cudaStream_t st) {
   const int max_cand = splits * kp;
-  const size_t smem = static_cast<size_t>(K5_WARPS) * max_cand * 40;
+  int warps = K5_WARPS;
+  while (warps > 1 && static_cast<size_t>(warps) * max_cand * 48 > 200 * 1024) warps >>= 1;
+  const size_t smem = static_cast<size_t>(warps) * max_cand * 48;
   if (smem > 200 * 1024) {
-    tvbf_set_error("rescore: splits*candidates = %d is too large", max_cand);
+    tvbf_set_error("rescore: lists*candidates = %d is too large", max_cand);
     return TVBF_ERR_INVALID;
   }
   TVBF_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
-  const int grid = (n_rows + K5_WARPS - 1) / K5_WARPS;
-  rescore_kernel<<<grid, K5_WARPS * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, lay, kp,
-                                                    row_begin, n_rows, out, flagged_rows, flagged_floor,
-                                                    max_cand);
+  const int grid = (n_rows + warps - 1) / warps;
+  rescore_kernel<<<grid, warps * 32, smem, st>>>(sp, cand, cand_cnt, cand_theta, splits, lay, kp,
+                                                 row_begin, n_rows, out, flagged_rows, flagged_floor,
+                                                 max_cand, 2 * kp);
   TVBF_LAUNCH_OK("rescore_kernel");
   return TVBF_OK;
 }

@@ -431,10 +431,13 @@ class HybridTopKEngine:
 
     def sym_rescore(self, cat: DeviceCatalogue, weights, k, min_similarity, cand_all: torch.Tensor,
                     cnt_all: torch.Tensor, bound_all: torch.Tensor, row_begin: int, row_end: int,
-                    splits: int = 0, tuning: int = 0) -> dict:
+                    splits: int = 0, tuning: int = 0, table_row0: int = 0) -> dict:
         """Phase 3: fp64 rescoring + certificate + exact repair of rows [row_begin, row_end) from the
-        gathered candidate tables ([world, N, L, 2] / [world, N])."""
+        exchanged candidate tables ([world, R, L, 2] / [world, R]) that cover the shows
+        [table_row0, table_row0 + R): R = N after an all-gather, R = this rank's rows after an
+        all-to-all."""
         dev, rows, world = self.device, row_end - row_begin, int(cand_all.shape[0])
+        table_rows = int(cand_all.shape[1])
         with torch.cuda.device(dev):
             t = {
                 "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
@@ -453,16 +456,18 @@ class HybridTopKEngine:
                 cout = TopKOut(**{name: t[name].data_ptr() for name in
                                   ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
                 check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(), cnt_all.data_ptr(),
-                                                  bound_all.data_ptr(), world, C.byref(cout), ws.data_ptr(),
+                                                  bound_all.data_ptr(), world, int(table_row0), table_rows,
+                                                  C.byref(cout), ws.data_ptr(),
                                                   ws.numel(), self._stream()), "tvbf_rescore_lists")
         return t
 
     def top_k_device_sym_sharded(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
-                                 all_reduce_max, all_gather, row_range, splits: int = 0, tuning: int = 0,
+                                 all_reduce_max, exchange, row_range, splits: int = 0, tuning: int = 0,
                                  k1_events: list | None = None) -> dict:
         """This GPU's part of the tile-sharded symmetric job: the three phases with the two
-        collectives between them passed in as callables (``all_reduce_max(int32 tensor)`` in place,
-        ``all_gather(tensor) -> tensor with a leading [world] dimension``)."""
+        collectives between them passed in as callables: ``all_reduce_max(int32 tensor)`` in place,
+        and ``exchange(tensor [N, ...]) -> tensor [world, rows, ...]`` holding every rank's entries
+        for THIS rank's rows ``row_range`` (an all-to-all over the row shards)."""
         def mark():
             if k1_events is None:
                 return None
@@ -480,9 +485,10 @@ class HybridTopKEngine:
         e3 = mark()
         if k1_events is not None:
             k1_events.append(((e0, e1), (e2, e3)))
-        cand_all, cnt_all, bound_all = all_gather(cand), all_gather(cnt), all_gather(bound)
+        cand_all, cnt_all, bound_all = exchange(cand), exchange(cnt), exchange(bound)
         b, e = row_range
-        return self.sym_rescore(cat, weights, k, min_similarity, cand_all, cnt_all, bound_all, b, e, splits, tuning)
+        return self.sym_rescore(cat, weights, k, min_similarity, cand_all, cnt_all, bound_all, b, e, splits, tuning,
+                                table_row0=b)
 
     # ------------------------------------------------------------------------------------ exact
     def exact_rows(self, cat: DeviceCatalogue, rows, weights=(0.4, 0.5, 0.1), k: int = 10,

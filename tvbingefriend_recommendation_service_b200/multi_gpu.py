@@ -25,8 +25,8 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
 
     * symmetric (default when eligible): tile sharding -- every rank sweeps the tiles on/above the
       diagonal of its zigzag-dealt 256-row super blocks and feeds both shows of each score; the
-      partial candidate lists are all-gathered (N x 32 x 8 B per rank) and each rank rescores its
-      row shard.  Halves the tensor-core work.
+      partial candidate lists go through one all-to-all over the row shards (N x 32 x 8 B sent per
+      rank) and each rank rescores its row shard.  Halves the tensor-core work.
     * one-sided: row sharding, no exchange before the final gather.
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -38,13 +38,19 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
         def all_reduce_max(t):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
 
-        def all_gather(t):
-            out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(out, t, group=group)
+        bounds = [row_shard(n, world, r) for r in range(world)]
+
+        def exchange(t):
+            """all-to-all over the row shards: [N, ...] -> [world, my rows, ...] (every rank's partial
+            lists for this rank's rows; 1/world of the bytes an all-gather would move)."""
+            per_row = int(np.prod(t.shape[1:], dtype=np.int64))
+            out = torch.empty((world, e - b) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_to_all_single(out.view(-1), t.reshape(-1), output_split_sizes=[(e - b) * per_row] * world,
+                                   input_split_sizes=[(r1 - r0) * per_row for r0, r1 in bounds], group=group)
             return out
 
         local = eng.top_k_device_sym_sharded(cat, weights, k, min_similarity, rank, world, all_reduce_max,
-                                             all_gather, (b, e), splits=splits, tuning=tuning, k1_events=k1_events)
+                                             exchange, (b, e), splits=splits, tuning=tuning, k1_events=k1_events)
     elif e > b:
         tun = tuning | (1 << 20)
         if k1_events is None:
