@@ -10,7 +10,8 @@ import scipy.sparse as sp
 import torch
 
 from tvbingefriend_recommendation_service_b200.engine import TopK, stage
-from tvbingefriend_recommendation_service_b200.sharding import gather_tables, max_shard_rows, row_shard
+from tvbingefriend_recommendation_service_b200.sharding import (exchange_row_shards, gather_tables, max_shard_rows,
+                                                                row_shard)
 from tvbingefriend_recommendation_service_b200.sinks import InMemorySimilaritySink
 from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, make_catalogue
 
@@ -104,6 +105,12 @@ def _gloo_worker(rank, world, port, n, k, q):
               and torch.equal(full["counts"].long(), torch.arange(n) % (k + 1))
               and torch.allclose(full["text"][:, 1], torch.arange(n).double() + 2 + 0.01)
               and int(full["stats"][0]) == sum(range(1, world + 1)))
+        # the exchange of partial candidate lists: every rank holds entries for all shows
+        mine = torch.arange(n)[:, None] * 4 + torch.arange(3)[None, :] + 1_000_000 * rank
+        got = exchange_row_shards(mine.to(torch.int32), n)
+        want = torch.stack([torch.arange(b, e)[:, None] * 4 + torch.arange(3)[None, :] + 1_000_000 * r
+                            for r in range(world)]).to(torch.int32)
+        ok = ok and got.shape == (world, e - b, 3) and torch.equal(got, want)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 from .engine import HybridTopKEngine, TopK, stage
-from .sharding import empty_tables, gather_tables, row_shard
+from .sharding import empty_tables, exchange_row_shards, gather_tables, row_shard
 
 
 def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float,
@@ -38,16 +38,8 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
         def all_reduce_max(t):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
 
-        bounds = [row_shard(n, world, r) for r in range(world)]
-
         def exchange(t):
-            """all-to-all over the row shards: [N, ...] -> [world, my rows, ...] (every rank's partial
-            lists for this rank's rows; 1/world of the bytes an all-gather would move)."""
-            per_row = int(np.prod(t.shape[1:], dtype=np.int64))
-            out = torch.empty((world, e - b) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            dist.all_to_all_single(out.view(-1), t.reshape(-1), output_split_sizes=[(e - b) * per_row] * world,
-                                   input_split_sizes=[(r1 - r0) * per_row for r0, r1 in bounds], group=group)
-            return out
+            return exchange_row_shards(t[:n], n, group)
 
         local = eng.top_k_device_sym_sharded(cat, weights, k, min_similarity, rank, world, all_reduce_max,
                                              exchange, (b, e), splits=splits, tuning=tuning, k1_events=k1_events)

@@ -31,6 +31,22 @@ def max_shard_rows(n_shows: int, world_size: int) -> int:
                for r in range(world_size))
 
 
+def exchange_row_shards(t: torch.Tensor, n_shows: int, group=None) -> torch.Tensor:
+    """All-to-all over the row shards: every rank holds per-show entries ``t[N, ...]`` for ALL
+    shows (its partial candidate lists); rank r receives every rank's entries for ITS rows and
+    returns ``[world, rows_r, ...]``.  Moves 1/world of the bytes an all-gather would."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    spans = [row_shard(n_shows, world, r) for r in range(world)]
+    rows = spans[rank][1] - spans[rank][0]
+    per_row = 1
+    for d in t.shape[1:]:
+        per_row *= int(d)
+    out = torch.empty((world, rows) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_to_all_single(out.view(-1), t.contiguous().view(-1), output_split_sizes=[rows * per_row] * world,
+                           input_split_sizes=[(e - b) * per_row for b, e in spans], group=group)
+    return out
+
+
 def empty_tables(k: int, device) -> dict:
     """Local tables of a rank that owns no rows."""
     t = {"indices": torch.empty((0, k), dtype=torch.int32, device=device),
