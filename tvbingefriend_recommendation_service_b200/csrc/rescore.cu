@@ -300,8 +300,10 @@ struct SelectSmem {
 // Exact top-k of one source row from its N order-preserving keys (0 = invalid): radix select of the
 // count-th largest key, everything above it, then the LOWEST column indices among keys equal to
 // it, finally ordered by (score desc, column asc).  Called by all threads of the block.
-// `keys` has n entries in ascending column order; entry e is column jmap[e] (or e when jmap is null).
-template <class Scorer>
+// `keys` has n entries; entry e is column jmap[e] (or e when jmap is null).  kOrdered: the entries
+// are in ascending column order, so the tie group is cut by position; otherwise (survivor lists
+// appended in arbitrary order) by a second radix select over the column numbers.
+template <bool kOrdered, class Scorer>
 __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, const int* jmap, int n,
                                 int k, int valid, int i, size_t orow, const Scorer& scorer,
                                 const tvbf_topk_out& out) {
@@ -350,25 +352,62 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
     const int above = sm.above;
     const int need = count - above;  // >= 1 : lowest column indices among keys == v*
     const int nwarps = nthr >> 5;
-    for (int base = 0; base < n; base += nthr) {
-      const int j = base + tid;
-      const bool flag = j < n && keys[j] == vstar;
-      const unsigned bal = __ballot_sync(kFullMask, flag);
-      if (lane == 0) sm.warp_tot[warp] = __popc(bal);
-      __syncthreads();
-      int before = sm.taken;
-      for (int w = 0; w < warp; ++w) before += sm.warp_tot[w];
-      int chunk_total = 0;
-      for (int w = 0; w < nwarps; ++w) chunk_total += sm.warp_tot[w];
-      const int pos = before + __popc(bal & ((1u << lane) - 1u));
-      if (flag && pos < need) {
-        sm.win_key[above + pos] = vstar;
-        sm.win_j[above + pos] = jmap ? jmap[j] : j;
+    if (kOrdered) {
+      for (int base = 0; base < n; base += nthr) {
+        const int j = base + tid;
+        const bool flag = j < n && keys[j] == vstar;
+        const unsigned bal = __ballot_sync(kFullMask, flag);
+        if (lane == 0) sm.warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int before = sm.taken;
+        for (int w = 0; w < warp; ++w) before += sm.warp_tot[w];
+        int chunk_total = 0;
+        for (int w = 0; w < nwarps; ++w) chunk_total += sm.warp_tot[w];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        if (flag && pos < need) {
+          sm.win_key[above + pos] = vstar;
+          sm.win_j[above + pos] = jmap ? jmap[j] : j;
+        }
+        __syncthreads();
+        if (tid == 0) sm.taken += chunk_total;
+        __syncthreads();
+        if (sm.taken >= need) break;
       }
+    } else {
+      // need-th smallest column among the entries equal to v* (columns are distinct)
+      if (tid == 0) { sm.prefix = 0ull; sm.rank = need; }
       __syncthreads();
-      if (tid == 0) sm.taken += chunk_total;
-      __syncthreads();
-      if (sm.taken >= need) break;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += nthr) sm.hist[b] = 0u;
+        __syncthreads();
+        const unsigned int prefix = static_cast<unsigned int>(sm.prefix);
+        const unsigned int hi_mask = shift == 24 ? 0u : (~0u << (shift + 8));
+        for (int e = tid; e < n; e += nthr) {
+          const unsigned int col = static_cast<unsigned int>(jmap[e]);
+          if (keys[e] == vstar && (col & hi_mask) == prefix) atomicAdd(&sm.hist[(col >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int rank = sm.rank;
+          int d = 0;
+          for (; d < 255; ++d) {
+            const int c = static_cast<int>(sm.hist[d]);
+            if (rank <= c) break;
+            rank -= c;
+          }
+          sm.prefix = prefix | (static_cast<unsigned int>(d) << shift);
+          sm.rank = rank;
+        }
+        __syncthreads();
+      }
+      const int jstar = static_cast<int>(sm.prefix);
+      for (int e = tid; e < n; e += nthr) {
+        if (keys[e] == vstar && jmap[e] <= jstar) {
+          const int pos = atomicAdd(&sm.taken, 1);
+          sm.win_key[above + pos] = vstar;
+          sm.win_j[above + pos] = jmap[e];
+        }
+      }
     }
     __syncthreads();
     for (int e = tid; e < count; e += nthr) {
@@ -425,7 +464,7 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(kFullMask, my_valid, o);
     if (lane == 0 && my_valid) atomicAdd(&sm.valid, my_valid);
     __syncthreads();
-    select_and_emit(sm, keys, nullptr, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
+    select_and_emit<true>(sm, keys, nullptr, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
   }
 }
 
@@ -458,9 +497,14 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
   // dynamic smem: [mask: vocab bytes][small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
   extern __shared__ __align__(16) unsigned int mask_words[];
   __shared__ SelectSmem sm;
-  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB], s_scan[K6B_THREADS / 32], s_base;
+  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB];
   __shared__ long long s_b[K6B_MAXB], s_e[K6B_MAXB];
   __shared__ double s_floor[K6B_MAXB];
+  // factors that do not depend on the column show: 1/sqrt(n) for the set sizes, eq/3, and the
+  // batch rows' packed genre / metadata words with their reciprocal norms
+  __shared__ double s_rs[65], s_m3[4], s_gr[K6B_MAXB], s_mr[K6B_MAXB];
+  __shared__ unsigned long long s_gb[K6B_MAXB];
+  __shared__ unsigned int s_mb[K6B_MAXB];
   // the batch rows' own (column, value) lists, staged so that a mask hit is resolved by a binary
   // search in shared memory (rows with more than K6B_ROWNNZ entries are searched in global memory)
   __shared__ int s_cols[K6B_MAXB][K6B_ROWNNZ];
@@ -479,6 +523,16 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
   const int words = (f.vocab + 3) / 4;
   const unsigned char* mask = reinterpret_cast<const unsigned char*>(mask_words);
   unsigned long long* keys0 = key_scratch + static_cast<size_t>(blockIdx.x) * K6B_MAXB * n;
+  // survivor lists (columns that reach the row's floor), appended in arbitrary order while scoring
+  unsigned long long* surv_key = key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB * n +
+                                 static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_SMALL;
+  int* surv_j = reinterpret_cast<int*>(key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB *
+                                                         (static_cast<size_t>(n) + K6B_SMALL)) +
+                static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_SMALL;
+  const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
+  const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+  if (tid < 65) s_rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
+  if (tid < 4) s_m3[tid] = static_cast<double>(tid) / 3.0;
 
   for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int nb = (listed - batch * B) < B ? (listed - batch * B) : B;
@@ -493,6 +547,14 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
         s_b[tid] = f.text_indptr[i];
         s_e[tid] = f.text_indptr[i + 1];
         s_floor[tid] = floors ? floors[batch * B + tid] : -INFINITY;
+        if (packed) {
+          const TvbfColSide ci = cs[i];
+          const int gni = __popcll(ci.genre_bits), mni = __popc(ci.meta_bits);
+          s_gb[tid] = ci.genre_bits;
+          s_mb[tid] = ci.meta_bits;
+          s_gr[tid] = gni ? 1.0 / sqrt(static_cast<double>(gni)) : 0.0;
+          s_mr[tid] = mni ? 1.0 / sqrt(static_cast<double>(mni)) : 0.0;
+        }
       } else {
         s_row[tid] = -1; s_b[tid] = 0; s_e[tid] = 0; s_floor[tid] = INFINITY;
       }
@@ -513,11 +575,6 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
     }
     __syncthreads();
 
-    int my_valid[K6B_MAXB];
-#pragma unroll
-    for (int r = 0; r < K6B_MAXB; ++r) my_valid[r] = 0;
-    const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
-    const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
     for (int j = tid; j < n; j += K6B_THREADS) {
       double acc[K6B_MAXB];
 #pragma unroll
@@ -564,14 +621,11 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
       // genre / metadata parts: same expressions as genre_score() / meta_score(), with the
       // column show's factors computed once for the whole batch
       TvbfColSide cj;
-      int gnj = 0, mnj = 0;
       double g_rj = 0.0, m_rj = 0.0;
       if (packed) {
         cj = cs[j];
-        gnj = __popcll(cj.genre_bits);
-        mnj = __popc(cj.meta_bits);
-        if (gnj) g_rj = 1.0 / sqrt(static_cast<double>(gnj));
-        if (mnj) m_rj = 1.0 / sqrt(static_cast<double>(mnj));
+        g_rj = s_rs[__popcll(cj.genre_bits)];
+        m_rj = s_rs[__popc(cj.meta_bits)];
       }
 #pragma unroll
       for (int r = 0; r < K6B_MAXB; ++r) {
@@ -579,23 +633,13 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
           const int i = s_row[r];
           double g, mm;
           if (packed) {
-            const TvbfColSide ci = cs[i];
             g = 0.0;
             mm = 0.0;
-            if (f.genre_mode == TVBF_GROUP_PACKED) {
-              const int gni = __popcll(ci.genre_bits);
-              if (gni && gnj)
-                g = static_cast<double>(__popcll(ci.genre_bits & cj.genre_bits)) *
-                    ((1.0 / sqrt(static_cast<double>(gni))) * g_rj);
-            }
+            if (f.genre_mode == TVBF_GROUP_PACKED)
+              g = static_cast<double>(__popcll(s_gb[r] & cj.genre_bits)) * (s_gr[r] * g_rj);
             if (f.meta_mode == TVBF_GROUP_PACKED) {
-              const int eq = __popc(ci.meta_bits & cj.meta_bits);
-              if (f.meta_kind == TVBF_META_MEAN3) {
-                mm = static_cast<double>(eq) / 3.0;
-              } else {
-                const int mni = __popc(ci.meta_bits);
-                if (mni && mnj) mm = static_cast<double>(eq) * ((1.0 / sqrt(static_cast<double>(mni))) * m_rj);
-              }
+              const int eq = __popc(s_mb[r] & cj.meta_bits);
+              mm = f.meta_kind == TVBF_META_MEAN3 ? s_m3[eq] : static_cast<double>(eq) * (s_mr[r] * m_rj);
             }
           } else {
             g = genre_score(f, i, j);
@@ -605,17 +649,17 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
           // only columns that reach the row's floor (a lower bound of its k-th best score) can
           // matter; everything else is written as "invalid"
           const bool ok = (h >= sp.min_similarity) && (h >= s_floor[r]) && !(sp.exclude_self && j == i);
-          keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(h) : 0ull;
-          my_valid[r] += ok;
+          const unsigned long long key = ok ? f64_orderable(h) : 0ull;
+          keys0[static_cast<size_t>(r) * n + j] = key;
+          if (ok) {
+            const int pos = atomicAdd(&s_valid[r], 1);
+            if (pos < K6B_SMALL) {
+              surv_key[r * K6B_SMALL + pos] = key;
+              surv_j[r * K6B_SMALL + pos] = j;
+            }
+          }
         }
       }
-    }
-#pragma unroll
-    for (int r = 0; r < K6B_MAXB; ++r) {
-      int v = my_valid[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-      if (lane == 0 && v) atomicAdd(&s_valid[r], v);
     }
     __syncthreads();
     const FeatureScorer scorer{sp};
@@ -625,39 +669,19 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
       const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
       const int survivors = s_valid[r];
       if (survivors <= K6B_SMALL) {
-        // few survivors: one ordered compaction pass over the dense keys, then select from smem
-        // (instead of ~10 passes over N keys)
-        if (tid == 0) s_base = 0;
+        // few survivors: select from their list, staged in shared memory (instead of ~10 passes
+        // over N keys)
         __syncthreads();
-        for (int base = 0; base < n; base += K6B_THREADS) {
-          const int j = base + tid;
-          const unsigned long long key = j < n ? __ldcg(keys_r + j) : 0ull;
-          const bool flag = key != 0ull;
-          const unsigned bal = __ballot_sync(kFullMask, flag);
-          if (lane == 0) s_scan[tid >> 5] = __popc(bal);
-          __syncthreads();
-          int before = s_base;
-          for (int w = 0; w < (tid >> 5); ++w) before += s_scan[w];
-          if (flag) {
-            const int pos = before + __popc(bal & ((1u << lane) - 1u));
-            small_key[pos] = key;
-            small_j[pos] = j;
-          }
-          __syncthreads();
-          if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < K6B_THREADS / 32; ++w) tot += s_scan[w];
-            s_base += tot;
-          }
-          __syncthreads();
-          if (s_base >= survivors) break;
+        for (int e = tid; e < survivors; e += K6B_THREADS) {
+          small_key[e] = __ldcg(surv_key + r * K6B_SMALL + e);
+          small_j[e] = __ldcg(surv_j + r * K6B_SMALL + e);
         }
         __syncthreads();
-        select_and_emit(sm, small_key, small_j, survivors, sp.k, survivors, s_row[r],
-                        static_cast<size_t>(orow), scorer, out);
+        select_and_emit<false>(sm, small_key, small_j, survivors, sp.k, survivors, s_row[r],
+                               static_cast<size_t>(orow), scorer, out);
       } else {
-        select_and_emit(sm, keys_r, nullptr, n, sp.k, survivors, s_row[r], static_cast<size_t>(orow),
-                        scorer, out);
+        select_and_emit<true>(sm, keys_r, nullptr, n, sp.k, survivors, s_row[r], static_cast<size_t>(orow),
+                              scorer, out);
       }
     }
   }
@@ -710,7 +734,8 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
 
 size_t k6_scratch_bytes(int n_shows, int sm_count) {
   // batched feature kernel: one CTA per SM, up to K6B_MAXB key rows each
-  return static_cast<size_t>(sm_count) * K6B_MAXB * static_cast<size_t>(n_shows) * 8;
+  // + survivor lists of K6B_SMALL (key, column) entries per batch row
+  return static_cast<size_t>(sm_count) * K6B_MAXB * (static_cast<size_t>(n_shows) * 8 + K6B_SMALL * 12);
 }
 
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
