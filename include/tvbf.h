@@ -115,7 +115,8 @@ typedef struct tvbf_topk_out {
   double* text;      /* [rows, k] text_score                                                  */
   double* metadata;  /* [rows, k] metadata_score                                              */
   int32_t* stats;    /* [8] device ints: 0 flagged rows repaired by the exact kernel,         */
-                     /*     1 candidate pairs rescored, 2 rows processed, rest reserved       */
+                     /*     1 candidate pairs rescored, 2 / 3 flagged rows with / without text,*/
+                     /*     rest reserved                                                     */
 } tvbf_topk_out;
 
 int tvbf_version(void);

@@ -246,3 +246,22 @@ def test_streaming_statistics_at_c3_scale(engine):
         s = got[name]
         assert 0.0 <= s["min"] <= s["median"] <= s["max"] <= 1.0 + 2e-7 and s["std"] >= 0   # genre/metadata extrema are fp32
     assert got["text_similarity"]["max"] == pytest.approx(1.0, abs=1e-9)   # planted duplicate shows
+
+
+@pytest.mark.parametrize("with_text", [False, True], ids=["no_text", "text"])
+def test_tie_plateau_wider_than_the_survivor_lists(engine, with_text):
+    """17 000 identical shows: every row's floor is reached by all other columns, more than the exact
+    kernel lists per row (16 384), so it must fall back to dense keys -- with and without text."""
+    import scipy.sparse as sp
+
+    n = 17_000
+    text = sp.csr_matrix(np.tile(np.array([[0.6, 0.8, 0.0]]), (n, 1))) if with_text else sp.csr_matrix((n, 3))
+    f = {"genre_features": np.ones((n, 3), dtype=np.int64), "text_features": text,
+         "platform_features": np.tile(np.array([[1.0, 0.0]]), (n, 1)),
+         "type_features": np.tile(np.array([[True, False]]), (n, 1)),
+         "language_features": np.tile(np.array([[1.0, 0.0]]), (n, 1))}
+    top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1)
+    for i in (0, 7, 9000, n - 1):
+        assert top.indices[i].tolist() == [j for j in range(n) if j != i][:20]
+    assert np.allclose(top.hybrid, 1.0 if with_text else 0.5)
+    assert top.flagged_rows == n

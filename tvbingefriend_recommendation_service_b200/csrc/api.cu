@@ -361,7 +361,7 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (rc != TVBF_OK) return rc;
   }
   if ((phases & 4) && !p->skip_fallback) {
-    rc = tvbf::k6_launch(sp, flagged, 0, out->stats + 0, floors, p->row_begin, 1, keys, pl.k6_grid, *out, st);
+    rc = tvbf::k6_launch_flagged(sp, flagged, floors, pl.rows, p->row_begin, keys, pl.k6_grid, *out, st);
     if (rc != TVBF_OK) return rc;
   }
   return TVBF_OK;
@@ -556,7 +556,7 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   int sms = 0;
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
-  return tvbf::k6_launch(scp, flagged, 0, out->stats + 0, floors, p->row_begin, 1, keys, sms, *out, st);
+  return tvbf::k6_launch_flagged(scp, flagged, floors, rows, p->row_begin, keys, sms, *out, st);
 }
 
 // ---- streaming statistics of the four similarity matrices (no N x N) --------------------------

@@ -102,7 +102,11 @@ int score_pairs_launch(const ScoreParams& sp, const int* pairs, int n_pairs, dou
 size_t k6_scratch_bytes(int n_shows, int sm_count);
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               const double* floors, int row_begin, int rows_are_local, unsigned long long* key_scratch,
-              int grid, const tvbf_topk_out& out, cudaStream_t st);
+              int grid, const tvbf_topk_out& out, cudaStream_t st, int no_text = 0, int list_cap = 0);
+// the two lists K5 leaves behind: flagged shows with text (front) and without (back of the arrays)
+int k6_launch_flagged(const ScoreParams& sp, const int* flagged, const double* floors, int n_rows,
+                      int row_begin, unsigned long long* key_scratch, int grid, const tvbf_topk_out& out,
+                      cudaStream_t st);
 
 int k6_launch_matrix(const double* h, const double* g, const double* t, const double* m, int n,
                      int k, int exclude_self, double min_similarity, const int* rows, int n_listed,

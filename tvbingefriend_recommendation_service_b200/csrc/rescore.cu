@@ -27,7 +27,7 @@ __device__ __forceinline__ double text_dot(const tvbf_features& f, int i, int j)
   double s = 0.0;
   while (true) {
     if (ca == cb) {
-      s += f.text_values[a] * f.text_values[b];
+      s = __dadd_rn(s, __dmul_rn(f.text_values[a], f.text_values[b]));
       ++a; ++b;
       if (a >= ei || b >= ej) break;
       ca = f.text_indices[a];
@@ -235,7 +235,11 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
     const double bound = s_kth[warp];  // k-th exact score, or min_similarity if fewer than k
     const bool safe = static_cast<double>(theta) < bound;
     if (!safe) {
-      const int pos = atomicAdd(&out.stats[0], 1);
+      atomicAdd(&out.stats[0], 1);
+      // shows with text are listed from the front, shows without (the usual tie plateaus, which
+      // never need the text CSR) from the back: the exact kernel handles the two kinds separately
+      const bool has_text = sp.f.text_indptr[i + 1] > sp.f.text_indptr[i];
+      const int pos = has_text ? atomicAdd(&out.stats[2], 1) : n_rows - 1 - atomicAdd(&out.stats[3], 1);
       flagged_rows[pos] = r;
       // the k-th best exact score among the candidates is a lower bound of the true k-th best:
       // the exact kernel only needs to keep columns that reach it
@@ -311,6 +315,36 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
   const int count = valid < k ? valid : k;
   const size_t obase = orow * static_cast<size_t>(k);
   __syncthreads();
+  if (!kOrdered && n <= nthr) {
+    // short survivor list: every thread ranks one entry against all others, no selection passes
+    if (tid < n) {
+      const unsigned long long ke = keys[tid];
+      const int je = jmap[tid];
+      int rank = 0;
+      for (int o = 0; o < n; ++o) {
+        const unsigned long long ko = keys[o];
+        rank += (ko > ke) || (ko == ke && jmap[o] < je);
+      }
+      if (rank < count) {
+        const Scores s = scorer(i, je);
+        out.indices[obase + rank] = je;
+        out.hybrid[obase + rank] = f64_from_orderable(ke);
+        out.genre[obase + rank] = s.g;
+        out.text[obase + rank] = s.t;
+        out.metadata[obase + rank] = s.m;
+      }
+    }
+    for (int e = count + tid; e < k; e += nthr) {
+      out.indices[obase + e] = -1;
+      out.hybrid[obase + e] = NAN;
+      out.genre[obase + e] = NAN;
+      out.text[obase + e] = NAN;
+      out.metadata[obase + e] = NAN;
+    }
+    if (tid == 0) out.counts[orow] = count;
+    __syncthreads();
+    return;
+  }
   if (tid == 0) { sm.above = 0; sm.taken = 0; sm.prefix = 0ull; sm.rank = count; }
   __syncthreads();
   if (count > 0) {
@@ -439,15 +473,16 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
 template <class Scorer>
 __global__ void __launch_bounds__(K6_THREADS)
 exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __restrict__ rows,
-                  int n_listed, const int* __restrict__ count_ptr, int row_begin,
+                  int n_listed, const int* __restrict__ count_ptr, int list_cap, int row_begin,
                   int rows_are_local, unsigned long long* __restrict__ key_scratch,
                   tvbf_topk_out out) {
   __shared__ SelectSmem sm;
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = sel.n;
   const int listed = count_ptr ? *count_ptr : n_listed;
+  const int list0 = list_cap > 0 ? list_cap - listed : 0;
   unsigned long long* keys = key_scratch + static_cast<size_t>(blockIdx.x) * n;
-  for (int t = blockIdx.x; t < listed; t += gridDim.x) {
+  for (int t = list0 + blockIdx.x; t < list0 + listed; t += gridDim.x) {
     const int r = rows[t];
     const int i = rows_are_local ? row_begin + r : r;
     const int orow = rows_are_local ? r : t;
@@ -468,14 +503,17 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
   }
 }
 
-// Feature form, batched: a CTA takes up to K6B_MAXB source rows at once so that the CSR of the
+// Feature form, batched: a CTA takes up to MAXB source rows at once so that the CSR of the
 // catalogue (the dominant traffic: ~12 B per text nnz, 56 MB at C3) is streamed once per BATCH
 // instead of once per row.  mask[c] (one byte per vocabulary column, shared memory) has bit r set
-// when batch row r uses column c; a column show's entries are tested against it and only hits are
-// looked up in the batch rows.  Sums run over ascending column index, exactly like text_dot.
+// when batch row r uses column c.  Two instantiations:
+//   kText = true,  MAXB = 4: rows that may have text; the CSR is streamed warp-cooperatively
+//   kText = false, MAXB = 8: rows known to have no text (the tie plateaus K5 flags); no CSR at all
 constexpr int K6B_THREADS = 1024;
-constexpr int K6B_MAXB = 8;
+constexpr int K6B_MAXB = 8;       // scratch is sized for this many key rows per CTA
+constexpr int K6B_TEXTB = 4;      // batch rows of the text instantiation
 constexpr int K6B_SMALL = 4096;   // survivors that are selected from shared memory
+constexpr int K6B_LIST = 16384;   // survivors listed per batch row (global scratch); more -> dense keys
 constexpr int K6B_ROWNNZ = 192;   // text entries of a batch row staged in shared memory
 
 __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, int64_t e, int c) {
@@ -489,26 +527,30 @@ __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, 
   return 0.0;
 }
 
+// rows / floors hold `listed` entries at [0, listed), or at [list_cap - listed, list_cap) when
+// list_cap > 0 (K5 lists the shows without text from the back).
+template <bool kText, int MAXB>
 __global__ void __launch_bounds__(K6B_THREADS, 1)
 exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
-                          const int* __restrict__ count_ptr, const double* __restrict__ floors,
-                          int row_begin, int rows_are_local, int mask_bytes,
-                          unsigned long long* __restrict__ key_scratch, tvbf_topk_out out) {
+                          const int* __restrict__ count_ptr, int list_cap,
+                          const double* __restrict__ floors, int row_begin, int rows_are_local,
+                          int mask_bytes, unsigned long long* __restrict__ key_scratch,
+                          tvbf_topk_out out) {
   // dynamic smem: [mask: vocab bytes][small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
   extern __shared__ __align__(16) unsigned int mask_words[];
   __shared__ SelectSmem sm;
-  __shared__ int s_row[K6B_MAXB], s_valid[K6B_MAXB];
-  __shared__ long long s_b[K6B_MAXB], s_e[K6B_MAXB];
-  __shared__ double s_floor[K6B_MAXB];
+  __shared__ int s_row[MAXB], s_valid[MAXB];
+  __shared__ long long s_b[MAXB], s_e[MAXB];
+  __shared__ double s_floor[MAXB];
   // factors that do not depend on the column show: 1/sqrt(n) for the set sizes, eq/3, and the
   // batch rows' packed genre / metadata words with their reciprocal norms
-  __shared__ double s_rs[65], s_m3[4], s_gr[K6B_MAXB], s_mr[K6B_MAXB];
-  __shared__ unsigned long long s_gb[K6B_MAXB];
-  __shared__ unsigned int s_mb[K6B_MAXB];
+  __shared__ double s_rs[65], s_m3[4], s_gr[MAXB], s_mr[MAXB];
+  __shared__ unsigned long long s_gb[MAXB];
+  __shared__ unsigned int s_mb[MAXB];
   // the batch rows' own (column, value) lists, staged so that a mask hit is resolved by a binary
   // search in shared memory (rows with more than K6B_ROWNNZ entries are searched in global memory)
-  __shared__ int s_cols[K6B_MAXB][K6B_ROWNNZ];
-  __shared__ double s_vals[K6B_MAXB][K6B_ROWNNZ];
+  __shared__ int s_cols[kText ? MAXB : 1][kText ? K6B_ROWNNZ : 1];
+  __shared__ double s_vals[kText ? MAXB : 1][kText ? K6B_ROWNNZ : 1];
   unsigned long long* small_key =
       reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(mask_words) + mask_bytes);
   int* small_j = reinterpret_cast<int*>(small_key + K6B_SMALL);
@@ -517,36 +559,41 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
   const int n = f.n_shows;
   const int listed = count_ptr ? *count_ptr : n_listed;
   if (listed <= 0) return;
+  const int list0 = list_cap > 0 ? list_cap - listed : 0;
   int B = (listed + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  B = B < 1 ? 1 : (B > K6B_MAXB ? K6B_MAXB : B);
+  B = B < 1 ? 1 : (B > MAXB ? MAXB : B);
   const int n_batches = (listed + B - 1) / B;
   const int words = (f.vocab + 3) / 4;
   const unsigned char* mask = reinterpret_cast<const unsigned char*>(mask_words);
   unsigned long long* keys0 = key_scratch + static_cast<size_t>(blockIdx.x) * K6B_MAXB * n;
   // survivor lists (columns that reach the row's floor), appended in arbitrary order while scoring
   unsigned long long* surv_key = key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB * n +
-                                 static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_SMALL;
+                                 static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_LIST;
   int* surv_j = reinterpret_cast<int*>(key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB *
-                                                         (static_cast<size_t>(n) + K6B_SMALL)) +
-                static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_SMALL;
+                                                         (static_cast<size_t>(n) + K6B_LIST)) +
+                static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_LIST;
   const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
   const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+  // without floors every column is a survivor and the selection runs over dense keys; with floors
+  // the survivor lists almost always suffice and the dense keys are not written at all
+  const bool dense = floors == nullptr;
   if (tid < 65) s_rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
   if (tid < 4) s_m3[tid] = static_cast<double>(tid) / 3.0;
 
   for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int nb = (listed - batch * B) < B ? (listed - batch * B) : B;
     __syncthreads();
-    for (int w = tid; w < words; w += K6B_THREADS) mask_words[w] = 0u;
-    if (tid < K6B_MAXB) {
+    if (kText)
+      for (int w = tid; w < words; w += K6B_THREADS) mask_words[w] = 0u;
+    if (tid < MAXB) {
       s_valid[tid] = 0;
       if (tid < nb) {
-        const int r = rows[batch * B + tid];
+        const int r = rows[list0 + batch * B + tid];
         const int i = rows_are_local ? row_begin + r : r;
         s_row[tid] = i;
         s_b[tid] = f.text_indptr[i];
         s_e[tid] = f.text_indptr[i + 1];
-        s_floor[tid] = floors ? floors[batch * B + tid] : -INFINITY;
+        s_floor[tid] = floors ? floors[list0 + batch * B + tid] : -INFINITY;
         if (packed) {
           const TvbfColSide ci = cs[i];
           const int gni = __popcll(ci.genre_bits), mni = __popc(ci.meta_bits);
@@ -561,63 +608,100 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
     }
     __syncthreads();
     bool any_text = false;
-    for (int r = 0; r < nb; ++r) {
-      any_text |= s_e[r] > s_b[r];
-      const bool staged = (s_e[r] - s_b[r]) <= K6B_ROWNNZ;
-      for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
-        const int c = f.text_indices[e];
-        atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
-        if (staged) {
-          s_cols[r][e - s_b[r]] = c;
-          s_vals[r][e - s_b[r]] = f.text_values[e];
+    if (kText) {
+      for (int r = 0; r < nb; ++r) {
+        any_text |= s_e[r] > s_b[r];
+        const bool staged = (s_e[r] - s_b[r]) <= K6B_ROWNNZ;
+        for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
+          const int c = f.text_indices[e];
+          atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
+          if (staged) {
+            s_cols[r][e - s_b[r]] = c;
+            s_vals[r][e - s_b[r]] = f.text_values[e];
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
 
-    for (int j = tid; j < n; j += K6B_THREADS) {
-      double acc[K6B_MAXB];
+    // Each warp takes 32 consecutive column shows per step (lane = column).  Their CSR segments
+    // are one contiguous span, streamed with coalesced loads (lane = entry) and tested against
+    // the mask.  Every hit lane looks its product up in parallel; the products then go to the
+    // lane that owns the entry's column one by one in ascending entry order, so each pair's sum
+    // runs over ascending column index with one rounding per product and per add, like text_dot.
+    for (int j0 = (tid >> 5) * 32; j0 < n; j0 += K6B_THREADS) {
+      const int j = j0 + lane;
+      double acc[MAXB];
 #pragma unroll
-      for (int r = 0; r < K6B_MAXB; ++r) acc[r] = 0.0;
-      // a batch of shows without any text (a common reason for a tie plateau) never touches the CSR
-      const int64_t bj = any_text ? f.text_indptr[j] : 0, ej = any_text ? f.text_indptr[j + 1] : 0;
-      // four entries per step: the index loads and mask probes of a step are independent, so
-      // their latencies overlap; hits (rare) are resolved in ascending column order
-      for (int64_t e = bj; e < ej; e += 4) {
+      for (int r = 0; r < MAXB; ++r) acc[r] = 0.0;
+      if (kText && any_text) {
+        const long long ip = f.text_indptr[j < n ? j : n];   // first entry of this lane's column
+        const long long span_b = __shfl_sync(kFullMask, ip, 0);
+        const long long span_e = f.text_indptr[j0 + 32 < n ? j0 + 32 : n];
+        // four 32-entry groups (8 loads) are always in flight: a slot is refilled with the group
+        // 128 entries ahead as soon as it has been consumed
         int c[4];
-        unsigned m[4];
+        double v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (e + u < ej) ? f.text_indices[e + u] : -1;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) m[u] = c[u] >= 0 ? mask[c[u]] : 0u;
-        if (m[0] | m[1] | m[2] | m[3]) {
+        for (int u = 0; u < 4; ++u) {
+          const long long e = span_b + u * 32 + lane;
+          c[u] = e < span_e ? f.text_indices[e] : -1;
+          v[u] = e < span_e ? f.text_values[e] : 0.0;
+        }
+        for (long long off = span_b; off < span_e; off += 128) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (m[u]) {
-              const double v = f.text_values[e + u];
+            const long long e = off + u * 32 + lane;
+            const int cu = c[u];
+            const double vu = v[u];
+            {
+              const long long en = e + 128;
+              c[u] = en < span_e ? f.text_indices[en] : -1;
+              v[u] = en < span_e ? f.text_values[en] : 0.0;
+            }
+            const unsigned mu = cu >= 0 ? mask[cu] : 0u;
+            if (__ballot_sync(kFullMask, mu != 0u) == 0u) continue;
+            // lane that owns this lane's entry: the last one whose column starts at or before it
+            int owner = 0;
 #pragma unroll
-              for (int r = 0; r < K6B_MAXB; ++r)
-                if (m[u] & (1u << r)) {
-                  const int len = static_cast<int>(s_e[r] - s_b[r]);
-                  double xv;
-                  if (len <= K6B_ROWNNZ) {
-                    int lo = 0, hi = len;
-                    xv = 0.0;
-                    while (lo < hi) {
-                      const int mid = (lo + hi) >> 1;
-                      const int cm = s_cols[r][mid];
-                      if (cm == c[u]) { xv = s_vals[r][mid]; break; }
-                      if (cm < c[u]) lo = mid + 1; else hi = mid;
-                    }
-                  } else {
-                    xv = csr_lookup(f, s_b[r], s_e[r], c[u]);
+            for (int step = 16; step > 0; step >>= 1) {
+              const long long ipc = __shfl_sync(kFullMask, ip, (owner + step) & 31);
+              if (ipc <= e) owner += step;
+            }
+#pragma unroll
+            for (int r = 0; r < MAXB; ++r) {
+              const bool mine = (mu >> r) & 1u;
+              unsigned hits = __ballot_sync(kFullMask, mine);
+              if (hits == 0u) continue;
+              double prod = 0.0;
+              if (mine) {
+                const int len = static_cast<int>(s_e[r] - s_b[r]);
+                double xv = 0.0;
+                if (len <= K6B_ROWNNZ) {
+                  int lo = 0, hi = len;
+                  while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int cm = s_cols[r][mid];
+                    if (cm == cu) { xv = s_vals[r][mid]; break; }
+                    if (cm < cu) lo = mid + 1; else hi = mid;
                   }
-                  acc[r] += xv * v;
+                } else {
+                  xv = csr_lookup(f, s_b[r], s_e[r], cu);
                 }
+                prod = __dmul_rn(xv, vu);
+              }
+              while (hits) {
+                const int hl = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int o = __shfl_sync(kFullMask, owner, hl);
+                const double pp = __shfl_sync(kFullMask, prod, hl);
+                if (lane == o) acc[r] = __dadd_rn(acc[r], pp);
+              }
             }
           }
         }
       }
+      if (j >= n) continue;
       // genre / metadata parts: same expressions as genre_score() / meta_score(), with the
       // column show's factors computed once for the whole batch
       TvbfColSide cj;
@@ -628,7 +712,7 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
         m_rj = s_rs[__popc(cj.meta_bits)];
       }
 #pragma unroll
-      for (int r = 0; r < K6B_MAXB; ++r) {
+      for (int r = 0; r < MAXB; ++r) {
         if (r < nb) {
           const int i = s_row[r];
           double g, mm;
@@ -650,12 +734,12 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
           // matter; everything else is written as "invalid"
           const bool ok = (h >= sp.min_similarity) && (h >= s_floor[r]) && !(sp.exclude_self && j == i);
           const unsigned long long key = ok ? f64_orderable(h) : 0ull;
-          keys0[static_cast<size_t>(r) * n + j] = key;
+          if (dense) keys0[static_cast<size_t>(r) * n + j] = key;
           if (ok) {
             const int pos = atomicAdd(&s_valid[r], 1);
-            if (pos < K6B_SMALL) {
-              surv_key[r * K6B_SMALL + pos] = key;
-              surv_j[r * K6B_SMALL + pos] = j;
+            if (pos < K6B_LIST) {
+              surv_key[r * K6B_LIST + pos] = key;
+              surv_j[r * K6B_LIST + pos] = j;
             }
           }
         }
@@ -664,7 +748,7 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
     __syncthreads();
     const FeatureScorer scorer{sp};
     for (int r = 0; r < nb; ++r) {
-      const int t = batch * B + r;
+      const int t = list0 + batch * B + r;
       const int orow = rows_are_local ? rows[t] : t;
       const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
       const int survivors = s_valid[r];
@@ -673,13 +757,29 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
         // over N keys)
         __syncthreads();
         for (int e = tid; e < survivors; e += K6B_THREADS) {
-          small_key[e] = __ldcg(surv_key + r * K6B_SMALL + e);
-          small_j[e] = __ldcg(surv_j + r * K6B_SMALL + e);
+          small_key[e] = __ldcg(surv_key + r * K6B_LIST + e);
+          small_j[e] = __ldcg(surv_j + r * K6B_LIST + e);
         }
         __syncthreads();
         select_and_emit<false>(sm, small_key, small_j, survivors, sp.k, survivors, s_row[r],
                                static_cast<size_t>(orow), scorer, out);
+      } else if (survivors <= K6B_LIST) {
+        // a wide tie plateau: select over the survivor list where it lies (L2), not over N keys
+        select_and_emit<false>(sm, surv_key + r * K6B_LIST, surv_j + r * K6B_LIST, survivors, sp.k, survivors,
+                               s_row[r], static_cast<size_t>(orow), scorer, out);
       } else {
+        if (!dense) {
+          // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
+          const int i = s_row[r];
+          const double floor_r = s_floor[r];
+          __syncthreads();
+          for (int j = tid; j < n; j += K6B_THREADS) {
+            const Scores sc = scorer(i, j);
+            const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_r) && !(sp.exclude_self && j == i);
+            keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(sc.h) : 0ull;
+          }
+          __syncthreads();
+        }
         select_and_emit<true>(sm, keys_r, nullptr, n, sp.k, survivors, s_row[r], static_cast<size_t>(orow),
                               scorer, out);
       }
@@ -734,36 +834,54 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
 
 size_t k6_scratch_bytes(int n_shows, int sm_count) {
   // batched feature kernel: one CTA per SM, up to K6B_MAXB key rows each
-  // + survivor lists of K6B_SMALL (key, column) entries per batch row
-  return static_cast<size_t>(sm_count) * K6B_MAXB * (static_cast<size_t>(n_shows) * 8 + K6B_SMALL * 12);
+  // + survivor lists of K6B_LIST (key, column) entries per batch row
+  return static_cast<size_t>(sm_count) * K6B_MAXB * (static_cast<size_t>(n_shows) * 8 + K6B_LIST * 12);
 }
 
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
               const double* floors, int row_begin, int rows_are_local, unsigned long long* key_scratch,
-              int grid, const tvbf_topk_out& out, cudaStream_t st) {
+              int grid, const tvbf_topk_out& out, cudaStream_t st, int no_text, int list_cap) {
   if (sp.k > K6_MAXK) {
     tvbf_set_error("exact rows: k=%d exceeds %d", sp.k, K6_MAXK);
     return TVBF_ERR_INVALID;
   }
   const size_t mask_bytes = (static_cast<size_t>(sp.f.vocab) + 15) / 16 * 16;
+  if (no_text) {
+    // rows known to have no text: no mask, no CSR
+    const size_t smem = static_cast<size_t>(K6B_SMALL) * 12;
+    auto kern = exact_rows_batched_kernel<false, K6B_MAXB>;
+    TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    kern<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors, row_begin,
+                                          rows_are_local, 0, key_scratch, out);
+    TVBF_LAUNCH_OK("exact_rows_batched_kernel<no text>");
+    return TVBF_OK;
+  }
   const size_t smem = mask_bytes + static_cast<size_t>(K6B_SMALL) * 12;
   if (smem <= 200 * 1024) {
-    TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_batched_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+    auto kern = exact_rows_batched_kernel<true, K6B_TEXTB>;
+    TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    exact_rows_batched_kernel<<<grid, K6B_THREADS, smem, st>>>(
-        sp, rows, n_listed, count_ptr, floors, row_begin, rows_are_local, static_cast<int>(mask_bytes),
-        key_scratch, out);
-    TVBF_LAUNCH_OK("exact_rows_batched_kernel");
+    kern<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors, row_begin,
+                                          rows_are_local, static_cast<int>(mask_bytes), key_scratch, out);
+    TVBF_LAUNCH_OK("exact_rows_batched_kernel<text>");
     return TVBF_OK;
   }
   // vocabulary too wide for the shared-memory mask: one row per CTA pass
   FeatureScorer sc{sp};
   SelectParams sel{sp.f.n_shows, sp.k, sp.exclude_self, sp.min_similarity};
   exact_rows_kernel<FeatureScorer><<<grid, K6_THREADS, 0, st>>>(
-      sc, sel, rows, n_listed, count_ptr, row_begin, rows_are_local, key_scratch, out);
+      sc, sel, rows, n_listed, count_ptr, list_cap, row_begin, rows_are_local, key_scratch, out);
   TVBF_LAUNCH_OK("exact_rows_kernel");
   return TVBF_OK;
+}
+
+int k6_launch_flagged(const ScoreParams& sp, const int* flagged, const double* floors, int n_rows,
+                      int row_begin, unsigned long long* key_scratch, int grid, const tvbf_topk_out& out,
+                      cudaStream_t st) {
+  int rc = k6_launch(sp, flagged, 0, out.stats + 2, floors, row_begin, 1, key_scratch, grid, out, st, 0, 0);
+  if (rc != TVBF_OK) return rc;
+  return k6_launch(sp, flagged, 0, out.stats + 3, floors, row_begin, 1, key_scratch, grid, out, st, 1, n_rows);
 }
 
 int k6_launch_matrix(const double* h, const double* g, const double* t, const double* m, int n,
@@ -776,7 +894,7 @@ int k6_launch_matrix(const double* h, const double* g, const double* t, const do
   }
   MatrixScorer sc{h, g, t, m, n};
   SelectParams sel{n, k, exclude_self, min_similarity};
-  exact_rows_kernel<MatrixScorer><<<grid, K6_THREADS, 0, st>>>(sc, sel, rows, n_listed, nullptr, 0,
+  exact_rows_kernel<MatrixScorer><<<grid, K6_THREADS, 0, st>>>(sc, sel, rows, n_listed, nullptr, 0, 0,
                                                                0, key_scratch, out);
   TVBF_LAUNCH_OK("exact_rows_kernel<matrix>");
   return TVBF_OK;

@@ -238,6 +238,10 @@ class HybridTopKEngine:
             code, tdt = _DTYPES[self.text_dtype]
             keep = []
             indptr, indices, rawv = raw["indptr"], raw["indices"], raw["values"]
+            if rawv.numel() == 0:
+                # a catalogue without any text: the C ABI wants non-NULL arrays, which are never read
+                indices = torch.zeros((1,), dtype=torch.int32, device=dev)
+                rawv = torch.zeros((1,), dtype=torch.float64, device=dev)
             values = torch.empty_like(rawv)
             operand = torch.zeros((n_pad, k_pad), dtype=tdt, device=dev)
             col_side = torch.zeros((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
