@@ -307,23 +307,30 @@ struct SelectSmem {
 // `keys` has n entries; entry e is column jmap[e] (or e when jmap is null).  kOrdered: the entries
 // are in ascending column order, so the tie group is cut by position; otherwise (survivor lists
 // appended in arbitrary order) by a second radix select over the column numbers.
-template <bool kOrdered, class Scorer>
+// kCg: the arrays were written by other CTAs of this launch -> read them through L2 (ld.cg).
+template <bool kOrdered, bool kCg, class Scorer>
 __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, const int* jmap, int n,
                                 int k, int valid, int i, size_t orow, const Scorer& scorer,
                                 const tvbf_topk_out& out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  auto ldk = [](const unsigned long long* p) {
+    if constexpr (kCg) return __ldcg(p); else return *p;
+  };
+  auto ldj = [](const int* p) {
+    if constexpr (kCg) return __ldcg(p); else return *p;
+  };
   const int count = valid < k ? valid : k;
   const size_t obase = orow * static_cast<size_t>(k);
   __syncthreads();
   if (!kOrdered && n <= nthr) {
     // short survivor list: every thread ranks one entry against all others, no selection passes
     if (tid < n) {
-      const unsigned long long ke = keys[tid];
-      const int je = jmap[tid];
+      const unsigned long long ke = ldk(keys + tid);
+      const int je = ldj(jmap + tid);
       int rank = 0;
       for (int o = 0; o < n; ++o) {
-        const unsigned long long ko = keys[o];
-        rank += (ko > ke) || (ko == ke && jmap[o] < je);
+        const unsigned long long ko = ldk(keys + o);
+        rank += (ko > ke) || (ko == ke && ldj(jmap + o) < je);
       }
       if (rank < count) {
         const Scores s = scorer(i, je);
@@ -355,7 +362,7 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
       const unsigned long long hi_mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
 #pragma unroll 4
       for (int j = tid; j < n; j += nthr) {
-        const unsigned long long key = keys[j];  // generic: global scratch or shared memory
+        const unsigned long long key = ldk(keys + j);  // generic: global scratch or shared memory
         if (key != 0ull && (key & hi_mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 0xFFu], 1u);
       }
       __syncthreads();
@@ -375,11 +382,11 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
     const unsigned long long vstar = sm.prefix;  // count-th largest key
 #pragma unroll 4
     for (int j = tid; j < n; j += nthr) {
-      const unsigned long long key = keys[j];
+      const unsigned long long key = ldk(keys + j);
       if (key > vstar) {
         const int pos = atomicAdd(&sm.above, 1);
         sm.win_key[pos] = key;
-        sm.win_j[pos] = jmap ? jmap[j] : j;
+        sm.win_j[pos] = jmap ? ldj(jmap + j) : j;
       }
     }
     __syncthreads();
@@ -389,7 +396,7 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
     if (kOrdered) {
       for (int base = 0; base < n; base += nthr) {
         const int j = base + tid;
-        const bool flag = j < n && keys[j] == vstar;
+        const bool flag = j < n && ldk(keys + j) == vstar;
         const unsigned bal = __ballot_sync(kFullMask, flag);
         if (lane == 0) sm.warp_tot[warp] = __popc(bal);
         __syncthreads();
@@ -400,7 +407,7 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
         const int pos = before + __popc(bal & ((1u << lane) - 1u));
         if (flag && pos < need) {
           sm.win_key[above + pos] = vstar;
-          sm.win_j[above + pos] = jmap ? jmap[j] : j;
+          sm.win_j[above + pos] = jmap ? ldj(jmap + j) : j;
         }
         __syncthreads();
         if (tid == 0) sm.taken += chunk_total;
@@ -417,8 +424,8 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
         const unsigned int prefix = static_cast<unsigned int>(sm.prefix);
         const unsigned int hi_mask = shift == 24 ? 0u : (~0u << (shift + 8));
         for (int e = tid; e < n; e += nthr) {
-          const unsigned int col = static_cast<unsigned int>(jmap[e]);
-          if (keys[e] == vstar && (col & hi_mask) == prefix) atomicAdd(&sm.hist[(col >> shift) & 0xFFu], 1u);
+          const unsigned int col = static_cast<unsigned int>(ldj(jmap + e));
+          if (ldk(keys + e) == vstar && (col & hi_mask) == prefix) atomicAdd(&sm.hist[(col >> shift) & 0xFFu], 1u);
         }
         __syncthreads();
         if (tid == 0) {
@@ -436,10 +443,10 @@ __device__ void select_and_emit(SelectSmem& sm, const unsigned long long* keys, 
       }
       const int jstar = static_cast<int>(sm.prefix);
       for (int e = tid; e < n; e += nthr) {
-        if (keys[e] == vstar && jmap[e] <= jstar) {
+        if (ldk(keys + e) == vstar && ldj(jmap + e) <= jstar) {
           const int pos = atomicAdd(&sm.taken, 1);
           sm.win_key[above + pos] = vstar;
-          sm.win_j[above + pos] = jmap[e];
+          sm.win_j[above + pos] = ldj(jmap + e);
         }
       }
     }
@@ -499,22 +506,28 @@ exact_rows_kernel(const Scorer scorer, const SelectParams sel, const int* __rest
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_xor_sync(kFullMask, my_valid, o);
     if (lane == 0 && my_valid) atomicAdd(&sm.valid, my_valid);
     __syncthreads();
-    select_and_emit<true>(sm, keys, nullptr, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
+    select_and_emit<true, false>(sm, keys, nullptr, n, sel.k, sm.valid, i, static_cast<size_t>(orow), scorer, out);
   }
 }
 
-// Feature form, batched: a CTA takes up to MAXB source rows at once so that the CSR of the
-// catalogue (the dominant traffic: ~12 B per text nnz, 56 MB at C3) is streamed once per BATCH
-// instead of once per row.  mask[c] (one byte per vocabulary column, shared memory) has bit r set
-// when batch row r uses column c.  Two instantiations:
-//   kText = true,  MAXB = 4: rows that may have text; the CSR is streamed warp-cooperatively
-//   kText = false, MAXB = 8: rows known to have no text (the tie plateaus K5 flags); no CSR at all
+// ---------------------------------------------------------------------------------------------
+// K6, feature form.  Two kernels:
+//   exact_rows_notext_kernel  rows known to have no text (the tie plateaus K5 flags): genre /
+//                             metadata only, up to 8 rows per CTA, no CSR traffic at all
+//   exact_rows_text_kernel    rows that may have text: the catalogue CSR (~12 B per text nnz, 56 MB
+//                             at C3) is streamed warp-cooperatively against a shared-memory mask
+//                             of the batch rows' vocabulary; when only a few rows are listed (the
+//                             usual case: near-ties under the fp16 bound are rare, and the online
+//                             single-show query) each row's COLUMNS are split over the CTAs and
+//                             the last CTA of a row selects from the shared survivor list
+// ---------------------------------------------------------------------------------------------
 constexpr int K6B_THREADS = 1024;
-constexpr int K6B_MAXB = 8;       // scratch is sized for this many key rows per CTA
-constexpr int K6B_TEXTB = 4;      // batch rows of the text instantiation
+constexpr int K6B_MAXB = 8;       // no-text kernel: batch rows per CTA (scratch is sized for this)
+constexpr int K6B_TEXTB = 4;      // text kernel: batch rows
 constexpr int K6B_SMALL = 4096;   // survivors that are selected from shared memory
-constexpr int K6B_LIST = 16384;   // survivors listed per batch row (global scratch); more -> dense keys
+constexpr int K6B_LIST = 16384;   // survivors listed per row (global scratch); more -> dense keys
 constexpr int K6B_ROWNNZ = 192;   // text entries of a batch row staged in shared memory
+constexpr size_t K6T_COUNTER_BYTES = 65536;   // text kernel: survivor counters + batch tickets
 
 __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, int64_t e, int c) {
   // value of column c in the sorted row segment [b, e); the caller knows it is present
@@ -527,35 +540,76 @@ __device__ __forceinline__ double csr_lookup(const tvbf_features& f, int64_t b, 
   return 0.0;
 }
 
+// column-independent pieces of the genre / metadata scores of the batch rows (shared memory)
+template <int MAXB>
+struct BatchRows {
+  int row[MAXB];
+  double floor[MAXB];
+  double gr[MAXB], mr[MAXB];          // 1/sqrt(set size) of the row's genre / metadata bits
+  unsigned long long gb[MAXB];
+  unsigned int mb[MAXB];
+  double rs[65], m3[4];               // 1/sqrt(n), n/3
+};
+
+// hybrid score of batch row r against column show j (text part given); same expressions as
+// genre_score() / meta_score() / score_pair()
+template <int MAXB>
+__device__ __forceinline__ double batch_hybrid(const ScoreParams& sp, const BatchRows<MAXB>& br, int r,
+                                               int j, bool packed, const TvbfColSide& cj, double g_rj,
+                                               double m_rj, double text) {
+  const tvbf_features& f = sp.f;
+  double g = 0.0, mm = 0.0;
+  if (packed) {
+    if (f.genre_mode == TVBF_GROUP_PACKED)
+      g = static_cast<double>(__popcll(br.gb[r] & cj.genre_bits)) * (br.gr[r] * g_rj);
+    if (f.meta_mode == TVBF_GROUP_PACKED) {
+      const int eq = __popc(br.mb[r] & cj.meta_bits);
+      mm = f.meta_kind == TVBF_META_MEAN3 ? br.m3[eq] : static_cast<double>(eq) * (br.mr[r] * m_rj);
+    }
+  } else {
+    g = genre_score(f, br.row[r], j);
+    mm = meta_score(f, br.row[r], j);
+  }
+  return sp.wg * g + sp.wt * text + sp.wm * mm;
+}
+
+template <int MAXB>
+__device__ __forceinline__ void batch_rows_init(BatchRows<MAXB>& br, int tid) {
+  if (tid < 65) br.rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
+  if (tid < 4) br.m3[tid] = static_cast<double>(tid) / 3.0;
+}
+
+template <int MAXB>
+__device__ __forceinline__ void batch_rows_load(BatchRows<MAXB>& br, int slot, int i, double floor_v,
+                                                bool packed, const TvbfColSide* cs) {
+  br.row[slot] = i;
+  br.floor[slot] = floor_v;
+  if (packed && i >= 0) {
+    const TvbfColSide ci = cs[i];
+    const int gni = __popcll(ci.genre_bits), mni = __popc(ci.meta_bits);
+    br.gb[slot] = ci.genre_bits;
+    br.mb[slot] = ci.meta_bits;
+    br.gr[slot] = gni ? 1.0 / sqrt(static_cast<double>(gni)) : 0.0;
+    br.mr[slot] = mni ? 1.0 / sqrt(static_cast<double>(mni)) : 0.0;
+  }
+}
+
 // rows / floors hold `listed` entries at [0, listed), or at [list_cap - listed, list_cap) when
 // list_cap > 0 (K5 lists the shows without text from the back).
-template <bool kText, int MAXB>
 __global__ void __launch_bounds__(K6B_THREADS, 1)
-exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
-                          const int* __restrict__ count_ptr, int list_cap,
-                          const double* __restrict__ floors, int row_begin, int rows_are_local,
-                          int mask_bytes, unsigned long long* __restrict__ key_scratch,
-                          tvbf_topk_out out) {
-  // dynamic smem: [mask: vocab bytes][small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
-  extern __shared__ __align__(16) unsigned int mask_words[];
+exact_rows_notext_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
+                         const int* __restrict__ count_ptr, int list_cap,
+                         const double* __restrict__ floors, int row_begin, int rows_are_local,
+                         unsigned long long* __restrict__ key_scratch, tvbf_topk_out out) {
+  constexpr int MAXB = K6B_MAXB;
+  // dynamic smem: [small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
+  extern __shared__ __align__(16) unsigned long long small_key[];
   __shared__ SelectSmem sm;
-  __shared__ int s_row[MAXB], s_valid[MAXB];
-  __shared__ long long s_b[MAXB], s_e[MAXB];
-  __shared__ double s_floor[MAXB];
-  // factors that do not depend on the column show: 1/sqrt(n) for the set sizes, eq/3, and the
-  // batch rows' packed genre / metadata words with their reciprocal norms
-  __shared__ double s_rs[65], s_m3[4], s_gr[MAXB], s_mr[MAXB];
-  __shared__ unsigned long long s_gb[MAXB];
-  __shared__ unsigned int s_mb[MAXB];
-  // the batch rows' own (column, value) lists, staged so that a mask hit is resolved by a binary
-  // search in shared memory (rows with more than K6B_ROWNNZ entries are searched in global memory)
-  __shared__ int s_cols[kText ? MAXB : 1][kText ? K6B_ROWNNZ : 1];
-  __shared__ double s_vals[kText ? MAXB : 1][kText ? K6B_ROWNNZ : 1];
-  unsigned long long* small_key =
-      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(mask_words) + mask_bytes);
+  __shared__ BatchRows<MAXB> br;
+  __shared__ int s_valid[MAXB];
   int* small_j = reinterpret_cast<int*>(small_key + K6B_SMALL);
   const tvbf_features& f = sp.f;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int n = f.n_shows;
   const int listed = count_ptr ? *count_ptr : n_listed;
   if (listed <= 0) return;
@@ -563,78 +617,201 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
   int B = (listed + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   B = B < 1 ? 1 : (B > MAXB ? MAXB : B);
   const int n_batches = (listed + B - 1) / B;
-  const int words = (f.vocab + 3) / 4;
-  const unsigned char* mask = reinterpret_cast<const unsigned char*>(mask_words);
-  unsigned long long* keys0 = key_scratch + static_cast<size_t>(blockIdx.x) * K6B_MAXB * n;
+  unsigned long long* keys0 = key_scratch + static_cast<size_t>(blockIdx.x) * MAXB * n;
   // survivor lists (columns that reach the row's floor), appended in arbitrary order while scoring
-  unsigned long long* surv_key = key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB * n +
-                                 static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_LIST;
-  int* surv_j = reinterpret_cast<int*>(key_scratch + static_cast<size_t>(gridDim.x) * K6B_MAXB *
+  unsigned long long* surv_key = key_scratch + static_cast<size_t>(gridDim.x) * MAXB * n +
+                                 static_cast<size_t>(blockIdx.x) * MAXB * K6B_LIST;
+  int* surv_j = reinterpret_cast<int*>(key_scratch + static_cast<size_t>(gridDim.x) * MAXB *
                                                          (static_cast<size_t>(n) + K6B_LIST)) +
-                static_cast<size_t>(blockIdx.x) * K6B_MAXB * K6B_LIST;
+                static_cast<size_t>(blockIdx.x) * MAXB * K6B_LIST;
   const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
   const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
   // without floors every column is a survivor and the selection runs over dense keys; with floors
   // the survivor lists almost always suffice and the dense keys are not written at all
   const bool dense = floors == nullptr;
-  if (tid < 65) s_rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
-  if (tid < 4) s_m3[tid] = static_cast<double>(tid) / 3.0;
+  batch_rows_init(br, tid);
 
   for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int nb = (listed - batch * B) < B ? (listed - batch * B) : B;
     __syncthreads();
-    if (kText)
-      for (int w = tid; w < words; w += K6B_THREADS) mask_words[w] = 0u;
     if (tid < MAXB) {
       s_valid[tid] = 0;
       if (tid < nb) {
         const int r = rows[list0 + batch * B + tid];
+        batch_rows_load(br, tid, rows_are_local ? row_begin + r : r,
+                        floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs);
+      } else {
+        batch_rows_load(br, tid, -1, INFINITY, packed, cs);
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += K6B_THREADS) {
+      TvbfColSide cj;
+      double g_rj = 0.0, m_rj = 0.0;
+      if (packed) {
+        cj = cs[j];
+        g_rj = br.rs[__popcll(cj.genre_bits)];
+        m_rj = br.rs[__popc(cj.meta_bits)];
+      }
+#pragma unroll
+      for (int r = 0; r < MAXB; ++r) {
+        if (r < nb) {
+          const double h = batch_hybrid(sp, br, r, j, packed, cj, g_rj, m_rj, 0.0);
+          // only columns that reach the row's floor (a lower bound of its k-th best score) can
+          // matter; everything else is "invalid"
+          const bool ok = (h >= sp.min_similarity) && (h >= br.floor[r]) && !(sp.exclude_self && j == br.row[r]);
+          const unsigned long long key = ok ? f64_orderable(h) : 0ull;
+          if (dense) keys0[static_cast<size_t>(r) * n + j] = key;
+          if (ok) {
+            const int pos = atomicAdd(&s_valid[r], 1);
+            if (pos < K6B_LIST) {
+              surv_key[r * K6B_LIST + pos] = key;
+              surv_j[r * K6B_LIST + pos] = j;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const FeatureScorer scorer{sp};
+    for (int r = 0; r < nb; ++r) {
+      const int t = list0 + batch * B + r;
+      const int orow = rows_are_local ? rows[t] : t;
+      const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
+      const int survivors = s_valid[r];
+      if (survivors <= K6B_SMALL) {
+        // few survivors: select from their list, staged in shared memory (instead of ~10 passes
+        // over N keys)
+        __syncthreads();
+        for (int e = tid; e < survivors; e += K6B_THREADS) {
+          small_key[e] = __ldcg(surv_key + r * K6B_LIST + e);
+          small_j[e] = __ldcg(surv_j + r * K6B_LIST + e);
+        }
+        __syncthreads();
+        select_and_emit<false, false>(sm, small_key, small_j, survivors, sp.k, survivors, br.row[r],
+                                      static_cast<size_t>(orow), scorer, out);
+      } else if (survivors <= K6B_LIST) {
+        // a wide tie plateau: select over the survivor list where it lies (L2), not over N keys
+        select_and_emit<false, false>(sm, surv_key + r * K6B_LIST, surv_j + r * K6B_LIST, survivors, sp.k,
+                                      survivors, br.row[r], static_cast<size_t>(orow), scorer, out);
+      } else {
+        if (!dense) {
+          // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
+          const int i = br.row[r];
+          const double floor_r = br.floor[r];
+          __syncthreads();
+          for (int j = tid; j < n; j += K6B_THREADS) {
+            const Scores sc = scorer(i, j);
+            const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_r) && !(sp.exclude_self && j == i);
+            keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(sc.h) : 0ull;
+          }
+          __syncthreads();
+        }
+        select_and_emit<true, false>(sm, keys_r, nullptr, n, sp.k, survivors, br.row[r],
+                                     static_cast<size_t>(orow), scorer, out);
+      }
+    }
+  }
+}
+
+// Text form.  scratch (key_scratch): [counters: K6T_COUNTER_BYTES][surv_key: cap_rows x K6B_LIST u64]
+// [surv_j: cap_rows x K6B_LIST int][dense keys: cap_rows x n u64].  Row slots: the listed position
+// when listed <= cap_rows (column-split mode, counters zeroed by the launcher), else per-CTA slots.
+__global__ void __launch_bounds__(K6B_THREADS, 1)
+exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n_listed,
+                       const int* __restrict__ count_ptr, int list_cap,
+                       const double* __restrict__ floors, int row_begin, int rows_are_local,
+                       int mask_bytes, unsigned long long* __restrict__ key_scratch, int cap_rows,
+                       tvbf_topk_out out) {
+  constexpr int MAXB = K6B_TEXTB;
+  // dynamic smem: [mask: vocab bytes][small_key: K6B_SMALL u64][small_j: K6B_SMALL int]
+  extern __shared__ __align__(16) unsigned int mask_words[];
+  __shared__ SelectSmem sm;
+  __shared__ BatchRows<MAXB> br;
+  __shared__ long long s_b[MAXB], s_e[MAXB];
+  __shared__ int s_last;
+  // the batch rows' own (column, value) lists, staged so that a mask hit is resolved by a binary
+  // search in shared memory (rows with more than K6B_ROWNNZ entries are searched in global memory)
+  __shared__ int s_cols[MAXB][K6B_ROWNNZ];
+  __shared__ double s_vals[MAXB][K6B_ROWNNZ];
+  unsigned long long* small_key =
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(mask_words) + mask_bytes);
+  int* small_j = reinterpret_cast<int*>(small_key + K6B_SMALL);
+  const tvbf_features& f = sp.f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = f.n_shows;
+  const int listed = count_ptr ? *count_ptr : n_listed;
+  if (listed <= 0) return;
+  const int list0 = list_cap > 0 ? list_cap - listed : 0;
+  const int G = static_cast<int>(gridDim.x);
+  int B = (listed + G - 1) / G;
+  B = B < 1 ? 1 : (B > MAXB ? MAXB : B);
+  const int n_batches = (listed + B - 1) / B;
+  const bool split = listed <= cap_rows;          // one scratch slot per listed row
+  const int S = split && n_batches < G ? G / n_batches : 1;   // column slices per batch
+  const int items = n_batches * S;
+  const int chunks = (n + 31) / 32;
+  const int words = (f.vocab + 3) / 4;
+  const unsigned char* mask = reinterpret_cast<const unsigned char*>(mask_words);
+  int* cnt = reinterpret_cast<int*>(key_scratch);
+  int* ticket = cnt + 8192;
+  unsigned long long* surv_key = key_scratch + K6T_COUNTER_BYTES / 8;
+  int* surv_j = reinterpret_cast<int*>(surv_key + static_cast<size_t>(cap_rows) * K6B_LIST);
+  unsigned long long* dense_keys = surv_key + static_cast<size_t>(cap_rows) * K6B_LIST * 3 / 2;
+  const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
+  const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+  const bool dense = floors == nullptr;
+  batch_rows_init(br, tid);
+
+  for (int item = blockIdx.x; item < items; item += G) {
+    const int batch = item / S, slice = item % S;
+    const int nb = (listed - batch * B) < B ? (listed - batch * B) : B;
+    const int slot0 = split ? batch * B : static_cast<int>(blockIdx.x) * MAXB;
+    __syncthreads();
+    for (int w = tid; w < words; w += K6B_THREADS) mask_words[w] = 0u;
+    if (tid < MAXB) {
+      if (tid < nb) {
+        const int r = rows[list0 + batch * B + tid];
         const int i = rows_are_local ? row_begin + r : r;
-        s_row[tid] = i;
+        batch_rows_load(br, tid, i, floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs);
         s_b[tid] = f.text_indptr[i];
         s_e[tid] = f.text_indptr[i + 1];
-        s_floor[tid] = floors ? floors[list0 + batch * B + tid] : -INFINITY;
-        if (packed) {
-          const TvbfColSide ci = cs[i];
-          const int gni = __popcll(ci.genre_bits), mni = __popc(ci.meta_bits);
-          s_gb[tid] = ci.genre_bits;
-          s_mb[tid] = ci.meta_bits;
-          s_gr[tid] = gni ? 1.0 / sqrt(static_cast<double>(gni)) : 0.0;
-          s_mr[tid] = mni ? 1.0 / sqrt(static_cast<double>(mni)) : 0.0;
-        }
+        if (!split) cnt[slot0 + tid] = 0;   // per-CTA slots are reused from batch to batch
       } else {
-        s_row[tid] = -1; s_b[tid] = 0; s_e[tid] = 0; s_floor[tid] = INFINITY;
+        batch_rows_load(br, tid, -1, INFINITY, packed, cs);
+        s_b[tid] = 0; s_e[tid] = 0;
       }
     }
     __syncthreads();
     bool any_text = false;
-    if (kText) {
-      for (int r = 0; r < nb; ++r) {
-        any_text |= s_e[r] > s_b[r];
-        const bool staged = (s_e[r] - s_b[r]) <= K6B_ROWNNZ;
-        for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
-          const int c = f.text_indices[e];
-          atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
-          if (staged) {
-            s_cols[r][e - s_b[r]] = c;
-            s_vals[r][e - s_b[r]] = f.text_values[e];
-          }
+    for (int r = 0; r < nb; ++r) {
+      any_text |= s_e[r] > s_b[r];
+      const bool staged = (s_e[r] - s_b[r]) <= K6B_ROWNNZ;
+      for (long long e = s_b[r] + tid; e < s_e[r]; e += K6B_THREADS) {
+        const int c = f.text_indices[e];
+        atomicOr(&mask_words[c >> 2], (1u << r) << (8 * (c & 3)));
+        if (staged) {
+          s_cols[r][e - s_b[r]] = c;
+          s_vals[r][e - s_b[r]] = f.text_values[e];
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
 
     // Each warp takes 32 consecutive column shows per step (lane = column).  Their CSR segments
     // are one contiguous span, streamed with coalesced loads (lane = entry) and tested against
     // the mask.  Every hit lane looks its product up in parallel; the products then go to the
     // lane that owns the entry's column one by one in ascending entry order, so each pair's sum
     // runs over ascending column index with one rounding per product and per add, like text_dot.
-    for (int j0 = (tid >> 5) * 32; j0 < n; j0 += K6B_THREADS) {
+    const int ch0 = static_cast<int>(static_cast<long long>(chunks) * slice / S);
+    const int ch1 = static_cast<int>(static_cast<long long>(chunks) * (slice + 1) / S);
+    for (int ch = ch0 + warp; ch < ch1; ch += K6B_THREADS / 32) {
+      const int j0 = ch * 32;
       const int j = j0 + lane;
       double acc[MAXB];
 #pragma unroll
       for (int r = 0; r < MAXB; ++r) acc[r] = 0.0;
-      if (kText && any_text) {
+      if (any_text) {
         const long long ip = f.text_indptr[j < n ? j : n];   // first entry of this lane's column
         const long long span_b = __shfl_sync(kFullMask, ip, 0);
         const long long span_e = f.text_indptr[j0 + 32 < n ? j0 + 32 : n];
@@ -701,87 +878,85 @@ exact_rows_batched_kernel(const ScoreParams sp, const int* __restrict__ rows, in
           }
         }
       }
-      if (j >= n) continue;
-      // genre / metadata parts: same expressions as genre_score() / meta_score(), with the
-      // column show's factors computed once for the whole batch
-      TvbfColSide cj;
+      // genre / metadata parts and the survivor test (all lanes stay in: ballots below)
+      const bool in = j < n;
+      TvbfColSide cj{0ull, 0.0f, 0u};
       double g_rj = 0.0, m_rj = 0.0;
-      if (packed) {
+      if (packed && in) {
         cj = cs[j];
-        g_rj = s_rs[__popcll(cj.genre_bits)];
-        m_rj = s_rs[__popc(cj.meta_bits)];
+        g_rj = br.rs[__popcll(cj.genre_bits)];
+        m_rj = br.rs[__popc(cj.meta_bits)];
       }
 #pragma unroll
       for (int r = 0; r < MAXB; ++r) {
         if (r < nb) {
-          const int i = s_row[r];
-          double g, mm;
-          if (packed) {
-            g = 0.0;
-            mm = 0.0;
-            if (f.genre_mode == TVBF_GROUP_PACKED)
-              g = static_cast<double>(__popcll(s_gb[r] & cj.genre_bits)) * (s_gr[r] * g_rj);
-            if (f.meta_mode == TVBF_GROUP_PACKED) {
-              const int eq = __popc(s_mb[r] & cj.meta_bits);
-              mm = f.meta_kind == TVBF_META_MEAN3 ? s_m3[eq] : static_cast<double>(eq) * (s_mr[r] * m_rj);
-            }
-          } else {
-            g = genre_score(f, i, j);
-            mm = meta_score(f, i, j);
+          bool ok = false;
+          unsigned long long key = 0ull;
+          if (in) {
+            const double h = batch_hybrid(sp, br, r, j, packed, cj, g_rj, m_rj, acc[r]);
+            ok = (h >= sp.min_similarity) && (h >= br.floor[r]) && !(sp.exclude_self && j == br.row[r]);
+            key = ok ? f64_orderable(h) : 0ull;
+            if (dense) dense_keys[static_cast<size_t>(slot0 + r) * n + j] = key;
           }
-          const double h = sp.wg * g + sp.wt * acc[r] + sp.wm * mm;
-          // only columns that reach the row's floor (a lower bound of its k-th best score) can
-          // matter; everything else is written as "invalid"
-          const bool ok = (h >= sp.min_similarity) && (h >= s_floor[r]) && !(sp.exclude_self && j == i);
-          const unsigned long long key = ok ? f64_orderable(h) : 0ull;
-          if (dense) keys0[static_cast<size_t>(r) * n + j] = key;
-          if (ok) {
-            const int pos = atomicAdd(&s_valid[r], 1);
-            if (pos < K6B_LIST) {
-              surv_key[r * K6B_LIST + pos] = key;
-              surv_j[r * K6B_LIST + pos] = j;
+          const unsigned okb = __ballot_sync(kFullMask, ok);
+          if (okb) {   // one counter update per warp: the row's survivor list may be shared by many CTAs
+            const int leader = __ffs(okb) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cnt[slot0 + r], __popc(okb));
+            base = __shfl_sync(kFullMask, base, leader);
+            const int pos = base + __popc(okb & ((1u << lane) - 1u));
+            if (ok && pos < K6B_LIST) {
+              surv_key[static_cast<size_t>(slot0 + r) * K6B_LIST + pos] = key;
+              surv_j[static_cast<size_t>(slot0 + r) * K6B_LIST + pos] = j;
             }
           }
         }
       }
     }
+    // the last CTA to finish a batch selects its rows (no waiting: everybody else just leaves)
+    __threadfence();
     __syncthreads();
+    if (S > 1) {
+      if (tid == 0) s_last = atomicAdd(&ticket[batch], 1) == S - 1;
+      __syncthreads();
+      if (!s_last) continue;
+      __threadfence();
+    }
     const FeatureScorer scorer{sp};
     for (int r = 0; r < nb; ++r) {
       const int t = list0 + batch * B + r;
       const int orow = rows_are_local ? rows[t] : t;
-      const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
-      const int survivors = s_valid[r];
+      const size_t slot = static_cast<size_t>(slot0 + r);
+      unsigned long long* keys_r = dense_keys + slot * n;
+      const int survivors = __ldcg(cnt + slot);
       if (survivors <= K6B_SMALL) {
-        // few survivors: select from their list, staged in shared memory (instead of ~10 passes
-        // over N keys)
         __syncthreads();
         for (int e = tid; e < survivors; e += K6B_THREADS) {
-          small_key[e] = __ldcg(surv_key + r * K6B_LIST + e);
-          small_j[e] = __ldcg(surv_j + r * K6B_LIST + e);
+          small_key[e] = __ldcg(surv_key + slot * K6B_LIST + e);
+          small_j[e] = __ldcg(surv_j + slot * K6B_LIST + e);
         }
         __syncthreads();
-        select_and_emit<false>(sm, small_key, small_j, survivors, sp.k, survivors, s_row[r],
-                               static_cast<size_t>(orow), scorer, out);
+        select_and_emit<false, false>(sm, small_key, small_j, survivors, sp.k, survivors, br.row[r],
+                                      static_cast<size_t>(orow), scorer, out);
       } else if (survivors <= K6B_LIST) {
-        // a wide tie plateau: select over the survivor list where it lies (L2), not over N keys
-        select_and_emit<false>(sm, surv_key + r * K6B_LIST, surv_j + r * K6B_LIST, survivors, sp.k, survivors,
-                               s_row[r], static_cast<size_t>(orow), scorer, out);
+        select_and_emit<false, true>(sm, surv_key + slot * K6B_LIST, surv_j + slot * K6B_LIST, survivors, sp.k,
+                                     survivors, br.row[r], static_cast<size_t>(orow), scorer, out);
       } else {
         if (!dense) {
           // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
-          const int i = s_row[r];
-          const double floor_r = s_floor[r];
+          const int i = br.row[r];
+          const double floor_r = br.floor[r];
           __syncthreads();
           for (int j = tid; j < n; j += K6B_THREADS) {
             const Scores sc = scorer(i, j);
             const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_r) && !(sp.exclude_self && j == i);
-            keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(sc.h) : 0ull;
+            keys_r[j] = ok ? f64_orderable(sc.h) : 0ull;
           }
+          __threadfence();
           __syncthreads();
         }
-        select_and_emit<true>(sm, keys_r, nullptr, n, sp.k, survivors, s_row[r], static_cast<size_t>(orow),
-                              scorer, out);
+        select_and_emit<true, true>(sm, keys_r, nullptr, n, sp.k, survivors, br.row[r],
+                                    static_cast<size_t>(orow), scorer, out);
       }
     }
   }
@@ -832,10 +1007,14 @@ int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
   return TVBF_OK;
 }
 
+static int k6_cap_rows(int sm_count) { return sm_count * K6B_MAXB; }
+
 size_t k6_scratch_bytes(int n_shows, int sm_count) {
-  // batched feature kernel: one CTA per SM, up to K6B_MAXB key rows each
-  // + survivor lists of K6B_LIST (key, column) entries per batch row
-  return static_cast<size_t>(sm_count) * K6B_MAXB * (static_cast<size_t>(n_shows) * 8 + K6B_LIST * 12);
+  // no-text kernel: one CTA per SM, up to K6B_MAXB rows each: dense keys + survivor lists of
+  // K6B_LIST (key, column) entries per row; the text kernel lays the same bytes out per listed row
+  // behind its counters
+  return K6T_COUNTER_BYTES + static_cast<size_t>(k6_cap_rows(sm_count)) *
+                                 (static_cast<size_t>(n_shows) * 8 + K6B_LIST * 12);
 }
 
 int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* count_ptr,
@@ -849,22 +1028,23 @@ int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* c
   if (no_text) {
     // rows known to have no text: no mask, no CSR
     const size_t smem = static_cast<size_t>(K6B_SMALL) * 12;
-    auto kern = exact_rows_batched_kernel<false, K6B_MAXB>;
-    TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_notext_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    kern<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors, row_begin,
-                                          rows_are_local, 0, key_scratch, out);
-    TVBF_LAUNCH_OK("exact_rows_batched_kernel<no text>");
+    exact_rows_notext_kernel<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors,
+                                                              row_begin, rows_are_local, key_scratch, out);
+    TVBF_LAUNCH_OK("exact_rows_notext_kernel");
     return TVBF_OK;
   }
   const size_t smem = mask_bytes + static_cast<size_t>(K6B_SMALL) * 12;
-  if (smem <= 200 * 1024) {
-    auto kern = exact_rows_batched_kernel<true, K6B_TEXTB>;
-    TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (smem <= 160 * 1024) {
+    TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    kern<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors, row_begin,
-                                          rows_are_local, static_cast<int>(mask_bytes), key_scratch, out);
-    TVBF_LAUNCH_OK("exact_rows_batched_kernel<text>");
+    TVBF_CUDA_OK(cudaMemsetAsync(key_scratch, 0, K6T_COUNTER_BYTES, st));
+    exact_rows_text_kernel<<<grid, K6B_THREADS, smem, st>>>(sp, rows, n_listed, count_ptr, list_cap, floors,
+                                                            row_begin, rows_are_local,
+                                                            static_cast<int>(mask_bytes), key_scratch,
+                                                            k6_cap_rows(grid), out);
+    TVBF_LAUNCH_OK("exact_rows_text_kernel");
     return TVBF_OK;
   }
   // vocabulary too wide for the shared-memory mask: one row per CTA pass
