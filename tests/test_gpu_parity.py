@@ -386,3 +386,26 @@ class TestReferenceUnitTests:
         st = c.get_similarity_statistics(m)
         assert st["std"] == pytest.approx(0.0, abs=1e-6) and st["median"] == pytest.approx(0.7)
         assert all(isinstance(v, float) for v in st.values())
+
+
+# ---- weight sweep over one device-resident catalogue ------------------------------------------------
+def test_weight_sweep_equals_separate_runs(engine, cat2k):
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import WEIGHT_SWEEP
+
+    comp = SimilarityComputer(engine=engine)
+    tabs = comp.compute_top_k_sweep(cat2k.features(), WEIGHT_SWEEP, k=10)
+    assert len(tabs) == len(WEIGHT_SWEEP)
+    for w, got in zip(WEIGHT_SWEEP, tabs):
+        ref = SimilarityComputer(*w, engine=engine).compute_top_k(cat2k.features(), k=10)
+        assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.hybrid, ref.hybrid, equal_nan=True)
+    assert_topk_matches(tabs[3], cat2k.features(), np.arange(0, 2000, 41), WEIGHT_SWEEP[3], 10, 0.1)
+
+
+def test_weight_sweep_with_folded_features_uploads_per_triple(engine):
+    z, cat = load_golden("populate_random_float_n48")
+    triples = [(2.0, 3.0, 1.0), (0.4, 0.5, 0.1)]
+    tabs = engine.compute_top_k_sweep(cat.features(), triples, 7, 0.5)
+    for w, got in zip(triples, tabs):
+        ref = engine.compute_top_k(cat.features(), w, 7, 0.5)
+        assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.hybrid, ref.hybrid, equal_nan=True)

@@ -352,6 +352,35 @@ class HybridTopKEngine:
         t["row_begin"] = row_begin
         return t
 
+    def top_k_sweep_device(self, cat: DeviceCatalogue, weight_list, k: int = 20, min_similarity: float = 0.1,
+                           exclude_self: bool = True, **kw) -> list[dict]:
+        """Weight sweep (BASELINE config C5; notebooks/03 cell 6 of the reference): one table per
+        weight triple over ONE device-resident catalogue -- H2D, normalisation, the fp16 operand and
+        the packed genre / metadata words do not depend on the weights and are shared; the candidate
+        sweep runs per triple.  (Sharing the tensor-core sweep too was tried with one candidate list
+        per show scored by max_w U_w / sum_w: correct, but the bound on what a list dropped is then
+        too loose to certify rows once the triples differ as much as the reference's schemes do;
+        it needs one list per triple in the epilogue -- see DESIGN.md section 8.)"""
+        if cat.folded:
+            raise _lib.TvbfError("a catalogue with folded (non-binary) groups bakes the weights into the "
+                                 "operand; use compute_top_k_sweep, which uploads once per triple")
+        return [self.top_k_device(cat, tuple(float(x) for x in w), k, min_similarity, exclude_self, **kw)
+                for w in weight_list]
+
+    def compute_top_k_sweep(self, features: dict, weight_list, k: int = 20, min_similarity: float = 0.1,
+                            metadata_mode: str = "mean3", exclude_self: bool = True, **kw) -> list[TopK]:
+        """features dict -> one host TopK per weight triple (staging and upload shared when the
+        features are binary / one-hot)."""
+        triples = [tuple(float(x) for x in w) for w in weight_list]
+        if not triples:
+            return []
+        st = stage(features, metadata_mode)
+        cat = self.upload(st, triples[0])
+        if cat.folded:   # weights are baked into the operand: one upload per triple
+            return [self.to_host(self.top_k_device(self.upload(st, w), w, k, min_similarity, exclude_self, **kw))
+                    for w in triples]
+        return [self.to_host(t) for t in self.top_k_sweep_device(cat, triples, k, min_similarity, exclude_self, **kw)]
+
     def to_host(self, t: dict, copy: bool = True) -> TopK:
         """D2H of a result table into cached pinned buffers (synchronises).  With ``copy=False`` the
         returned arrays alias the pinned buffers and are valid until the next ``to_host`` of the

@@ -127,3 +127,16 @@ class SimilarityComputer:
                                            exclude_self, list(device_ids), **kw)
         eng = self.engine if device_ids is None else HybridTopKEngine(device_ids[0])
         return eng.compute_top_k(features, weights, k, min_similarity, metadata_mode, exclude_self, **kw)
+
+    def compute_top_k_sweep(self, features: dict, weight_list, k: int = 20, min_similarity: float = 0.1,
+                            exclude_self: bool = True, metadata_mode: str = "mean3",
+                            normalize_weights: bool = False, **kw) -> list[TopK]:
+        """One top-K table per (genre, text, metadata) weight triple -- the comparison of weighting
+        schemes the reference does by re-running everything per scheme (notebooks/03 cell 6) -- with
+        staging, upload and feature prep shared by all triples.  Each table is identical to what
+        ``SimilarityComputer(*triple).compute_top_k(...)`` returns."""
+        triples = []
+        for gw, tw, mw in weight_list:
+            tot = float(gw) + float(tw) + float(mw)
+            triples.append((gw / tot, tw / tot, mw / tot) if normalize_weights else (float(gw), float(tw), float(mw)))
+        return self.engine.compute_top_k_sweep(features, triples, k, min_similarity, metadata_mode, exclude_self, **kw)
