@@ -232,9 +232,14 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   kp.tile_stride = 1;
   kp.seed_theta = 0;
   if (pl.sym) {
-    // bits 22-27 of tuning: column-tile stride of the threshold seed pass (0 = 48, 63 = no seeding)
+    // bits 22-27 of tuning: column-tile stride of the threshold seed pass (0 = auto, 63 = no seeding)
+    // (values above 48 step by 8: 50 -> 64, 54 -> 96, 58 -> 128, 62 -> 160)
     const int st_req = (p->tuning >> 22) & 0x3F;
-    kp.tile_stride = st_req == 0 ? 48 : (st_req == 63 ? 1 : st_req);
+    // default: every 96th tile but at least 4 sampled tiles (measured on C3: stride 48 62.2 ms per
+    // step, 64 61.1, 96 61.0, 128 61.6, 160 61.5)
+    int st_auto = pl.col_tiles / 4;
+    st_auto = st_auto > 96 ? 96 : (st_auto < 8 ? 8 : st_auto);
+    kp.tile_stride = st_req == 0 ? st_auto : (st_req == 63 ? 1 : (st_req <= 48 ? st_req : 48 + (st_req - 48) * 8));
     if (kp.tile_stride > pl.col_tiles) kp.tile_stride = pl.col_tiles > 1 ? pl.col_tiles : 1;
   }
   kp.sym_cap = pl.sym_cap;
@@ -441,6 +446,9 @@ int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan&
   kp->rb_per_group = sp.pl.sb_per_group;
   kp->sb_world = world;
   kp->sb_rank = rank;
+  // a rank that sweeps 1/world of the tiles gets fewer threshold refreshes: seed more densely
+  // (measured at world = 8 on C3: stride 48 -> 0.6 + 8.0 ms per rank, stride 96 -> 0.4 + 8.5 ms)
+  if (world >= 4 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
   return TVBF_OK;
 }
 
