@@ -167,7 +167,7 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
  *                                                              lists of ITS rows (or all_gather)
  *        tvbf_rescore_lists  rows [row_begin,row_end) of p  -> gather of the result tables
  *      L = tvbf_sym_list_len(); eligibility (packed groups, non-negative weights, positive
- *      min_similarity, k <= 48): tvbf_sym_eligible().  row_begin/row_end of p are ignored by the
+ *      min_similarity, k <= 100): tvbf_sym_eligible().  row_begin/row_end of p are ignored by the
  *      first two calls. */
 int tvbf_sym_eligible(const tvbf_features* f, const tvbf_params* p);
 int32_t tvbf_sym_list_len(const tvbf_features* f, const tvbf_params* p);

@@ -199,7 +199,7 @@ def test_other_k(engine, cat2k, k):
     assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 7), (0.4, 0.5, 0.1), k, 0.0)
 
 
-@pytest.mark.parametrize("k", [1, 20, 48])
+@pytest.mark.parametrize("k", [1, 20, 48, 64, 100])
 def test_other_k_symmetric(engine, cat2k, k):
     top = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), k, 0.02, tuning=SYM_ON)
     assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 7), (0.4, 0.5, 0.1), k, 0.02)
@@ -208,8 +208,8 @@ def test_other_k_symmetric(engine, cat2k, k):
 def test_symmetric_request_on_ineligible_job_is_refused(engine, cat2k):
     from tvbingefriend_recommendation_service_b200._lib import TvbfError
 
-    with pytest.raises(TvbfError):   # k = 100 needs more candidates per show than the shared lists keep
-        engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 100, 0.1, tuning=SYM_ON)
+    with pytest.raises(TvbfError):   # k = 150 needs more candidates per show than the shared lists keep
+        engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 150, 0.1, tuning=SYM_ON)
     with pytest.raises(TvbfError):   # non-positive threshold
         engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.0, tuning=SYM_ON)
 

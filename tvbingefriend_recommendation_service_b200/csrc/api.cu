@@ -99,7 +99,7 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   if (pl->stages > max_stages) pl->stages = max_stages;
   if (pl->stages < 2) pl->stages = 2;
   pl->sym = 0;
-  pl->sym_cap = 1024;
+  pl->sym_cap = 1024;   // entries per shared list; 4096 once more than 64 candidates are kept (set below)
   const int sb_rows = 128 * pl->cg;
   pl->sb_count = (pl->rows + sb_rows - 1) / sb_rows;
   pl->col_tiles = (f->n_shows + 255) / 256;
@@ -129,11 +129,12 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
     // computed and each score is offered to both shows.  Needs the whole catalogue in one shard,
     // CTA pairs (256-row super block == 256-column tile), packed groups with non-negative weights
     // and a positive threshold (so that every dropped U <= theta_init is below min_similarity).
+    if (pl->kp > 64) pl->sym_cap = 4096;
     const int sym_req = (tune >> 20) & 0x3;
     const bool eligible = pl->cg == 2 && p->row_begin == 0 && p->row_end == f->n_shows &&
                           f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED &&
                           p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0 &&
-                          p->min_similarity > 1e-30 && pl->kp <= 64 && p->exclude_self;
+                          p->min_similarity > 1e-30 && pl->kp <= 128 && p->exclude_self;
     if (sym_req == 2) TVBF_REQUIRE(eligible, "symmetric mode requested but the job is not eligible");
     // auto: worth it once the triangle is large (measured: C2, 79 tiles, is 15 % slower; C3, 391
     // tiles, 1.5x faster)
@@ -417,7 +418,7 @@ int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int wo
   pl.grid = pl.sb_per_group * pl.splits * 2;
   size_t off = 0;
   sp->off_prog = off;    off = align_up(off + 256, 256);
-  sp->off_scratch = off; off = align_up(off + static_cast<size_t>(sms) * 128 * 32 * 4 * 8, 256);
+  sp->off_scratch = off; off = align_up(off + static_cast<size_t>(sms) * 128 * 32 * pl.entries * 8, 256);
   sp->off_gcnt = off;    off = align_up(off + static_cast<size_t>(f->n_pad) * 4, 256);
   sp->off_glist = off;   off = align_up(off + static_cast<size_t>(f->n_pad) * pl.sym_cap * 8, 256);
   sp->off_flag = off;    off = align_up(off + static_cast<size_t>(f->n_shows) * 4, 256);

@@ -183,10 +183,13 @@ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
 
 // ---- symmetric mode helpers ---------------------------------------------------------------------
 // Raise the shared threshold of one show to the kp-th largest score of the first n entries of its
-// list (n a power of two <= 1024).  Entries reserved but not yet written read as 0 = -inf, so the
+// list (n a power of two).  Entries reserved but not yet written read as 0 = -inf, so the
 // result can only be too LOW, never too high.  Warp-cooperative, deliberately not inlined.
 __device__ __noinline__ void sym_refresh_theta(const uint2* list, int n, int kp,
                                                unsigned int* theta_slot, int lane) {
+  // lists longer than 1024 (kp > 64): the most recent 1024 entries -- the kp-th largest of ANY
+  // subset is a valid lower bound, and the latest entries passed the highest thresholds
+  if (n > 1024) { list += n - 1024; n = 1024; }
   uint32_t v[32];
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
@@ -761,53 +764,71 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= n_rows) return;
   const unsigned total = p.g_cnt[r];
-  const int n = static_cast<int>(total < static_cast<unsigned>(p.sym_cap) ? total : p.sym_cap);
-  const uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
-  uint32_t v[32], cidx[32];
-#pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    const int idx = q * 32 + lane;
-    uint2 e = make_uint2(0u, 0u);
-    if (idx < n) e = __ldcg(list + idx);
-    v[q] = idx < n ? e.x : 0u;
-    cidx[q] = e.y;
-  }
+  const int n_all = static_cast<int>(total < static_cast<unsigned>(p.sym_cap) ? total : p.sym_cap);
+  uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
   const int kp = p.kp;
-  uint32_t best = 0u;  // kp-th largest score bits (0 when n < kp)
-  if (n > kp) {
-#pragma unroll 1
-    for (int bit = 30; bit >= 0; --bit) {
-      const uint32_t t = best | (1u << bit);
-      int c = 0;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) c += (v[q] >= t);
-      c = __reduce_add_sync(kFullMask, c);
-      if (c >= kp) best = t;
-    }
-  }
-  // entries strictly above the kp-th value always fit; entries equal to it fill the rest
   uint2* dst = p.cand + static_cast<size_t>(r) * kp;
-  int out = 0;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
+  // Lists of up to 1024 entries are selected in one go from registers (32 per lane).  Longer ones
+  // (kp > 64) in windows: the kp survivors so far, parked at the head of the list, plus the next
+  // 1024 - kp entries; the kp-th value only rises from window to window, so the last one bounds
+  // everything that was cut.
+  uint32_t best = 0u;  // kp-th largest score bits (0 when n <= kp)
+  int done = 0, kept = 0;
+  do {
+    const int fresh = n_all - done < 1024 - kept ? n_all - done : 1024 - kept;
+    const int n = kept + fresh;
+    uint32_t v[32], cidx[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
       const int idx = q * 32 + lane;
-      const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
-      const unsigned bal = __ballot_sync(kFullMask, take);
-      const int pos = out + __popc(bal & ((1u << lane) - 1u));
-      if (take && pos < kp) dst[pos] = make_uint2(v[q], cidx[q]);
-      out += __popc(bal);
+      uint2 e = make_uint2(0u, 0u);
+      if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
+      v[q] = idx < n ? e.x : 0u;
+      cidx[q] = e.y;
     }
-    if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
-  }
+    done += fresh;
+    const bool last = done >= n_all;
+    uint2* out_p = last ? dst : list;
+    best = 0u;
+    if (n > kp) {
+#pragma unroll 1
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t t = best | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) c += (v[q] >= t);
+        c = __reduce_add_sync(kFullMask, c);
+        if (c >= kp) best = t;
+      }
+    }
+    __syncwarp();   // all loads of this window are done before its head is overwritten
+    // entries strictly above the kp-th value always fit; entries equal to it fill the rest
+    int out = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int idx = q * 32 + lane;
+        const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
+        const unsigned bal = __ballot_sync(kFullMask, take);
+        const int pos = out + __popc(bal & ((1u << lane) - 1u));
+        if (take && pos < kp) out_p[pos] = make_uint2(v[q], cidx[q]);
+        out += __popc(bal);
+      }
+      if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
+    }
+    kept = n < kp ? n : kp;
+    __syncwarp();
+    if (last) break;
+    __threadfence_block();
+  } while (true);
   if (lane == 0) {
     const unsigned int th_bits = p.g_theta[r];
     float bound = __int_as_float(0xff800000);                        // nothing dropped so far
     if (th_bits > __float_as_uint(p.theta_init)) bound = __uint_as_float(th_bits);  // elements were rejected
-    if (n > kp) bound = fmaxf(bound, __uint_as_float(best));         // list entries cut here
+    if (n_all > kp) bound = fmaxf(bound, __uint_as_float(best));     // list entries cut here
     if (total > static_cast<unsigned>(p.sym_cap)) bound = __int_as_float(0x7f800000);  // overflow: send to K6
-    p.cand_cnt[r] = n < kp ? n : kp;
+    p.cand_cnt[r] = kept;
     p.cand_theta[r] = bound;
   }
 }
@@ -960,7 +981,8 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
         const int clusters = grid / 2;
         seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
         if (seed.rb_per_group < 1) seed.rb_per_group = 1;
-        int rc = launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
+        int rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
+                             : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
         if (rc != TVBF_OK) return rc;
         TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
       }

@@ -422,7 +422,7 @@ class HybridTopKEngine:
 
     def sym_eligible(self, cat: DeviceCatalogue, weights, k, min_similarity) -> bool:
         """Can this job use the symmetric (tile-sharded) sweep?  (packed groups, non-negative
-        weights, positive threshold, k <= 48)"""
+        weights, positive threshold, k <= 100)"""
         if cat.folded:
             return False
         p = self._params(cat, weights, k, min_similarity)
