@@ -157,6 +157,17 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
 size_t tvbf_topk_workspace_bytes(const tvbf_features* f, const tvbf_params* p);
 int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_topk_out* out,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* ---- weight sweep (BASELINE config C5; notebooks/03 cell 6 of the reference compares weighting
+ *      schemes by re-running everything): the same whole-catalogue job for n_weights <= 5 triples
+ *      p[0..n) that differ ONLY in their weights, sharing ONE symmetric tensor-core sweep.  The
+ *      epilogue scores every pair under every triple and keeps one shared candidate list per
+ *      (triple, show); rescoring, certificate and exact repair run per triple into out[w].  Every
+ *      triple must be eligible for the symmetric sweep (tvbf_sym_eligible).  The tables are
+ *      identical to those of n_weights separate tvbf_hybrid_topk calls. */
+size_t tvbf_topk_sweep_workspace_bytes(const tvbf_features* f, const tvbf_params* p, int32_t n_weights);
+int tvbf_hybrid_topk_sweep(const tvbf_features* f, const tvbf_params* p, int32_t n_weights,
+                           const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
+                           void* stream);
 /* ---- the same job tile-sharded over several GPUs (symmetric sweep).  hybrid(i,j) == hybrid(j,i),
  *      so GPU `rank` of `world` computes only the tiles on/above the diagonal of the 256-row super
  *      blocks dealt to it and feeds BOTH shows of every score; it ends with partial candidate lists

@@ -409,3 +409,32 @@ def test_weight_sweep_with_folded_features_uploads_per_triple(engine):
     for w, got in zip(triples, tabs):
         ref = engine.compute_top_k(cat.features(), w, 7, 0.5)
         assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.hybrid, ref.hybrid, equal_nan=True)
+
+
+@pytest.mark.parametrize("k", [20, 100])
+def test_shared_tensor_core_sweep_equals_separate_runs(engine, cat2k, k):
+    """One symmetric sweep for five weight triples (one candidate list per triple and show)."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import WEIGHT_SWEEP
+
+    dc = engine.upload(stage(cat2k.features()))
+    triples = list(WEIGHT_SWEEP) + [(0.0, 1.0, 0.0)]       # 6 triples: two launches (5 + 1)
+    tabs = [engine.to_host(t) for t in engine.top_k_sweep_device(dc, triples, k, 0.1, shared=True)]
+    assert len(tabs) == len(triples)
+    for w, got in zip(triples, tabs):
+        ref = engine.to_host(engine.top_k_device(dc, w, k, 0.1))
+        assert np.array_equal(got.indices, ref.indices), w
+        assert np.array_equal(got.counts, ref.counts), w
+        m = ref.indices >= 0
+        for name in ("hybrid", "genre", "text", "metadata"):
+            assert np.array_equal(getattr(got, name)[m], getattr(ref, name)[m]), (w, name)
+    assert_topk_matches(tabs[3], cat2k.features(), np.arange(0, 2000, 41), triples[3], k, 0.1)
+
+
+def test_shared_sweep_refuses_ineligible_triples(engine, cat2k):
+    from tvbingefriend_recommendation_service_b200._lib import TvbfError
+    from tvbingefriend_recommendation_service_b200.engine import stage
+
+    dc = engine.upload(stage(cat2k.features()))
+    with pytest.raises(TvbfError):   # negative weight: not eligible for the symmetric sweep
+        engine.top_k_sweep_device(dc, [(0.4, 0.5, 0.1), (-0.1, 0.5, 0.1)], 20, 0.1, shared=True)

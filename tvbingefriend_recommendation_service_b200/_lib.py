@@ -75,6 +75,9 @@ SIGNATURES = {
     "tvbf_topk_workspace_bytes": (c_size_t, [C.POINTER(Features), C.POINTER(Params)]),
     "tvbf_hybrid_topk": (C.c_int, [C.POINTER(Features), C.POINTER(Params), C.POINTER(TopKOut),
                                    c_void_p, c_size_t, c_void_p]),
+    "tvbf_topk_sweep_workspace_bytes": (c_size_t, [C.POINTER(Features), C.POINTER(Params), c_int32]),
+    "tvbf_hybrid_topk_sweep": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, C.POINTER(TopKOut),
+                                         c_void_p, c_size_t, c_void_p]),
     "tvbf_sym_eligible": (C.c_int, [C.POINTER(Features), C.POINTER(Params)]),
     "tvbf_sym_list_len": (c_int32, [C.POINTER(Features), C.POINTER(Params)]),
     "tvbf_sym_workspace_bytes": (c_size_t, [C.POINTER(Features), C.POINTER(Params), c_int32]),

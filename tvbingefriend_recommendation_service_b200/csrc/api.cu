@@ -82,7 +82,8 @@ int validate_params(const tvbf_features* f, const tvbf_params* p) {
   return TVBF_OK;
 }
 
-int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
+// sweep > 1: a weight sweep -- every list-shaped region holds `sweep` slices of n_pad virtual shows
+int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl, int sweep = 1) {
   int sms = 0;
   int rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
@@ -154,12 +155,14 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl) {
   pl->k6_grid = sms;
   size_t off = 0;
   pl->off_scratch = off; off = align_up(off + (use_k1 ? static_cast<size_t>(pl->grid) * 128 * 32 * pl->entries * 8 : 0), 256);
-  pl->off_cand = off;    off = align_up(off + (use_k1 ? static_cast<size_t>(pl->rows) * pl->cand_lists * pl->kp * 8 : 0), 256);
-  pl->off_cnt = off;     off = align_up(off + static_cast<size_t>(pl->rows) * pl->cand_lists * 4, 256);
-  pl->off_theta = off;   off = align_up(off + static_cast<size_t>(pl->rows) * pl->cand_lists * 4, 256);
-  pl->off_gtheta = off;  off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * 4 : 0), 256);
-  pl->off_gcnt = off;    off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * 4 : 0), 256);
-  pl->off_glist = off;   off = align_up(off + (pl->sym ? static_cast<size_t>(f->n_pad) * pl->sym_cap * 8 : 0), 256);
+  const size_t list_rows = sweep > 1 ? static_cast<size_t>(sweep) * f->n_pad : static_cast<size_t>(pl->rows);
+  const size_t sym_rows = static_cast<size_t>(sweep > 1 ? sweep : 1) * f->n_pad;
+  pl->off_cand = off;    off = align_up(off + (use_k1 ? list_rows * pl->cand_lists * pl->kp * 8 : 0), 256);
+  pl->off_cnt = off;     off = align_up(off + list_rows * pl->cand_lists * 4, 256);
+  pl->off_theta = off;   off = align_up(off + list_rows * pl->cand_lists * 4, 256);
+  pl->off_gtheta = off;  off = align_up(off + (pl->sym ? sym_rows * 4 : 0), 256);
+  pl->off_gcnt = off;    off = align_up(off + (pl->sym ? sym_rows * 4 : 0), 256);
+  pl->off_glist = off;   off = align_up(off + (pl->sym ? sym_rows * pl->sym_cap * 8 : 0), 256);
   pl->off_flag = off;    off = align_up(off + static_cast<size_t>(pl->rows) * 4, 256);
   pl->off_floor = off;   off = align_up(off + static_cast<size_t>(pl->rows) * 8, 256);
   pl->off_count = off;   off = align_up(off + 256, 256);
@@ -190,7 +193,7 @@ double default_text_rel_err(int dtype) {
 // Everything the candidate kernel needs besides the launch geometry: pointers into the workspace,
 // the fp32 weights of the epilogue and the slack terms of the upper bound U.
 int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl, uint8_t* ws,
-                   tvbf::K1Params* out_kp) {
+                   tvbf::K1Params* out_kp, int n_sweep = 1) {
   const int s = f->text_scale_log2;
   const double inv_scale2 = std::ldexp(1.0, -2 * s);
   const double rel = p->text_rel_err > 0 ? p->text_rel_err : default_text_rel_err(f->text_dtype);
@@ -273,6 +276,22 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
     th = std::nextafterf(th, -INFINITY);
     if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
     kp.theta_init = th;
+  }
+  kp.n_weights = 1;
+  kp.n_pad = f->n_pad;
+  if (n_sweep > 1) {
+    // weight sweep over the triples p[0 .. n_sweep) (packed groups only, checked by the caller):
+    // the epilogue constants of every triple, same formulas as above
+    kp.n_weights = n_sweep;
+    for (int w = 0; w < n_sweep; ++w) {
+      const tvbf_params& q = p[w];
+      const double ws_ = std::fabs(q.genre_weight) + std::fabs(q.text_weight) + std::fabs(q.metadata_weight);
+      kp.mw_text[w] = static_cast<float>(q.text_weight * inv_scale2);
+      kp.mw_text_err[w] = static_cast<float>(std::fabs(q.text_weight) * inv_scale2 * rel);
+      kp.mw_eps[w] = static_cast<float>(4e-6 * (ws_ + 1.0));
+      kp.mw_genre[w] = static_cast<float>(q.genre_weight);
+      kp.mw_meta[w] = static_cast<float>(q.metadata_weight);
+    }
   }
   return TVBF_OK;
 }
@@ -369,6 +388,88 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
   if ((phases & 4) && !p->skip_fallback) {
     rc = tvbf::k6_launch_flagged(sp, flagged, floors, pl.rows, p->row_begin, keys, pl.k6_grid, *out, st);
     if (rc != TVBF_OK) return rc;
+  }
+  return TVBF_OK;
+}
+
+// ---- weight sweep: several weight triples share ONE symmetric tensor-core sweep ----------------
+namespace {
+int sweep_plan(const tvbf_features* f, const tvbf_params* p, int n, tvbf_params* q, Plan* pl) {
+  TVBF_REQUIRE(p != nullptr && n >= 1 && n <= tvbf::kMaxSweep, "weight sweep: 1..%d triples per call",
+               tvbf::kMaxSweep);
+  for (int w = 0; w < n; ++w) {
+    int rc = validate_params(f, &p[w]);
+    if (rc != TVBF_OK) return rc;
+    TVBF_REQUIRE(p[w].k == p[0].k && p[w].min_similarity == p[0].min_similarity &&
+                     p[w].exclude_self == p[0].exclude_self && p[w].row_begin == 0 &&
+                     p[w].row_end == f->n_shows && !p[w].force_exact && p[w].phases == 0,
+                 "weight sweep: triple %d differs from triple 0 in more than the weights (whole catalogue only)", w);
+    // every triple must be eligible for the symmetric sweep on its own
+    tvbf_params t = p[w];
+    t.tuning = (t.tuning & ~(0x3 << 20)) | (2 << 20);
+    t.tuning = (t.tuning & ~0xF) | 2;
+    Plan tmp;
+    rc = make_plan(f, &t, &tmp);
+    if (rc != TVBF_OK) return rc;
+  }
+  *q = p[0];
+  q->tuning = (q->tuning & ~(0x3 << 20)) | (2 << 20);
+  q->tuning = (q->tuning & ~0xF) | 2;
+  return make_plan(f, q, pl, n);
+}
+}  // namespace
+
+size_t tvbf_topk_sweep_workspace_bytes(const tvbf_features* f, const tvbf_params* p, int32_t n_weights) {
+  if (validate_features(f) != TVBF_OK) return 0;
+  tvbf_params q;
+  Plan pl;
+  if (sweep_plan(f, p, n_weights, &q, &pl) != TVBF_OK) return 0;
+  return pl.total;
+}
+
+int tvbf_hybrid_topk_sweep(const tvbf_features* f, const tvbf_params* p, int32_t n_weights,
+                           const tvbf_topk_out* out, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(out != nullptr && workspace != nullptr, "tvbf_hybrid_topk_sweep: NULL argument");
+  tvbf_params q;
+  Plan pl;
+  rc = sweep_plan(f, p, n_weights, &q, &pl);
+  if (rc != TVBF_OK) return rc;
+  for (int w = 0; w < n_weights; ++w)
+    TVBF_REQUIRE(out[w].indices && out[w].counts && out[w].hybrid && out[w].genre && out[w].text &&
+                     out[w].metadata && out[w].stats,
+                 "output table %d has NULL members", w);
+  if (workspace_bytes < pl.total) {
+    tvbf_set_error("workspace too small: %zu < %zu", workspace_bytes, pl.total);
+    return TVBF_ERR_WORKSPACE;
+  }
+  auto st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* flagged = reinterpret_cast<int*>(ws + pl.off_flag);
+  double* floors = reinterpret_cast<double*>(ws + pl.off_floor);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + pl.off_keys);
+  tvbf::K1Params kp;
+  rc = fill_k1_params(f, n_weights > 1 ? p : &q, pl, ws, &kp, n_weights);
+  if (rc != TVBF_OK) return rc;
+  TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+  rc = tvbf::k1_launch(f, kp, pl.entries, pl.cg, pl.grid, st);
+  if (rc != TVBF_OK) return rc;
+  // compaction of all n_weights * n_pad shared lists into the candidate tables [triple][show][kp]
+  rc = tvbf::k4s_launch(kp, (n_weights > 1 ? n_weights : 1) * (n_weights > 1 ? f->n_pad : pl.rows), st);
+  if (rc != TVBF_OK) return rc;
+  for (int w = 0; w < n_weights; ++w) {
+    TVBF_CUDA_OK(cudaMemsetAsync(out[w].stats, 0, 8 * sizeof(int32_t), st));
+    const tvbf::ScoreParams sp = score_params(f, &p[w]);
+    const tvbf::CandLayout lay{static_cast<long long>(w) * (n_weights > 1 ? f->n_pad : 0), 1, 1};
+    rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, 1, lay, pl.kp, 0, pl.rows, out[w], flagged,
+                         floors, st);
+    if (rc != TVBF_OK) return rc;
+    if (!q.skip_fallback) {
+      rc = tvbf::k6_launch_flagged(sp, flagged, floors, pl.rows, 0, keys, pl.k6_grid, out[w], st);
+      if (rc != TVBF_OK) return rc;
+    }
   }
   return TVBF_OK;
 }

@@ -58,7 +58,7 @@ struct Smem {
   static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
   static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
   // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][256] words
-  static constexpr uint32_t OFF_Q = OFF_TH + 2 * MS_BYTES;
+  static constexpr uint32_t OFF_Q = OFF_TH + 2 * kMaxSweep * MS_BYTES;   // (one slice per triple of a weight sweep)
   static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * 256 * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
@@ -241,7 +241,8 @@ struct Pacer {
   }
 };
 
-// kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep
+// kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep,
+// 5 symmetric top-k sweep for p.n_weights weight triples at once (one shared list per triple and show)
 template <int E, bool kDump, int CG, int kMode>
 __global__ void __launch_bounds__(Roles<(kMode != 0)>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -250,6 +251,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   using L = Smem<CG>;
   constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 epilogue warps
   constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
+  constexpr bool kMulti = kMode == 5;    // weight sweep
   constexpr int STAGES = L::STAGES;
   constexpr int EPI = Roles<kSym>::EPI, PRODUCER_WARP = Roles<kSym>::PRODUCER, MMA_WARP = Roles<kSym>::MMA;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
@@ -327,11 +329,15 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (!kDump) {
             mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             if (elect_one()) {
-              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? MS_BYTES : 0u));
+              const uint32_t n_th = kMulti ? static_cast<uint32_t>(p.n_weights) : 1u;
+              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u));
               bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
               bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
               if (kSym && !kStats)  // snapshot of the column shows' thresholds (stale = lower = conservative)
-                bulk_load_1d(smem + L::OFF_TH + b * MS_BYTES, p.g_theta + col0, MS_BYTES, &col_full[b]);
+                for (uint32_t w = 0; w < n_th; ++w)
+                  bulk_load_1d(smem + L::OFF_TH + (b * kMaxSweep + w) * MS_BYTES,
+                               p.g_theta + static_cast<size_t>(w) * (kMulti ? p.n_pad : 0) + col0, MS_BYTES,
+                               &col_full[b]);
             }
             __syncwarp();
           }
@@ -448,12 +454,25 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         rn_wg = rs.genre_rnorm * p.w_genre;
         // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories)
         ci_wm = p.meta_scale[row] * p.w_meta * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
-        if (kStats) {  // plain cosines here; the weights enter only the hybrid
+        if (kStats || kMulti) {  // plain cosines here; the weights enter only the hybrid
           rn_wg = rs.genre_rnorm;
           ci_wm = p.meta_scale[row] * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
         }
       }
       float theta = row_valid ? p.theta_init : __int_as_float(0x7f800000);  // +inf: never append
+      float thw[kMaxSweep];   // weight sweep: this show's threshold under every triple
+#pragma unroll
+      for (int w = 0; w < kMaxSweep; ++w) thw[w] = __int_as_float(0x7f800000);
+      auto load_thw = [&]() {
+#pragma unroll
+        for (int w = 0; w < kMaxSweep; ++w)
+          if (w < p.n_weights && row_valid) {
+            unsigned int tb;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];"
+                         : "=r"(tb) : "l"(p.g_theta + static_cast<size_t>(w) * p.n_pad + row) : "memory");
+            thw[w] = __uint_as_float(tb);
+          }
+      };
       int cnt = 0;
       bool dropped = false;
       const int self_col = p.exclude_self ? row : -1;
@@ -520,7 +539,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const uint32_t b = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int col0 = kDump ? p.dump_col0 : jt * BN;
-        if (kSym && !kStats) {
+        if (kMulti) {
+          load_thw();
+        } else if (kSym && !kStats) {
           // current shared threshold of this thread's show (raised by any CTA working on it)
           unsigned int tb = 0x7f800000u;
           if (row_valid)
@@ -532,7 +553,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tc_fence_after();
         const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + L::OFF_COL + b * COL_BYTES);
         const float* sms = reinterpret_cast<const float*>(smem + L::OFF_MS + b * MS_BYTES);
-        const float* sth = reinterpret_cast<const float*>(smem + L::OFF_TH + b * MS_BYTES);
+        const float* sth = reinterpret_cast<const float*>(smem + L::OFF_TH + b * kMaxSweep * MS_BYTES);
         const uint32_t taddr = tmem_base + tmem_lane + b * BN;
         // off-diagonal tiles also feed the column shows (their mirror tile is never computed)
         const bool do_col = kSym && row_valid && jt != c.sb;
@@ -543,6 +564,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int q = 0; q < 4; ++q) stat_scale[q] = kStats ? static_cast<float>(kStatsBins) / p.stats->hi[q] : 0.f;
         // score 16 accumulator columns held in registers
         auto score16 = [&](const uint32_t (&acc)[16], int cbase) {
+          float gcv[kMulti ? 16 : 1], mcv[kMulti ? 16 : 1];   // weight sweep: cosines of the 16 columns
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const float a = __uint_as_float(acc[e]);
@@ -581,6 +603,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   if (v[1] > st_arg_v[0]) { st_arg_v[0] = v[1]; st_arg_i[0] = row; st_arg_j[0] = col; }
                   if (v[3] > st_arg_v[1]) { st_arg_v[1] = v[3]; st_arg_i[1] = row; st_arg_j[1] = col; }
                 }
+              } else if (kMulti) {
+                gcv[e] = gdot * rn_wg;   // plain genre / metadata cosines, scored per triple below
+                mcv[e] = mdot * ci_wm;
               } else if (kSym) {
                 if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col);
                 // padded columns carry threshold +inf, so no bound check is needed here
@@ -589,6 +614,36 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (col != self_col && col < p.n_shows) {
                   __stcg(my_list + cnt, make_uint2(__float_as_uint(u), static_cast<uint32_t>(col)));
                   ++cnt;
+                }
+              }
+            }
+          }
+          if (kMulti) {
+            // Weight sweep: one pass per triple over the 16 columns (rolled over the triples so that
+            // the code stays the size of the single-triple kernel).  Triple w's lists live under the
+            // virtual show id w * n_pad + show.
+#pragma unroll 1
+            for (int w = 0; w < p.n_weights; ++w) {
+              const float wg = p.mw_genre[w], wm = p.mw_meta[w], wt = p.mw_text[w], wte = p.mw_text_err[w],
+                          we = p.mw_eps[w];
+              const float th = w == 0 ? thw[0] : (w == 1 ? thw[1] : (w == 2 ? thw[2] : (w == 3 ? thw[3] : thw[4])));
+              const float4* t4p = reinterpret_cast<const float4*>(sth + w * BN + cbase);
+              const int vrow = w * p.n_pad + row, vcol0 = w * p.n_pad + col0 + cbase;
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 t4 = t4p[e4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int e = e4 * 4 + q;
+                  const float a = __uint_as_float(acc[e]);
+                  float uw = fmaf(gcv[e], wg, fmaf(mcv[e], wm, we));
+                  uw = fmaf(a, wt, uw);
+                  uw = fmaf(fabsf(a), wte, uw);
+                  const float tc = q == 0 ? t4.x : (q == 1 ? t4.y : (q == 2 ? t4.z : t4.w));
+                  const int col = col0 + cbase + e;
+                  if (uw > th && col != self_col && col < p.n_shows) sym_append(vrow, uw, col);
+                  // padded columns carry threshold +inf, so no bound check is needed here
+                  if (do_col && uw > tc) sym_append(vcol0 + e, uw, row);
                 }
               }
             }
@@ -638,7 +693,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               sym_refresh_theta(p.g_list + static_cast<size_t>(show) * sym_cap, n, p.kp, p.g_theta + show, lane);
             }
             pend2_n = 0;
-            if (row_valid) {  // pick up raises made by other CTAs (and by the refreshes above)
+            if (kMulti) {
+              load_thw();
+            } else if (row_valid) {  // pick up raises made by other CTAs (and by the refreshes above)
               unsigned int tb;
               asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
               theta = __uint_as_float(tb);
@@ -833,9 +890,9 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   }
 }
 
-__global__ void sym_init_kernel(unsigned int* theta, int n_shows, int n_pad, float theta_init) {
+__global__ void sym_init_kernel(unsigned int* theta, int n_shows, int n_pad, int n_virtual, float theta_init) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) theta[i] = i < n_shows ? __float_as_uint(theta_init) : 0x7f800000u;
+  if (i < n_virtual) theta[i] = (i % n_pad) < n_shows ? __float_as_uint(theta_init) : 0x7f800000u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -968,31 +1025,46 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
       return TVBF_ERR_INVALID;
     }
     const int n_pad = f->n_pad;
+    const int nw = kp.n_weights > 1 ? kp.n_weights : 1;   // weight sweep: nw * n_pad virtual shows
+    const size_t n_virtual = static_cast<size_t>(nw) * n_pad;
     if (kp.sym_phase != 2) {
-      sym_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(kp.g_theta, f->n_shows, n_pad, kp.theta_init);
+      sym_init_kernel<<<static_cast<unsigned>((n_virtual + 255) / 256), 256, 0, st>>>(
+          kp.g_theta, f->n_shows, n_pad, static_cast<int>(n_virtual), kp.theta_init);
       TVBF_LAUNCH_OK("sym_init_kernel");
       if (kp.tile_stride > 1) {
         // seed pass: one-sided sweep over every tile_stride-th column tile, thresholds only
-        K1Params seed = kp;
-        seed.sym = 0;
-        seed.seed_theta = 1;
-        seed.splits = 1;
-        seed.tiles_per_split = kp.col_tiles;
-        const int clusters = grid / 2;
-        seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
-        if (seed.rb_per_group < 1) seed.rb_per_group = 1;
-        int rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
-                             : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
-        if (rc != TVBF_OK) return rc;
-        TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+        // (once per triple of a weight sweep, into that triple's slice of g_theta)
+        for (int w = 0; w < nw; ++w) {
+          K1Params seed = kp;
+          seed.sym = 0;
+          seed.seed_theta = 1;
+          seed.splits = 1;
+          seed.tiles_per_split = kp.col_tiles;
+          seed.n_weights = 1;
+          if (nw > 1) {
+            seed.w_text = kp.mw_text[w];
+            seed.w_text_err = kp.mw_text_err[w];
+            seed.w_genre = kp.mw_genre[w];
+            seed.w_meta = kp.mw_meta[w];
+            seed.eps = kp.mw_eps[w];
+            seed.g_theta = kp.g_theta + static_cast<size_t>(w) * n_pad;
+          }
+          const int clusters = grid / 2;
+          seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
+          if (seed.rb_per_group < 1) seed.rb_per_group = 1;
+          int rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
+                               : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
+          if (rc != TVBF_OK) return rc;
+          TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
+        }
       }
       if (kp.sym_phase == 1) return TVBF_OK;
     }
-    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(n_pad) * 4, st));
-    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, static_cast<size_t>(n_pad) * kp.sym_cap * 8, st));
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, n_virtual * 4, st));
+    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, n_virtual * kp.sym_cap * 8, st));
     K1Params sweep = kp;
     sweep.tile_stride = 1;
-    return launch_k1<4, false, 2, 1>(f, sweep, grid, st);
+    return nw > 1 ? launch_k1<4, false, 2, 5>(f, sweep, grid, st) : launch_k1<4, false, 2, 1>(f, sweep, grid, st);
   }
   if (cta_group == 2) {
     switch (entries_per_lane) {

@@ -23,6 +23,8 @@ struct StatsAccum {
 };
 
 // parameters of the tcgen05 candidate kernel (hybrid_topk.cu)
+constexpr int kMaxSweep = 5;   // weight triples that can share one symmetric tensor-core sweep
+
 struct K1Params {
   const TvbfColSide* col_side;
   const float* meta_scale;
@@ -71,6 +73,11 @@ struct K1Params {
   int meta_hstack;     // 1: per-column 1/sqrt(#categories) scale is read from meta_scale
   float eps;           // absolute slack: fp32 rounding of the epilogue (+ folded-group bounds)
   float theta_init;    // just below min_similarity
+  // weight sweep (symmetric mode, n_weights > 1): triple w keeps its own shared lists under the
+  // virtual show id  w * n_pad + show  (g_theta / g_cnt / g_list / cand have n_weights * n_pad rows)
+  int n_weights;
+  int n_pad;
+  float mw_text[kMaxSweep], mw_text_err[kMaxSweep], mw_genre[kMaxSweep], mw_meta[kMaxSweep], mw_eps[kMaxSweep];
 };
 
 // parameters of the exact fp64 scorers (rescore.cu)

@@ -353,19 +353,56 @@ class HybridTopKEngine:
         return t
 
     def top_k_sweep_device(self, cat: DeviceCatalogue, weight_list, k: int = 20, min_similarity: float = 0.1,
-                           exclude_self: bool = True, **kw) -> list[dict]:
+                           exclude_self: bool = True, shared: bool | None = None, tuning: int = 0, **kw) -> list[dict]:
         """Weight sweep (BASELINE config C5; notebooks/03 cell 6 of the reference): one table per
-        weight triple over ONE device-resident catalogue -- H2D, normalisation, the fp16 operand and
-        the packed genre / metadata words do not depend on the weights and are shared; the candidate
-        sweep runs per triple.  (Sharing the tensor-core sweep too was tried with one candidate list
-        per show scored by max_w U_w / sum_w: correct, but the bound on what a list dropped is then
-        too loose to certify rows once the triples differ as much as the reference's schemes do;
-        it needs one list per triple in the epilogue -- see DESIGN.md section 8.)"""
+        weight triple over ONE device-resident catalogue.  H2D, normalisation, the fp16 operand and
+        the packed genre / metadata words never depend on the weights.  ``shared`` (default: when
+        every triple is eligible for the symmetric sweep and the catalogue has >= 40 000 shows)
+        also shares the tensor-core sweep between up to 5 triples per launch
+        (``tvbf_hybrid_topk_sweep``: one candidate list per (triple, show)); otherwise the candidate
+        sweep runs once per triple.  Either way the tables equal those of separate jobs."""
         if cat.folded:
             raise _lib.TvbfError("a catalogue with folded (non-binary) groups bakes the weights into the "
                                  "operand; use compute_top_k_sweep, which uploads once per triple")
-        return [self.top_k_device(cat, tuple(float(x) for x in w), k, min_similarity, exclude_self, **kw)
-                for w in weight_list]
+        triples = [tuple(float(x) for x in w) for w in weight_list]
+        if shared is None:
+            shared = (exclude_self and cat.n_shows >= 40_000 and len(triples) > 1 and not kw
+                      and all(self.sym_eligible(cat, w, k, min_similarity) for w in triples))
+        if not shared:
+            return [self.top_k_device(cat, w, k, min_similarity, exclude_self, tuning=tuning, **kw) for w in triples]
+        k, rows, dev, out = int(k), cat.n_shows, self.device, []
+        with torch.cuda.device(dev):
+            for g0 in range(0, len(triples), 5):
+                part = triples[g0:g0 + 5]
+                n = len(part)
+                ps = (Params * n)()
+                for w, (gw, tw, mw) in enumerate(part):
+                    ps[w] = Params(genre_weight=gw, text_weight=tw, metadata_weight=mw,
+                                   min_similarity=float(min_similarity), k=k, exclude_self=int(bool(exclude_self)),
+                                   row_begin=0, row_end=rows, splits=0, candidates=0, force_exact=0,
+                                   skip_fallback=0, text_rel_err=0.0, phases=0, tuning=int(tuning))
+                nbytes = self.lib.tvbf_topk_sweep_workspace_bytes(C.byref(cat.c), ps, n)
+                if nbytes == 0:
+                    check(-1, "tvbf_topk_sweep_workspace_bytes")
+                ws = self._workspace(nbytes)
+                tabs = [{
+                    "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
+                    "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
+                    "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                    "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                    "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                    "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
+                    "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
+                    "row_begin": 0,
+                } for _ in range(n)]
+                couts = (TopKOut * n)()
+                for w, t in enumerate(tabs):
+                    couts[w] = TopKOut(**{name: t[name].data_ptr() for name in
+                                          ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+                check(self.lib.tvbf_hybrid_topk_sweep(C.byref(cat.c), ps, n, couts, ws.data_ptr(), ws.numel(),
+                                                      self._stream()), "tvbf_hybrid_topk_sweep")
+                out += tabs
+        return out
 
     def compute_top_k_sweep(self, features: dict, weight_list, k: int = 20, min_similarity: float = 0.1,
                             metadata_mode: str = "mean3", exclude_self: bool = True, **kw) -> list[TopK]:
