@@ -93,21 +93,27 @@ def test_c4_250k_full_catalogue(engine):
 
 
 def test_c5_200k_50k_vocab_top100_full_size(engine):
-    """BASELINE config 5 at full size (200 k shows, 50 k vocabulary, top-100), one weight triple of
-    the sweep: 20 GB operand, GEMM K = 50 048, k = 100 candidate lists (one-sided sweep)."""
+    """BASELINE config 5 at full size (200 k shows, 50 k vocabulary, top-100, weight sweep): 20 GB
+    operand, GEMM K = 50 048, 128-candidate lists; the five triples share ONE symmetric sweep
+    (one shared list per triple and show) and every table is checked against the oracle."""
     from tvbingefriend_recommendation_service_b200.engine import stage
     from tvbingefriend_recommendation_service_b200.synthetic import WEIGHT_SWEEP, make_config
 
     cat = make_config("C5")
-    w = WEIGHT_SWEEP[1]
-    dc = engine.upload(stage(cat.features()), w)
-    top = engine.to_host(engine.top_k_device(dc, w, 100, 0.1))
-    assert top.indices.shape == (200_000, 100)
-    valid = np.arange(100)[None, :] < top.counts[:, None]
-    assert (top.hybrid[valid] >= 0.1).all() and (np.diff(top.hybrid, axis=1)[valid[:, 1:]] <= 0).all()
-    rows = np.linspace(0, 199_999, 24).astype(np.int64)
-    assert_topk_matches(top, cat.features(), rows, w, 100, 0.1)
-    del dc
+    dc = engine.upload(stage(cat.features()), WEIGHT_SWEEP[0])
+    tabs = engine.top_k_sweep_device(dc, WEIGHT_SWEEP, 100, 0.1)        # shared sweep (auto)
+    rows = np.linspace(0, 199_999, 12).astype(np.int64)
+    for w, t in zip(WEIGHT_SWEEP, tabs):
+        top = engine.to_host(t)
+        assert top.indices.shape == (200_000, 100)
+        valid = np.arange(100)[None, :] < top.counts[:, None]
+        assert (top.hybrid[valid] >= 0.1).all() and (np.diff(top.hybrid, axis=1)[valid[:, 1:]] <= 0).all()
+        assert_topk_matches(top, cat.features(), rows, w, 100, 0.1)
+    # a separate job for one triple gives the same table
+    one = engine.to_host(engine.top_k_device(dc, WEIGHT_SWEEP[1], 100, 0.1))
+    got = engine.to_host(tabs[1])
+    assert np.array_equal(one.indices, got.indices) and np.array_equal(one.hybrid, got.hybrid, equal_nan=True)
+    del dc, tabs
     import torch
     engine._ws = None
     torch.cuda.empty_cache()

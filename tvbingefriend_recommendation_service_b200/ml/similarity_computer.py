@@ -133,8 +133,9 @@ class SimilarityComputer:
                             normalize_weights: bool = False, **kw) -> list[TopK]:
         """One top-K table per (genre, text, metadata) weight triple -- the comparison of weighting
         schemes the reference does by re-running everything per scheme (notebooks/03 cell 6) -- with
-        staging, upload and feature prep shared by all triples.  Each table is identical to what
-        ``SimilarityComputer(*triple).compute_top_k(...)`` returns."""
+        staging, upload and feature prep shared by all triples and, on large catalogues of binary /
+        one-hot features, ONE tensor-core sweep for up to five triples.  Each table is identical to
+        what ``SimilarityComputer(*triple).compute_top_k(...)`` returns."""
         triples = []
         for gw, tw, mw in weight_list:
             tot = float(gw) + float(tw) + float(mw)
