@@ -151,8 +151,8 @@ def test_single_process_multi_gpu_matches_single_gpu(engine):
     assert np.array_equal(one.hybrid[m], two.hybrid[m])
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world):
+@pytest.mark.parametrize("world,k", [(2, 20), (3, 20), (3, 100), (8, 100)])
+def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world, k):
     """The three-phase multi-GPU protocol (seed -> MAX-reduce -> sweep -> gather -> rescore) with the
     ranks run one after the other on a single GPU; must give exactly the single-GPU table."""
     import torch
@@ -162,7 +162,7 @@ def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world):
     from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
 
     cat = make_catalogue(6000, 1024, nnz=20, seed=31)
-    w, k, ms = (0.4, 0.5, 0.1), 20, 0.1
+    w, ms = (0.4, 0.5, 0.1), 0.1
     dc = engine.upload(stage(cat.features()), w)
     assert engine.sym_eligible(dc, w, k, ms)
     thetas = [engine.sym_seed(dc, w, k, ms, r, world) for r in range(world)]
