@@ -5,8 +5,8 @@ shows/sec to top-20, TFLOP/s vs peak, at 1/2/4/8 B200, beside the host-CPU refer
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--impl b200|reference]
 
 One "step" = one pass of the hot path over the whole synthetic catalogue: K0 prep kernels ->
-K1 tcgen05 candidate pass -> K5 fp64 rescore/certify -> K6 exact repair (-> all-gather of the
-[N, k] tables when N GPUs > 1).  ``value`` is timed with the raw features already resident in HBM;
+K1 tcgen05 candidate pass -> K5 fp64 rescore/certify -> K6 exact repair (with N GPUs > 1: candidate
+lists exchanged by all-to-all before K5, [N, k] tables all-gathered after K6).  ``value`` is timed with the raw features already resident in HBM;
 ``e2e`` adds, inside the timed region, the H2D copy of the staged (pinned) feature buffers and the
 D2H read of the result table through the public engine API.  Prints ONE JSON line on rank 0.
 """
@@ -156,8 +156,9 @@ def bench_config(args, cfg) -> dict:
                         f"(~{cfg['nnz']} nnz/row), {cfg['n_genres']} genres, metadata one-hot {cfg['meta']}, "
                         f"hybrid weights 0.4/0.5/0.1, top-{cfg['k']}, min_similarity 0.1",
             "n_shows": cfg["n_shows"], "vocab": cfg["vocab"], "k": cfg["k"],
-            "parallelism": f"features replicated; x{args.gpus}: tile-sharded symmetric sweep + candidate-list "
-                           f"all-gather (or row-sharded one-sided with --one-sided)",
+            "parallelism": f"features replicated; x{args.gpus}: tile-sharded symmetric sweep, candidate lists "
+                           f"exchanged by one all-to-all over the row shards (or row-sharded one-sided "
+                           f"with --one-sided)",
             "l2_policy": "inputs larger than L2 (fp16 operand %.1f GB, streamed every step)"
                          % (cfg["n_shows"] * cfg["vocab"] * 2 / 1e9)}
 
@@ -209,6 +210,8 @@ def main() -> None:
     if args.gpus != world and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
+    if args.one_sided and world == 1:
+        args.tuning = (args.tuning & ~(3 << 20)) | (1 << 20)     # symmetric sweep off
     eng = HybridTopKEngine(local_rank)
     cat = make_config(args.config, cfg["n_shows"])
     n, k = cat.n_shows, cfg["k"]
@@ -307,8 +310,15 @@ def main() -> None:
     sym_forced_off = ((args.tuning >> 20) & 3) == 1 or args.one_sided
     used_sym = (not sym_forced_off) and tiles >= 160 and eng.sym_eligible(eng.prepare(raw, weights), weights, k, 0.1)
     k_pad = (cfg["vocab"] + 63) // 64 * 64
-    if used_sym:   # tiles on/above the diagonal + the sampled threshold-seed pass (every 48th column tile)
-        exec_tiles = tiles * (tiles + 1) / 2 + tiles * ((tiles + 47) // 48)
+    if used_sym:   # tiles on/above the diagonal + the sampled threshold-seed pass (api.cu: fill_k1_params)
+        st_req = (args.tuning >> 22) & 0x3F
+        stride = min(96, max(8, tiles // 4))
+        if st_req:
+            stride = 1 if st_req == 63 else (st_req if st_req <= 48 else 48 + (st_req - 48) * 8)
+        elif world >= 4:
+            stride = min(stride, 48)
+        seed_tiles = 0 if stride <= 1 else (tiles + stride - 1) // stride
+        exec_tiles = tiles * (tiles + 1) / 2 + tiles * seed_tiles
     else:
         exec_tiles = tiles * tiles
     exec_flops = 2.0 * exec_tiles * 256 * 256 * k_pad / world
