@@ -312,6 +312,24 @@ class HybridTopKEngine:
                                weights_baked=(gw, tw, mw) if folded else None, keep=keep)
 
     # ------------------------------------------------------------------------------------ top-k
+    _TABLE_FIELDS = ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")
+
+    def _alloc_tables(self, rows: int, k: int, row_begin: int | None = None) -> dict:
+        """Device result table: indices int32[rows, k] (-1 padded), counts int32[rows], four
+        float64[rows, k] score arrays, stats int32[8]."""
+        dev = self.device
+        t = {"indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
+             "counts": torch.empty((rows,), dtype=torch.int32, device=dev)}
+        for name in ("hybrid", "genre", "text", "metadata"):
+            t[name] = torch.empty((rows, k), dtype=torch.float64, device=dev)
+        t["stats"] = torch.zeros((8,), dtype=torch.int32, device=dev)
+        if row_begin is not None:
+            t["row_begin"] = row_begin
+        return t
+
+    def _c_tables(self, t: dict) -> TopKOut:
+        return TopKOut(**{name: t[name].data_ptr() for name in self._TABLE_FIELDS})
+
     def top_k_device(self, cat: DeviceCatalogue, weights=(0.4, 0.5, 0.1), k: int = 20,
                      min_similarity: float = 0.1, exclude_self: bool = True, row_begin: int = 0,
                      row_end: int | None = None, splits: int = 0, candidates: int = 0,
@@ -335,18 +353,8 @@ class HybridTopKEngine:
             if nbytes == 0:
                 check(-1, "tvbf_topk_workspace_bytes")
             ws = self._workspace(nbytes)
-            dev = self.device
-            t = out if out is not None else {
-                "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
-                "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
-                "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
-            }
-            cout = TopKOut(**{name: t[name].data_ptr() for name in
-                              ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+            t = out if out is not None else self._alloc_tables(rows, k)
+            cout = self._c_tables(t)
             check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(cout), ws.data_ptr(),
                                             ws.numel(), self._stream()), "tvbf_hybrid_topk")
         t["row_begin"] = row_begin
@@ -385,20 +393,10 @@ class HybridTopKEngine:
                 if nbytes == 0:
                     check(-1, "tvbf_topk_sweep_workspace_bytes")
                 ws = self._workspace(nbytes)
-                tabs = [{
-                    "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
-                    "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
-                    "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                    "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                    "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                    "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                    "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
-                    "row_begin": 0,
-                } for _ in range(n)]
+                tabs = [self._alloc_tables(rows, k, 0) for _ in range(n)]
                 couts = (TopKOut * n)()
                 for w, t in enumerate(tabs):
-                    couts[w] = TopKOut(**{name: t[name].data_ptr() for name in
-                                          ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+                    couts[w] = self._c_tables(t)
                 check(self.lib.tvbf_hybrid_topk_sweep(C.byref(cat.c), ps, n, couts, ws.data_ptr(), ws.numel(),
                                                       self._stream()), "tvbf_hybrid_topk_sweep")
                 out += tabs
@@ -509,22 +507,12 @@ class HybridTopKEngine:
         dev, rows, world = self.device, row_end - row_begin, int(cand_all.shape[0])
         table_rows = int(cand_all.shape[1])
         with torch.cuda.device(dev):
-            t = {
-                "indices": torch.empty((rows, k), dtype=torch.int32, device=dev),
-                "counts": torch.empty((rows,), dtype=torch.int32, device=dev),
-                "hybrid": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "genre": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "text": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "metadata": torch.empty((rows, k), dtype=torch.float64, device=dev),
-                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
-                "row_begin": row_begin,
-            }
+            t = self._alloc_tables(rows, k, row_begin)
             if rows > 0:
                 p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end,
                                  splits=splits, tuning=tuning)
                 ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
-                cout = TopKOut(**{name: t[name].data_ptr() for name in
-                                  ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")})
+                cout = self._c_tables(t)
                 check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(), cnt_all.data_ptr(),
                                                   bound_all.data_ptr(), world, int(table_row0), table_rows,
                                                   C.byref(cout), ws.data_ptr(),
@@ -576,16 +564,8 @@ class HybridTopKEngine:
             dev = self.device
             r = rows_np.shape[0]
             rows_d = torch.from_numpy(rows_np).to(dev)
-            t = {
-                "indices": torch.empty((r, k), dtype=torch.int32, device=dev),
-                "counts": torch.empty((r,), dtype=torch.int32, device=dev),
-                "hybrid": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "genre": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "text": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "metadata": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
-            }
-            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
+            t = self._alloc_tables(r, k)
+            out = self._c_tables(t)
             nbytes = self.lib.tvbf_exact_workspace_bytes(C.byref(cat.c), r)
             ws = self._workspace(nbytes)
             check(self.lib.tvbf_exact_rows(C.byref(cat.c), C.byref(p), rows_d.data_ptr(), r, C.byref(out),
@@ -604,16 +584,8 @@ class HybridTopKEngine:
         with torch.cuda.device(self.device):
             dev = self.device
             rows_d = torch.from_numpy(rows_np).to(dev)
-            t = {
-                "indices": torch.empty((r, k), dtype=torch.int32, device=dev),
-                "counts": torch.empty((r,), dtype=torch.int32, device=dev),
-                "hybrid": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "genre": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "text": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "metadata": torch.empty((r, k), dtype=torch.float64, device=dev),
-                "stats": torch.zeros((8,), dtype=torch.int32, device=dev),
-            }
-            out = TopKOut(**{name: ten.data_ptr() for name, ten in t.items()})
+            t = self._alloc_tables(r, k)
+            out = self._c_tables(t)
             nbytes = min(2 * self.sm_count, r) * n * 8 + 256
             ws = self._workspace(nbytes)
             check(self.lib.tvbf_matrix_rows_topk(hybrid.data_ptr(), genre.data_ptr(), text.data_ptr(),
