@@ -315,7 +315,7 @@ def main() -> None:
         stride = min(96, max(8, tiles // 4))
         if st_req:
             stride = 1 if st_req == 63 else (st_req if st_req <= 48 else 48 + (st_req - 48) * 8)
-        elif world >= 4:
+        elif world >= 2:
             stride = min(stride, 48)
         seed_tiles = 0 if stride <= 1 else (tiles + stride - 1) // stride
         exec_tiles = tiles * (tiles + 1) / 2 + tiles * seed_tiles

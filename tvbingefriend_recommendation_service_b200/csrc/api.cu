@@ -550,7 +550,7 @@ int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan&
   kp->sb_rank = rank;
   // a rank that sweeps 1/world of the tiles gets fewer threshold refreshes: seed more densely
   // (measured at world = 8 on C3: stride 48 -> 0.6 + 8.0 ms per rank, stride 96 -> 0.4 + 8.5 ms)
-  if (world >= 4 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
+  if (world >= 2 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
   return TVBF_OK;
 }
 
