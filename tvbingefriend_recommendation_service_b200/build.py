@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("TVBF_EXTRA_NVCC_FLAGS", "").split()   # experiments only (e.g. -DTVBF_MBAR_HINT_NS=1000)
 
 
 def _nvcc() -> str:
