@@ -144,20 +144,20 @@ class TopK:
     def to_dict(self, show_ids, id_key: str = "similar_show_id") -> dict:
         """``all_similarities`` exactly as the hot loop builds it (populate_database.py:208-221):
         shows without a qualifying neighbour are omitted."""
-        ids = list(show_ids)
+        ids = np.asarray(list(show_ids))
+        # bulk conversion to Python scalars first: 2 M records of C3 take 2.2 s this way, 3.0 s with
+        # per-element float()/int() calls (the dicts themselves are the rest)
+        sim = ids[np.where(self.indices >= 0, self.indices, 0)].tolist()
+        hyb, gen, txt, met = self.hybrid.tolist(), self.genre.tolist(), self.text.tolist(), self.metadata.tolist()
+        cnt = self.counts.tolist()
+        own = ids[self.row_begin:self.row_begin + len(cnt)].tolist()
         out = {}
-        idx, cnt = self.indices, self.counts
-        for r in range(idx.shape[0]):
-            c = int(cnt[r])
+        for r, c in enumerate(cnt):
             if c == 0:
                 continue
-            out[ids[self.row_begin + r]] = [
-                {id_key: ids[int(idx[r, e])],
-                 "similarity_score": float(self.hybrid[r, e]),
-                 "genre_score": float(self.genre[r, e]),
-                 "text_score": float(self.text[r, e]),
-                 "metadata_score": float(self.metadata[r, e])}
-                for e in range(c)]
+            sr, hr, gr, tr, mr = sim[r], hyb[r], gen[r], txt[r], met[r]
+            out[own[r]] = [{id_key: sr[e], "similarity_score": hr[e], "genre_score": gr[e], "text_score": tr[e],
+                            "metadata_score": mr[e]} for e in range(c)]
         return out
 
     def records(self, show_ids) -> dict:
