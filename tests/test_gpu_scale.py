@@ -75,6 +75,10 @@ def test_c3_100k_properties_and_sample(engine, tuning):
     assert np.array_equal(ex.indices, top.indices[rows]) and np.array_equal(ex.counts, top.counts[rows])
     m = ex.indices >= 0
     assert np.array_equal(ex.hybrid[m], top.hybrid[rows][m])
+    # few listed rows: each row's columns are split over ~29 CTAs that share one survivor list
+    few = rows[40:45]
+    ex5 = engine.exact_rows(dc, few, w, k=20, min_similarity=0.1)
+    assert np.array_equal(ex5.indices, top.indices[few]) and np.array_equal(ex5.hybrid, top.hybrid[few], equal_nan=True)
     assert 0 < top.flagged_rows < 20_000
 
 
