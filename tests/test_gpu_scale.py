@@ -118,9 +118,7 @@ def test_c5_200k_50k_vocab_top100_full_size(engine):
     got = engine.to_host(tabs[1])
     assert np.array_equal(one.indices, got.indices) and np.array_equal(one.hybrid, got.hybrid, equal_nan=True)
     del dc, tabs
-    import torch
-    engine._ws = None
-    torch.cuda.empty_cache()
+    engine.release()
 
 
 def test_c5_shape_top100_sweep_on_reduced_rows(engine):

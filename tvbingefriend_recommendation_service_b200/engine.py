@@ -173,7 +173,10 @@ class TopK:
 
 
 class HybridTopKEngine:
-    """One engine per process / GPU."""
+    """One engine per process / GPU.  It caches a device workspace and pinned host buffers, so it
+    must not be shared between threads that run jobs concurrently (the reference's callers are
+    single-threaded); create one engine per thread instead.  All work is
+    issued on the current torch CUDA stream of ``device``."""
 
     def __init__(self, device: int | str | torch.device | None = None, text_dtype: str = "fp16"):
         self.lib = _lib.load()
@@ -199,6 +202,15 @@ class HybridTopKEngine:
     # ------------------------------------------------------------------------------------ utils
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def release(self) -> None:
+        """Drop the cached device workspace and pinned host buffers (they are re-created on demand);
+        useful between jobs of very different size, e.g. after a 200 k x 50 k catalogue."""
+        self._ws = None
+        self._pinned.clear()
+        if torch.cuda.is_available():
+            with torch.cuda.device(self.device):
+                torch.cuda.empty_cache()
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
