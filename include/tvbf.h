@@ -252,6 +252,14 @@ int tvbf_score_pairs(const tvbf_features* f, const tvbf_params* p, const int32_t
                      int32_t n_pairs, double* out4, void* stream);
 
 /* ---- diagnostics ---------------------------------------------------------------------------- */
+/* host-only (no device): the work items of one K1 launch for a catalogue of col_tiles 256-column
+ * tiles and super_blocks 256-row super blocks dealt to `world` GPUs; out[6 * item + {0..5}] =
+ * {super block or -1, column split, tile0, tile1, real0, real1}: the item walks [tile0, tile1) for
+ * the producer pacing and computes [real0, real1).  Returns the number of items.  Used by the CPU
+ * tests to prove that every tile on/above the diagonal is computed exactly once. */
+int32_t tvbf_debug_schedule(int32_t col_tiles, int32_t super_blocks, int32_t sb_per_group, int32_t splits,
+                            int32_t world, int32_t rank, int32_t symmetric, int32_t* out,
+                            int32_t max_items);
 /* raw tensor-core tile dump: out[i, j] = sum_k operand[row0+i, k] * operand[col0+j, k] for a
  * 128 x 256 tile (fp32), used by the tests to validate descriptors and the error bound. */
 int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,

@@ -133,3 +133,51 @@ def test_gather_tables_world_size_2_gloo(n):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---- K1 work decomposition (host copy of the kernel's item -> tiles map; no GPU needed) -----------
+def _schedule(col_tiles, super_blocks, sb_per_group, splits, world, rank, symmetric):
+    import ctypes as C
+
+    from tvbingefriend_recommendation_service_b200 import _lib
+
+    lib = _lib.load()
+    cap = 1 << 16
+    out = (C.c_int32 * (6 * cap))()
+    n = lib.tvbf_debug_schedule(col_tiles, super_blocks, sb_per_group, splits, world, rank, int(symmetric), out, cap)
+    assert 0 <= n <= cap
+    return np.frombuffer(out, dtype=np.int32, count=6 * n).reshape(n, 6).copy()
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 7, 40, 79, 160, 391])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("splits,per_group", [(1, 74), (4, 18), (8, 9), (12, 6), (3, 5)])
+def test_symmetric_schedule_covers_the_upper_triangle_exactly_once(tiles, world, splits, per_group):
+    seen = np.zeros((tiles, tiles), dtype=np.int32)
+    for rank in range(world):
+        items = _schedule(tiles, tiles, per_group, splits, world, rank, True)
+        # every item of a group walks equally many tiles (the producers pace one another)
+        walk = items[:, 3] - items[:, 2]
+        groups = walk.reshape(-1, per_group * splits)
+        assert (groups == groups[:, :1]).all()
+        for sb, _split, _t0, _t1, r0, r1 in items:
+            if sb < 0:
+                assert r0 == r1
+                continue
+            assert 0 <= sb < tiles and sb % world in (rank, world - 1 - rank)
+            if r0 == r1:          # this split of the group lies left of the block's diagonal tile
+                continue
+            assert sb <= r0 < r1 <= tiles
+            seen[sb, r0:r1] += 1
+    assert np.array_equal(seen, np.triu(np.ones((tiles, tiles), dtype=np.int32)))
+
+
+@pytest.mark.parametrize("tiles,blocks", [(1, 1), (5, 3), (79, 79), (391, 49)])
+@pytest.mark.parametrize("splits,per_group", [(1, 74), (4, 18), (8, 9)])
+def test_one_sided_schedule_covers_every_tile_of_the_row_shard_once(tiles, blocks, splits, per_group):
+    items = _schedule(tiles, blocks, per_group, splits, 1, 0, False)
+    seen = np.zeros((blocks, tiles), dtype=np.int32)
+    for sb, _split, _t0, _t1, r0, r1 in items:
+        if sb >= 0:
+            seen[sb, r0:r1] += 1
+    assert (seen == 1).all()

@@ -833,6 +833,27 @@ static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float*
   return tvbf::k1_launch_dump(f, kp, cg, static_cast<cudaStream_t>(stream));
 }
 
+// host-only: the work items of one K1 launch (no device needed)
+int32_t tvbf_debug_schedule(int32_t col_tiles, int32_t super_blocks, int32_t sb_per_group, int32_t splits,
+                            int32_t world, int32_t rank, int32_t symmetric, int32_t* out, int32_t max_items) {
+  if (col_tiles < 1 || super_blocks < 0 || sb_per_group < 1 || splits < 1 || world < 1 || rank < 0 ||
+      rank >= world || out == nullptr || max_items < 0) {
+    tvbf_set_error("tvbf_debug_schedule: bad arguments");
+    return TVBF_ERR_INVALID;
+  }
+  tvbf::K1Params kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.col_tiles = col_tiles;
+  kp.splits = splits;
+  kp.rb_count = tvbf::k1_local_super_blocks(super_blocks, world, rank);
+  kp.rb_per_group = sb_per_group;
+  kp.tiles_per_split = (col_tiles + splits - 1) / splits;
+  kp.sb_world = world;
+  kp.sb_rank = rank;
+  kp.sym = symmetric ? 1 : 0;
+  return tvbf::k1_debug_schedule(kp, out, max_items);
+}
+
 int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,
                          void* stream) {
   return debug_tile(f, row0, col0, out, 1, stream);

@@ -154,7 +154,7 @@ __host__ __device__ __forceinline__ int global_super_block(int local, int world,
   return local * world + ((local & 1) ? (world - 1 - rank) : rank);
 }
 
-__device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
+__host__ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
   const int per_group = p.rb_per_group * p.splits;
   const int g = item / per_group;
   const int w = item - g * per_group;
@@ -940,6 +940,18 @@ int k1_local_super_blocks(int total_super_blocks, int world, int rank) {
   int n = 0;
   while (global_super_block(n, world, rank) < total_super_blocks) ++n;
   return n;
+}
+
+// Host copy of the kernel's work decomposition (tests check coverage without a GPU): item i ->
+// {super block, split, tile0, tile1, real0, real1}; returns the number of items.
+int k1_debug_schedule(const K1Params& p, int* out, int max_items) {
+  const int n_items = ((p.rb_count + p.rb_per_group - 1) / p.rb_per_group) * p.rb_per_group * p.splits;
+  for (int item = 0; item < n_items && item < max_items; ++item) {
+    const ItemCoord c = item_coord(p, item);
+    int* o = out + 6 * item;
+    o[0] = c.sb; o[1] = c.split; o[2] = c.tile0; o[3] = c.tile1; o[4] = c.real0; o[5] = c.real1;
+  }
+  return n_items;
 }
 
 int k1_entries_per_lane(int k) {
