@@ -190,3 +190,41 @@ class TestComparator:
         ref = _mk([1, 2, 3], [0.9, 0.8, 0.8], 3)
         got = _mk([1, 3, 2], [0.9, 0.8, 0.8], 3)  # equal scores must be index-ascending
         assert not compare_topk(*ref, *got, self.ps, 3, 0.1).ok
+
+
+# ---- property test: hoisted oracle == verbatim loop on random (tie-heavy) inputs --------------------
+def test_hoisted_rows_equal_the_verbatim_loop_on_random_inputs():
+    """ProductionRows (normalisations hoisted; what the GPU parity tests use at scale) against the
+    verbatim loop on small random catalogues with many exact ties, empty rows and float features.
+    Both sort with the same unstable argsort, so only scores and tie-insensitive facts are compared
+    bit-for-bit: counts, score vectors, and the index sets above the cut."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    for trial in range(30):
+        n = int(rng.integers(2, 40))
+        g_dim, v = int(rng.integers(1, 6)), int(rng.integers(1, 12))
+        genre = (rng.random((n, g_dim)) < 0.5).astype(np.int64)
+        text = sp.csr_matrix(np.where(rng.random((n, v)) < 0.3, rng.integers(1, 3, (n, v)), 0).astype(np.float64))
+        onehot = lambda c: np.eye(c)[rng.integers(0, c, n)]   # noqa: E731
+        f = {"genre_features": genre if trial % 3 else rng.random((n, g_dim)),
+             "text_features": text, "platform_features": onehot(3),
+             "type_features": onehot(2).astype(bool), "language_features": onehot(2)}
+        if trial % 4 == 0:
+            f["genre_features"][0] = 0
+        w = tuple(float(x) for x in rng.choice([0.0, 0.1, 0.4, 0.5, 1.0, 2.0], 3))
+        if sum(w) == 0:
+            w = (0.4, 0.5, 0.1)
+        k, ms = int(rng.integers(1, 8)), float(rng.choice([0.0, 0.1, 0.5]))
+        ids = list(range(100, 100 + n))
+        ref = production_loop(f, ids, *w, top_n_per_show=k, min_similarity=ms)
+        ridx, rcnt, rsc = dict_to_arrays(ref, ids, k)
+        pr = ProductionRows(f, *w)
+        idx, cnt, sc = pr.topk_arrays(range(n), k, ms)
+        assert np.array_equal(cnt, rcnt), trial
+        assert np.allclose(np.nan_to_num(sc), np.nan_to_num(rsc), rtol=0, atol=1e-15), trial
+        for i in range(n):   # members strictly above the row's last kept score are the same set
+            c = int(cnt[i])
+            if c:
+                cut = rsc[0][i, c - 1]
+                assert set(idx[i, :c][sc[0][i, :c] > cut]) == set(ridx[i, :c][rsc[0][i, :c] > cut]), (trial, i)
