@@ -1036,6 +1036,10 @@ int k6_launch(const ScoreParams& sp, const int* rows, int n_listed, const int* c
     return TVBF_OK;
   }
   const size_t smem = mask_bytes + static_cast<size_t>(K6B_SMALL) * 12;
+  if (k6_cap_rows(grid) > 8192) {   // counters and tickets: two int arrays of 8192 in K6T_COUNTER_BYTES
+    tvbf_set_error("exact rows: grid of %d CTAs exceeds the counter area", grid);
+    return TVBF_ERR_INVALID;
+  }
   if (smem <= 160 * 1024) {
     TVBF_CUDA_OK(cudaFuncSetAttribute(exact_rows_text_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
