@@ -16,7 +16,8 @@
  *   - every function returns TVBF_OK (0) or a negative TVBF_ERR_* code; tvbf_last_error()
  *     returns a thread-local message for the last failure; no exception crosses the boundary;
  *   - functions enqueue work on `stream` and return without synchronising unless stated;
- *   - thread-compatible: no global mutable state besides the thread-local last error.
+ *   - thread-compatible: no global mutable state besides the thread-local last error and a
+ *     launch counter (tvbf_kernel_launches).
  */
 #ifndef TVBF_H_
 #define TVBF_H_
@@ -102,7 +103,9 @@ typedef struct tvbf_params {
                           /* 255 = off); bits 12-15: pacing slack in chunks (default 2);        */
                           /* bits 16-19: smem ring stages; bits 20-21: symmetric mode (0 auto,  */
                           /* 1 off, 2 on: compute only tiles on/above the diagonal and feed     */
-                          /* both shows of every score); bit 30: non-cooperative launch         */
+                          /* both shows of every score); bits 22-27: column-tile stride of the  */
+                          /* symmetric sweep's threshold seed pass (0 auto, 1..48 as given,     */
+                          /* 49..62 -> 48 + 8 per step, 63 none); bit 30: non-cooperative launch */
 } tvbf_params;
 
 /* Result table of the shard rows [row_begin, row_end): the a9 record stream of
