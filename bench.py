@@ -42,7 +42,8 @@ def _peaks() -> dict:
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML every 10 ms from a thread
+    (the timed region of a default run lasts ~0.3 s), ``nvidia-smi -lms 100`` if NVML is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -50,8 +51,49 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.lines, self.proc = index, [], None
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), "nvidia-smi"
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:      # the CUDA ordinal need not be the NVML index (CUDA_VISIBLE_DEVICES): go by UUID
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)     # probe
+        return pynvml, handle
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        flags = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in flags.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"],
@@ -65,6 +107,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None, "samples": len(self.sm),
+                    "reasons": sorted(self.reasons), "source": "nvml, 10 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -84,7 +132,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_baseline(cat, cfg, weights, budget_s: float = 20.0, use_sklearn: bool = True) -> dict:
