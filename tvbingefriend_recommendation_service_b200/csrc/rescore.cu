@@ -594,6 +594,46 @@ __device__ __forceinline__ void batch_rows_load(BatchRows<MAXB>& br, int slot, i
   }
 }
 
+// Exact top-k of one batch row from what the scoring pass left behind: its survivor list (columns
+// that reach the row's floor) when that holds everything, else dense keys over all N columns.
+// kCg: the lists were written by other CTAs of this launch (column-split text kernel).
+template <bool kCg>
+__device__ void k6_select_row(SelectSmem& sm, const ScoreParams& sp, const FeatureScorer& scorer, int i,
+                              double floor_i, int survivors, const unsigned long long* surv_key_r,
+                              const int* surv_j_r, unsigned long long* keys_r, bool dense_written,
+                              unsigned long long* small_key, int* small_j, size_t orow,
+                              const tvbf_topk_out& out) {
+  const int tid = threadIdx.x;
+  const int n = sp.f.n_shows;
+  if (survivors <= K6B_SMALL) {
+    // few survivors: select from their list, staged in shared memory (instead of ~10 passes over
+    // N keys)
+    __syncthreads();
+    for (int e = tid; e < survivors; e += K6B_THREADS) {
+      small_key[e] = __ldcg(surv_key_r + e);
+      small_j[e] = __ldcg(surv_j_r + e);
+    }
+    __syncthreads();
+    select_and_emit<false, false>(sm, small_key, small_j, survivors, sp.k, survivors, i, orow, scorer, out);
+  } else if (survivors <= K6B_LIST) {
+    // a wide tie plateau: select over the survivor list where it lies (L2), not over N keys
+    select_and_emit<false, kCg>(sm, surv_key_r, surv_j_r, survivors, sp.k, survivors, i, orow, scorer, out);
+  } else {
+    if (!dense_written) {
+      // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
+      __syncthreads();
+      for (int j = tid; j < n; j += K6B_THREADS) {
+        const Scores sc = scorer(i, j);
+        const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_i) && !(sp.exclude_self && j == i);
+        keys_r[j] = ok ? f64_orderable(sc.h) : 0ull;
+      }
+      __threadfence();
+      __syncthreads();
+    }
+    select_and_emit<true, kCg>(sm, keys_r, nullptr, n, sp.k, survivors, i, orow, scorer, out);
+  }
+}
+
 // rows / floors hold `listed` entries at [0, listed), or at [list_cap - listed, list_cap) when
 // list_cap > 0 (K5 lists the shows without text from the back).
 __global__ void __launch_bounds__(K6B_THREADS, 1)
@@ -677,39 +717,9 @@ exact_rows_notext_kernel(const ScoreParams sp, const int* __restrict__ rows, int
     for (int r = 0; r < nb; ++r) {
       const int t = list0 + batch * B + r;
       const int orow = rows_are_local ? rows[t] : t;
-      const unsigned long long* keys_r = keys0 + static_cast<size_t>(r) * n;
-      const int survivors = s_valid[r];
-      if (survivors <= K6B_SMALL) {
-        // few survivors: select from their list, staged in shared memory (instead of ~10 passes
-        // over N keys)
-        __syncthreads();
-        for (int e = tid; e < survivors; e += K6B_THREADS) {
-          small_key[e] = __ldcg(surv_key + r * K6B_LIST + e);
-          small_j[e] = __ldcg(surv_j + r * K6B_LIST + e);
-        }
-        __syncthreads();
-        select_and_emit<false, false>(sm, small_key, small_j, survivors, sp.k, survivors, br.row[r],
-                                      static_cast<size_t>(orow), scorer, out);
-      } else if (survivors <= K6B_LIST) {
-        // a wide tie plateau: select over the survivor list where it lies (L2), not over N keys
-        select_and_emit<false, false>(sm, surv_key + r * K6B_LIST, surv_j + r * K6B_LIST, survivors, sp.k,
-                                      survivors, br.row[r], static_cast<size_t>(orow), scorer, out);
-      } else {
-        if (!dense) {
-          // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
-          const int i = br.row[r];
-          const double floor_r = br.floor[r];
-          __syncthreads();
-          for (int j = tid; j < n; j += K6B_THREADS) {
-            const Scores sc = scorer(i, j);
-            const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_r) && !(sp.exclude_self && j == i);
-            keys0[static_cast<size_t>(r) * n + j] = ok ? f64_orderable(sc.h) : 0ull;
-          }
-          __syncthreads();
-        }
-        select_and_emit<true, false>(sm, keys_r, nullptr, n, sp.k, survivors, br.row[r],
-                                     static_cast<size_t>(orow), scorer, out);
-      }
+      k6_select_row<false>(sm, sp, scorer, br.row[r], br.floor[r], s_valid[r], surv_key + r * K6B_LIST,
+                           surv_j + r * K6B_LIST, keys0 + static_cast<size_t>(r) * n, dense, small_key, small_j,
+                           static_cast<size_t>(orow), out);
     }
   }
 }
@@ -927,37 +937,9 @@ exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n
       const int t = list0 + batch * B + r;
       const int orow = rows_are_local ? rows[t] : t;
       const size_t slot = static_cast<size_t>(slot0 + r);
-      unsigned long long* keys_r = dense_keys + slot * n;
-      const int survivors = __ldcg(cnt + slot);
-      if (survivors <= K6B_SMALL) {
-        __syncthreads();
-        for (int e = tid; e < survivors; e += K6B_THREADS) {
-          small_key[e] = __ldcg(surv_key + slot * K6B_LIST + e);
-          small_j[e] = __ldcg(surv_j + slot * K6B_LIST + e);
-        }
-        __syncthreads();
-        select_and_emit<false, false>(sm, small_key, small_j, survivors, sp.k, survivors, br.row[r],
-                                      static_cast<size_t>(orow), scorer, out);
-      } else if (survivors <= K6B_LIST) {
-        select_and_emit<false, true>(sm, surv_key + slot * K6B_LIST, surv_j + slot * K6B_LIST, survivors, sp.k,
-                                     survivors, br.row[r], static_cast<size_t>(orow), scorer, out);
-      } else {
-        if (!dense) {
-          // rare: a floor that more than K6B_LIST columns reach; the dense keys were not written
-          const int i = br.row[r];
-          const double floor_r = br.floor[r];
-          __syncthreads();
-          for (int j = tid; j < n; j += K6B_THREADS) {
-            const Scores sc = scorer(i, j);
-            const bool ok = (sc.h >= sp.min_similarity) && (sc.h >= floor_r) && !(sp.exclude_self && j == i);
-            keys_r[j] = ok ? f64_orderable(sc.h) : 0ull;
-          }
-          __threadfence();
-          __syncthreads();
-        }
-        select_and_emit<true, true>(sm, keys_r, nullptr, n, sp.k, survivors, br.row[r],
-                                    static_cast<size_t>(orow), scorer, out);
-      }
+      k6_select_row<true>(sm, sp, scorer, br.row[r], br.floor[r], __ldcg(cnt + slot), surv_key + slot * K6B_LIST,
+                          surv_j + slot * K6B_LIST, dense_keys + slot * n, dense, small_key, small_j,
+                          static_cast<size_t>(orow), out);
     }
   }
 }
