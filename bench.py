@@ -135,7 +135,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
-def cpu_baseline(cat, cfg, weights, budget_s: float = 20.0, use_sklearn: bool = True) -> dict:
+def cpu_baseline(cat, cfg, weights, budget_s: float = 20.0, use_sklearn: bool = True, min_rows: int = 256) -> dict:
     """The reference's production loop (scripts/populate_database.py:170-218) on a bounded,
     evenly spaced row sample of the same catalogue, on this box's host cores."""
     from oracle.reference_paths import production_loop
@@ -161,7 +161,8 @@ def cpu_baseline(cat, cfg, weights, budget_s: float = 20.0, use_sklearn: bool = 
     t0 = time.perf_counter()
     production_loop(feats, ids, *weights, top_n_per_show=cfg["k"], min_similarity=0.1, rows=[0, n // 2], **kw)
     per_row = (time.perf_counter() - t0) / 2
-    rows = int(max(4, min(n, budget_s / max(per_row, 1e-6))))
+    # at least 256 sampled rows (capped at 40 s of CPU work)
+    rows = int(max(4, min(n, max(budget_s, min(40.0, min_rows * per_row)) / max(per_row, 1e-6))))
     sample = np.linspace(0, n - 1, rows).astype(np.int64).tolist()
     t0 = time.perf_counter()
     production_loop(feats, ids, *weights, top_n_per_show=cfg["k"], min_similarity=0.1, rows=sample, **kw)
@@ -186,7 +187,7 @@ def run_reference(args, cfg, cat, weights) -> dict:
     res = None
     vals = []
     for i in range(warm + steps):
-        res = cpu_baseline(cat, cfg, weights, budget_s=per_step_budget)
+        res = cpu_baseline(cat, cfg, weights, budget_s=per_step_budget, min_rows=0)
         if i >= warm:
             vals.append(res["value"])
     v = float(np.mean(vals))
@@ -197,6 +198,65 @@ def run_reference(args, cfg, cat, weights) -> dict:
             "config": bench_config(args, cfg), "cpu_baseline": res,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+
+
+def parity_check(eng, cat, cfg, weights, table, single=None, rows: int = 96) -> dict:
+    """Correctness of the table this run produced, carried in the JSON line: an evenly spaced sample
+    of source rows against the CPU oracle (float64 restatement of the production loop; the oracle is
+    the checker here, nothing it computes is timed or reported as the product's), and -- when the
+    job ran on several GPUs -- exact equality with the single-GPU table computed by rank 0."""
+    from oracle.compare import compare_topk
+    from oracle.reference_paths import ProductionRows
+
+    n, k = cat.n_shows, cfg["k"]
+    pr = ProductionRows(cat.features(), *weights)
+    sample = np.unique(np.linspace(0, n - 1, rows).astype(np.int64))
+    ridx, rcnt, rsc = pr.topk_arrays(sample, k, 0.1)
+    rep = compare_topk(ridx, rcnt, rsc[0], table.indices[sample], table.counts[sample], table.hybrid[sample],
+                       lambda r, js: pr.pair_scores(int(sample[r]), js), k, 0.1)
+    out = {"rows": int(len(sample)), "identical": int(rep.rows_identical_ordered),
+           "tie_permuted": int(rep.rows_tie_permuted), "failures": int(len(rep.failures)), "ok": bool(rep.ok),
+           "max_rel_score_err": float(rep.max_rel_score_err),
+           "checker": "oracle.reference_paths.ProductionRows + tie-aware comparator (eps 1e-9)"}
+    if single is not None:
+        m = single.indices >= 0
+        same = (np.array_equal(single.indices, table.indices) and np.array_equal(single.counts, table.counts)
+                and np.array_equal(single.hybrid[m], table.hybrid[m]))
+        out["identical_to_single_gpu"] = bool(same)
+        out["ok"] = bool(out["ok"] and same)
+    return out
+
+
+def dense_text_probe(eng, dc, weights, k, tuning, steps: int = 3) -> dict:
+    """K1 on a dense-random operand of the same shape (SURVEY.md section 8d's pure-GEMM variant): the
+    synthetic TF-IDF operand is 99.5 % zeros, which keeps the tensor pipe's switching power -- and so
+    the power-capped clock -- far from what a dense GEMM sees.  Only the candidate kernel runs (the
+    random operand has no CSR behind it, so nothing is rescored or reported from it)."""
+    import torch
+
+    operand = dc.keep[3]
+    saved = operand.clone()
+    g = torch.Generator(device=operand.device)
+    g.manual_seed(1234)
+    operand.copy_(torch.rand(operand.shape, device=operand.device, dtype=torch.float32, generator=g).to(operand.dtype))
+    sampler = ClockSampler(operand.device.index or 0)
+    times = []
+    try:
+        eng.top_k_device(dc, weights, k, 0.1, True, phases=1, tuning=tuning)     # warm-up
+        torch.cuda.synchronize()
+        sampler.start()
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.top_k_device(dc, weights, k, 0.1, True, phases=1, tuning=tuning)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+    finally:
+        clocks = sampler.stop()
+        operand.copy_(saved)
+    return {"k1_ms": float(np.mean(times)), "clocks": clocks,
+            "operand": "U(0,1) fp16 in every entry (dense), same [N_pad, K_pad] shape"}
 
 
 def bench_config(args, cfg) -> dict:
@@ -220,6 +280,8 @@ def main() -> None:
     ap.add_argument("--n-shows", type=int, default=None, help="override N (debug)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-dense-probe", action="store_true")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--one-sided", action="store_true", help="disable the symmetric sweep at N > 1")
     ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
@@ -346,6 +408,16 @@ def main() -> None:
     if host_table is not None:
         d2h = sum(getattr(host_table, f).nbytes for f in ("indices", "counts", "hybrid", "genre", "text", "metadata"))
 
+    final_table = single_table = None
+    if rank == 0 and not args.no_parity_check:
+        from tvbingefriend_recommendation_service_b200.engine import TopK
+
+        final_table = TopK(**{f: getattr(host_table, f).copy() for f in
+                              ("indices", "counts", "hybrid", "genre", "text", "metadata")})
+        if world > 1:     # the same job on this GPU alone, for exact comparison with the gathered table
+            single_table = eng.to_host(eng.top_k_device(eng.prepare(raw, weights), weights, k, 0.1, True))
+    if world > 1:
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -354,22 +426,18 @@ def main() -> None:
     # algorithmic work of this GPU's share of the text contraction, counted as the reference
     # computes it (all N x N pairs); the symmetric sweep executes about half of it
     flops = 2.0 * n * n * cfg["vocab"] / world
-    tiles = (n + 255) // 256
+    dc_plan = eng.prepare(raw, weights)
     sym_forced_off = ((args.tuning >> 20) & 3) == 1 or args.one_sided
-    used_sym = (not sym_forced_off) and tiles >= 160 and eng.sym_eligible(eng.prepare(raw, weights), weights, k, 0.1)
-    k_pad = (cfg["vocab"] + 63) // 64 * 64
-    if used_sym:   # tiles on/above the diagonal + the sampled threshold-seed pass (api.cu: fill_k1_params)
-        st_req = (args.tuning >> 22) & 0x3F
-        stride = min(96, max(8, tiles // 4))
-        if st_req:
-            stride = 1 if st_req == 63 else (st_req if st_req <= 48 else 48 + (st_req - 48) * 8)
-        elif world >= 2:
-            stride = min(stride, 48)
-        seed_tiles = 0 if stride <= 1 else (tiles + stride - 1) // stride
-        exec_tiles = tiles * (tiles + 1) / 2 + tiles * seed_tiles
+    if world > 1:
+        sharded_sym = (not sym_forced_off) and n >= 40_000 and eng.sym_eligible(dc_plan, weights, k, 0.1)
+        plan = eng.plan_tiles(dc_plan, weights, k, 0.1, rank=0, world=world, tile_sharded=True, splits=args.splits,
+                              tuning=args.tuning) if sharded_sym else \
+            eng.plan_tiles(dc_plan, weights, k, 0.1, row_begin=rb, row_end=re_, splits=args.splits,
+                           tuning=args.tuning | (1 << 20))
     else:
-        exec_tiles = tiles * tiles
-    exec_flops = 2.0 * exec_tiles * 256 * 256 * k_pad / world
+        plan = eng.plan_tiles(dc_plan, weights, k, 0.1, splits=args.splits, tuning=args.tuning)
+    used_sym = plan["symmetric"]
+    exec_flops = plan["flops"]      # this GPU's tiles (seed pass + sweep) x tile rows x 256 x K_pad x 2
     traffic = None
     try:   # DRAM bytes per K1 launch from the committed ncu capture of this configuration
         tj = json.loads((ROOT / "profiles" / "k1_traffic.json").read_text())
@@ -377,30 +445,50 @@ def main() -> None:
             traffic = tj[args.config]["symmetric" if used_sym else "one_sided"]["bytes"]
     except Exception:
         traffic = None
-    achieved = flops / (k1_ms_mean * 1e-3) / 1e12 if k1_ms_mean > 0 else 0.0
+    traffic_src = None
+    try:
+        traffic_src = tj[args.config]["symmetric" if used_sym else "one_sided"].get("source")
+    except Exception:
+        pass
+    secs = k1_ms_mean * 1e-3
+    alg_tflops = flops / secs / 1e12 if secs > 0 else 0.0
+    exec_tflops = exec_flops / secs / 1e12 if secs > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": exec_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": exec_tflops / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "hybrid_topk_kernel (K1: threshold seed pass + sweep)", "kernel_ms": k1_ms_mean,
+                "flops_per_launch": exec_flops, "peak_kind": f"bf16 sustained, {peaks['source']}",
+                "peak_burst": peaks["bf16_tflops"], "frac_of_burst": exec_tflops / peaks["bf16_tflops"],
+                "symmetric_sweep": bool(used_sym), "seed_tiles": plan["seed_tiles"], "sweep_tiles": plan["sweep_tiles"],
+                "tile": f"{plan['tile_rows']}x256x{int(dc_plan.c.k_pad)}",
+                "algorithmic_flops_per_launch": flops, "algorithmic_tflops": alg_tflops,
+                "frac_algorithmic": alg_tflops / peak if peak else None,
+                "note": "achieved / frac count the flops the tensor pipe EXECUTES (256x256xK_pad tiles "
+                        "launched, seed pass included); algorithmic_* count the reference's full 2*N*N*V "
+                        "all-pairs contraction, of which the symmetric sweep needs about half.  The sparse "
+                        "synthetic operand keeps the SM clock above what a dense GEMM holds under the power "
+                        "cap: see dense_text for the same kernel on a dense-random operand"}
     line = {
         "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05) candidate pass, f64 for every reported score",
         "data": "synthetic", "config": bench_config(args, cfg),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "kernel": "hybrid_topk_kernel (K1: threshold seed pass + sweep)", "kernel_ms": k1_ms_mean,
-                     "flops_per_launch": flops, "peak_kind": f"bf16 sustained, {peaks['source']}",
-                     "peak_burst": peaks["bf16_tflops"], "frac_of_burst": achieved / peaks["bf16_tflops"],
-                     "symmetric_sweep": bool(used_sym), "executed_flops_per_launch": exec_flops,
-                     "executed_tflops": exec_flops / (k1_ms_mean * 1e-3) / 1e12 if k1_ms_mean > 0 else 0.0,
-                     "frac_executed": (exec_flops / (k1_ms_mean * 1e-3) / 1e12 / peak) if k1_ms_mean > 0 else None,
-                     "note": "achieved counts the algorithmic 2*N*N*V of the reference's all-pairs "
-                             "contraction; hybrid(i,j)==hybrid(j,i) lets the symmetric sweep execute "
-                             "about half of it (executed_* fields)"},
+        "roofline": roofline,
         "e2e": {"value": n / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": st.h2d_bytes(),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_per_step},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "flagged_rows": flagged, "rescored_pairs": pairs,
     }
+    if not args.no_dense_probe and world == 1:
+        dc = eng.prepare(raw, weights)
+        probe = dense_text_probe(eng, dc, weights, k, args.tuning)
+        psecs = probe["k1_ms"] * 1e-3
+        probe["executed_tflops"] = exec_flops / psecs / 1e12
+        probe["frac"] = probe["executed_tflops"] / peak
+        line["dense_text"] = probe
+    if not args.no_parity_check:
+        line["parity_check"] = parity_check(eng, cat, cfg, weights, final_table, single_table)
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(cat, cfg, weights, budget_s=20.0)
     print(json.dumps(line), flush=True)

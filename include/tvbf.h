@@ -78,6 +78,9 @@ typedef struct tvbf_features {
   const void* col_side;      /* [n_pad] 16-byte records {u64 genre bits, f32 1/sqrt(popc),    */
                              /*  u32 one-hot bits platform | type<<P | language<<(P+T)}       */
   const float* meta_scale;   /* [n_pad] MEAN3: 1/sqrt(3) ; HSTACK: 1/sqrt(#categories) or 0   */
+  int32_t text_signed;       /* 1: text values may be negative (embeddings, SVD): the candidate   */
+                             /* pass then bounds the fp16 error absolutely instead of relative to */
+                             /* the accumulator (cancellation); 0 for TF-IDF                      */
 } tvbf_features;
 
 /* Parameters of one top-K job: populate_database.py:85-91 (weights, top_n_per_show,
@@ -126,6 +129,9 @@ int tvbf_version(void);
 const char* tvbf_last_error(void);
 /* cumulative number of CUDA kernels this library has launched in this process */
 uint64_t tvbf_kernel_launches(void);
+/* K1 launches that the runtime refused as cooperative (a profiler patched the kernel) and that
+ * were retried as plain launches; 0 in normal operation */
+uint64_t tvbf_noncooperative_fallbacks(void);
 /* sm count and compute capability of the current device; TVBF_ERR_UNSUPPORTED unless 10.x */
 int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 
@@ -263,6 +269,18 @@ int tvbf_score_pairs(const tvbf_features* f, const tvbf_params* p, const int32_t
 int32_t tvbf_debug_schedule(int32_t col_tiles, int32_t super_blocks, int32_t sb_per_group, int32_t splits,
                             int32_t world, int32_t rank, int32_t symmetric, int32_t* out,
                             int32_t max_items);
+/* host-only: tensor-core tiles the candidate pass of this job executes -- out4 = {tiles of the
+ * threshold seed pass, tiles of the main sweep, rows per tile (128 or 256; columns are 256 and the
+ * depth is k_pad), 1 if the symmetric sweep is used}.  tile_sharded = 0: the job as tvbf_hybrid_topk
+ * runs it for rows [row_begin, row_end) of p; 1: as tvbf_sym_seed + tvbf_sym_sweep run it on GPU
+ * `rank` of `world`.  bench.py derives the executed FLOPs of its roofline line from this. */
+int tvbf_plan_tiles(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                    int32_t tile_sharded, int64_t* out4);
+/* host-only: the constants of the candidate pass' upper bound for this job.  For a pair whose
+ * source row has T non-zero operand entries and whose raw accumulator is a,
+ *   U = wg*g + wm*m + out5[0]*a + (out5[1] + T*out5[2])*|a| + out5[3] + T*out5[4]  >=  exact hybrid
+ * (api.cu: make_slack).  The tests check this inequality against float64. */
+int tvbf_debug_slack(const tvbf_features* f, const tvbf_params* p, float* out5);
 /* raw tensor-core tile dump: out[i, j] = sum_k operand[row0+i, k] * operand[col0+j, k] for a
  * 128 x 256 tile (fp32), used by the tests to validate descriptors and the error bound. */
 int tvbf_debug_gemm_tile(const tvbf_features* f, int32_t row0, int32_t col0, float* out,

@@ -58,9 +58,23 @@ def _populate_case(name: str, cat: Catalogue, cases: list[dict]) -> None:
     np.savez_compressed(GOLDEN / f"{name}.npz", **out)
 
 
+def make_c1() -> None:
+    """BASELINE.json configs[0]: 1 000 shows x 5 000 vocab through the UNMODIFIED production loop,
+    all rows, reference defaults (top-20, min_similarity 0.1, weights 0.4/0.5/0.1)."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+    _populate_case("populate_c1", make_config("C1"), [{}])
+
+
 def main() -> None:
     logging.disable(logging.CRITICAL)
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    import sys
+
+    if "--only-c1" in sys.argv:
+        make_c1()
+        return
+    make_c1()
 
     # (1) production loop (variant B) on a synthetic catalogue
     cat = make_catalogue(300, 2000, nnz=30, n_genres=40, meta=(5, 3, 2), seed=7)

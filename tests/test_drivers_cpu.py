@@ -74,3 +74,101 @@ def test_similarity_computer_keeps_the_reference_constructor():
     assert (c.genre_weight, c.text_weight, c.metadata_weight) == (0.4, 0.5, 0.1)      # reference :15-28
     c = SimilarityComputer(genre_weight=2.0, text_weight=3.0, metadata_weight=1.0)
     assert (c.genre_weight, c.text_weight, c.metadata_weight) == (2.0, 3.0, 1.0)
+
+
+# ---- storage half of the populate driver (no GPU: the table is made by hand) ---------------------
+class _FakeRepository:
+    """Shaped like SimilarityRepository (repos/similarity_repository.py:72-124): no ``records``
+    attribute, only the two methods the drivers call."""
+
+    def __init__(self):
+        self.calls = []
+        self.rows = {}
+
+    def bulk_store_all_similarities(self, all_similarities, batch_size=1000, clear_existing=True):
+        self.calls.append((len(all_similarities), clear_existing))
+        if clear_existing:
+            self.rows = {}
+        n = 0
+        for sid, recs in all_similarities.items():
+            self.rows[sid] = recs
+            n += len(recs)
+        return n
+
+    def get_similarity_stats(self):
+        total = sum(len(v) for v in self.rows.values())
+        return {"total_records": total, "unique_shows": len(self.rows),
+                "avg_similarities_per_show": total / max(len(self.rows), 1), "last_computed": None}
+
+
+def _hand_table(n=12001, k=3):
+    from tvbingefriend_recommendation_service_b200.engine import TopK
+
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, n, size=(n, k)).astype(np.int32)
+    cnt = rng.integers(0, k + 1, size=n).astype(np.int32)
+    cnt[5] = 0
+    idx[np.arange(k)[None, :] >= cnt[:, None]] = -1
+    sc = [rng.random((n, k)) for _ in range(4)]
+    return TopK(idx, cnt, *sc), np.arange(100, 100 + 3 * n, 3)
+
+
+def test_store_batches_clears_first_even_for_a_real_repository_shape():
+    """reference populate_database.py:156-162 deletes everything up front, then appends per 5000
+    shows (:223-234) -- also when the sink is a repository without a ``records`` attribute."""
+    from tvbingefriend_recommendation_service_b200.scripts.populate_database import store_similarity_batches
+
+    top, ids = _hand_table()
+    repo = _FakeRepository()
+    repo.rows = {-1: [{"stale": True}]}
+    total = store_similarity_batches(top, ids, repo)
+    assert repo.calls[0] == (0, True) and all(c[1] is False for c in repo.calls[1:])
+    assert len(repo.calls) == 1 + 3                     # 12001 shows -> batches of 5000, 5000, 2001
+    assert -1 not in repo.rows and total == int(top.counts.sum())
+    assert ids[5] not in repo.rows                      # shows without a neighbour are omitted (:220-221)
+    r = 7 if top.counts[7] else int(np.nonzero(top.counts)[0][0])
+    rec = repo.rows[ids[r]][0]
+    assert set(rec) == {"similar_show_id", "similarity_score", "genre_score", "text_score", "metadata_score"}
+    assert rec["similar_show_id"] == ids[top.indices[r, 0]] and rec["similarity_score"] == top.hybrid[r, 0]
+
+
+def test_columnar_sink_receives_the_same_record_stream():
+    from tvbingefriend_recommendation_service_b200.scripts.populate_database import store_similarity_batches
+    from tvbingefriend_recommendation_service_b200.sinks import ColumnarSimilaritySink, InMemorySimilaritySink
+
+    top, ids = _hand_table()
+    col, mem = ColumnarSimilaritySink(), InMemorySimilaritySink()
+    col.bulk_store_records({c: np.zeros(1, dtype=np.int64) for c in
+                            ("show_id", "similar_show_id", "similarity_score", "genre_score", "text_score",
+                             "metadata_score")})       # stale content that must be cleared
+    assert store_similarity_batches(top, ids, col) == store_similarity_batches(top, ids, mem)
+    c = col.columns()
+    flat = [(sid, r["similar_show_id"], r["similarity_score"], r["genre_score"], r["text_score"], r["metadata_score"])
+            for sid in ids.tolist() for r in mem.records.get(sid, [])]
+    assert len(flat) == len(c["show_id"]) == int(top.counts.sum())
+    got = list(zip(c["show_id"].tolist(), c["similar_show_id"].tolist(), c["similarity_score"].tolist(),
+                   c["genre_score"].tolist(), c["text_score"].tolist(), c["metadata_score"].tolist()))
+    assert got == flat
+    assert col.get_similarity_stats()["unique_shows"] == mem.get_similarity_stats()["unique_shows"]
+    assert set(col.get_similarity_stats()) >= {"total_records", "unique_shows", "avg_similarities_per_show",
+                                               "last_computed"}          # repos/similarity_repository.py:239-263
+
+
+def test_populate_cli_accepts_the_reference_flags(tmp_path):
+    """--skip-metadata / --skip-test (reference populate_database.py:318-323) parse; without a GPU the
+    similarity step then fails loudly and main exits 1 like the reference (:399-401)."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.scripts import populate_database as pd_
+
+    _write_features(tmp_path)
+    if torch.cuda.is_available():
+        stats = pd_.main(["--input-dir", str(tmp_path), "--skip-metadata", "--skip-test", "--top-n", "3"])
+        assert stats["top_n_per_show"] == 3
+    else:
+        with pytest.raises(SystemExit) as e:
+            pd_.main(["--input-dir", str(tmp_path), "--skip-metadata", "--skip-test", "--top-n", "3"])
+        assert e.value.code == 1
+    with pytest.raises(SystemExit) as e:      # unknown flags are still argparse errors (exit 2)
+        pd_.main(["--no-such-flag"])
+    assert e.value.code == 2

@@ -1,0 +1,249 @@
+"""GPU parity tests added in round 2 (``-m gpu``): the configurations BASELINE.md names on ALL rows,
+bit-level properties of the reported float64 scores, and the premise of the certificate (the
+candidate pass' upper bound) on dense / long-K / signed text.  Every call goes through the C ABI."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import load_golden
+from helpers import assert_topk_matches
+from oracle.compare import compare_topk
+from oracle.cosine import normalize_rows
+from oracle.reference_paths import ProductionRows
+
+pytestmark = pytest.mark.gpu
+
+SYM_OFF, SYM_ON = 1 << 20, 2 << 20
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from tvbingefriend_recommendation_service_b200.engine import HybridTopKEngine
+
+    return HybridTopKEngine(0)
+
+
+# ---- BASELINE.json configs[0] / configs[1] on every row ---------------------------------------------
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+def test_golden_c1_all_rows(engine, tuning):
+    """C1 (1 000 shows x 5 000 vocab): the table of the UNMODIFIED reference hot loop
+    (scripts/populate_database.py:85-259, fixture made by oracle/make_golden.py), all 1 000 rows."""
+    z, cat = load_golden("populate_c1")
+    gw, tw, mw, k, ms = z["case0_params"].tolist()
+    k = int(k)
+    top = engine.compute_top_k(cat.features(), (gw, tw, mw), k, ms, tuning=tuning)
+    pr = ProductionRows(cat.features(), gw, tw, mw)
+    rep = compare_topk(z["case0_idx"].astype(np.int64), z["case0_cnt"], z["case0_scores"][0], top.indices,
+                       top.counts, top.hybrid, lambda r, js: pr.pair_scores(r, js), k, ms)
+    assert rep.ok and rep.rows == 1000, rep.summary() + "\n" + "\n".join(rep.failures)
+    assert int(top.counts.sum()) == int(z["case0_total_records"])
+    # scores of entries at identical positions: 1e-5 relative is the bar; float64 gives ~1e-16
+    same = (z["case0_idx"] == top.indices) & (top.indices >= 0)
+    for c, name in enumerate(("hybrid", "genre", "text", "metadata")):
+        err = np.abs(getattr(top, name)[same] - z["case0_scores"][c][same])
+        assert err.max() <= 1e-14, (name, err.max())
+
+
+def test_c1_through_the_populate_driver(engine, tmp_path):
+    """Same fixture through the drop-in of ``compute_and_store_similarities`` (file contract, sink)."""
+    from oracle.reference_paths import dict_to_arrays
+    from tvbingefriend_recommendation_service_b200.scripts.populate_database import compute_and_store_similarities
+    from tvbingefriend_recommendation_service_b200.sinks import InMemorySimilaritySink
+
+    z, cat = load_golden("populate_c1")
+    cat.save(tmp_path)
+    sink = InMemorySimilaritySink()
+    stats = compute_and_store_similarities(tmp_path, sink=sink)
+    assert stats["total_records"] == int(z["case0_total_records"])
+    idx, cnt, sc = dict_to_arrays(sink.records, cat.show_ids.tolist(), 20)
+    pr = ProductionRows(cat.features())
+    rep = compare_topk(z["case0_idx"].astype(np.int64), z["case0_cnt"], z["case0_scores"][0], idx, cnt, sc[0],
+                       lambda r, js: pr.pair_scores(r, js), 20, 0.1)
+    assert rep.ok and rep.rows == 1000, rep.summary() + "\n" + "\n".join(rep.failures)
+
+
+def test_c2_all_rows_vs_oracle(engine):
+    """C2 (20 000 shows x 5 000 vocab, BASELINE.json configs[1]): all 20 000 rows against the CPU
+    restatement of the production loop (float64, per-row argsort walk)."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+    cat = make_config("C2")
+    top = engine.compute_top_k(cat.features(), (0.4, 0.5, 0.1), 20, 0.1)
+    pr = ProductionRows(cat.features())
+    rows = np.arange(cat.n_shows)
+    ridx, rcnt, rsc = pr.topk_arrays(rows, 20, 0.1, block=256)
+    rep = compare_topk(ridx, rcnt, rsc[0], top.indices, top.counts, top.hybrid,
+                       lambda r, js: pr.pair_scores(int(r), js), 20, 0.1)
+    assert rep.ok and rep.rows == 20000, rep.summary() + "\n" + "\n".join(rep.failures[:20])
+    same = (ridx == top.indices) & (ridx >= 0)
+    assert same.mean() > 0.95
+    for c, name in enumerate(("hybrid", "genre", "text", "metadata")):
+        err = np.abs(getattr(top, name)[same] - rsc[c][same])
+        assert err.max() <= 1e-5 * np.abs(rsc[c][same]).max() and err.max() < 1e-13, (name, err.max())
+
+
+# ---- reported scores: bit-level properties -------------------------------------------------------------
+@pytest.mark.parametrize("w", [(0.4, 0.5, 0.1), (2.0, 3.0, 1.0), (0.3, 0.6, 0.1)])
+def test_hybrid_is_the_numpy_expression_of_the_reported_components(engine, w):
+    """similarity_score == gw*genre_score + tw*text_score + mw*metadata_score evaluated the way numpy
+    evaluates scripts/populate_database.py:190-192 (three rounded products, two rounded sums, no
+    FMA), bit for bit, from every kernel that reports scores: K5 (certified rows), K6 (repaired /
+    forced-exact rows) and the single-show query."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(3000, 4000, nnz=35, seed=77)
+    gw, tw, mw = w
+    dc = engine.upload(stage(cat.features()), w)
+    tabs = [engine.to_host(engine.top_k_device(dc, w, 20, 0.05)),
+            engine.to_host(engine.top_k_device(dc, w, 20, 0.05, force_exact=True)),
+            engine.exact_rows(dc, np.arange(0, 3000, 11), w, k=50, min_similarity=0.0)]
+    for t in tabs:
+        m = t.indices >= 0
+        want = gw * t.genre[m] + tw * t.text[m] + mw * t.metadata[m]
+        assert np.array_equal(t.hybrid[m], want)
+    assert np.array_equal(tabs[0].indices, tabs[1].indices)
+    m = tabs[0].indices >= 0
+    for name in ("hybrid", "genre", "text", "metadata"):   # K5 and K6 agree bit for bit
+        assert np.array_equal(getattr(tabs[0], name)[m], getattr(tabs[1], name)[m]), name
+
+
+def test_no_cooperative_fallback_in_normal_operation(engine):
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(1500, 512, nnz=12, seed=3)
+    engine.compute_top_k(cat.features(), (0.4, 0.5, 0.1), 20, 0.1)
+    assert int(engine.lib.tvbf_noncooperative_fallbacks()) == 0
+    top = engine.compute_top_k(cat.features(), (0.4, 0.5, 0.1), 20, 0.1, tuning=1 << 30)   # plain launch on request
+    assert_topk_matches(top, cat.features(), np.arange(0, 1500, 13))
+
+
+# ---- the certificate's premise: U >= exact, on sparse, dense, long-K and signed text ----------------------
+def _upper_bound_tile(engine, feats, weights, row0=0, col0=0):
+    """(U, exact text part) of the 128 x 256 tile at (row0, col0): U from the raw tensor-core
+    accumulators and the library's own slack constants, exact = text_weight * float64 cosine."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+
+    dc = engine.upload(stage(feats), weights)
+    sl = engine.debug_slack(dc, weights)
+    acc = engine.debug_gemm_tile(dc, row0, col0).cpu().numpy().astype(np.float64)
+    tn = normalize_rows(sp.csr_matrix(feats["text_features"]))
+    n = tn.shape[0]
+    r1, c1 = min(row0 + 128, n), min(col0 + 256, n)
+    exact = weights[1] * np.asarray((tn[row0:r1] @ tn[col0:c1].T).todense())
+    terms = np.diff(tn.indptr)[row0:r1].astype(np.float64)[:, None]
+    a = acc[:r1 - row0, :c1 - col0]
+    u = sl["w_text"] * a + (sl["w_text_err"] + terms * sl["w_text_acc"]) * np.abs(a) + sl["eps"] + terms * sl["eps_term"]
+    return u, exact, sl, a
+
+
+def _only_text(n, text):
+    z = np.zeros((n, 1))
+    return {"genre_features": np.zeros((n, 2), dtype=np.int64), "text_features": text,
+            "platform_features": z.copy(), "type_features": z.copy().astype(bool), "language_features": z.copy()}
+
+
+def test_upper_bound_holds_on_dense_50k_text(engine):
+    """Dense U(0,1) text at V = 50 000: 782 k-blocks of truncating fp32 accumulation and 50 000
+    non-zero products per pair -- the regime the flat 2^-18 allowance of round 1 did not cover."""
+    rng = np.random.default_rng(5)
+    n, v = 256, 50_000
+    text = sp.csr_matrix(rng.random((n, v)))
+    w = (0.0, 1.0, 0.0)
+    u, exact, sl, a = _upper_bound_tile(engine, _only_text(n, text), w)
+    assert np.all(u >= exact), float((exact - u).max())
+    # how much of the allowance the hardware uses: accumulated value against the float64 sum of the
+    # SAME fp16 operands (isolates the accumulation error from the operand rounding)
+    from tvbingefriend_recommendation_service_b200.engine import TEXT_SCALE_LOG2
+
+    tn = normalize_rows(text).toarray()
+    op = (tn * 2.0 ** TEXT_SCALE_LOG2).astype(np.float16).astype(np.float64)
+    ref = op[:128] @ op[:256].T
+    loss = (ref - a) / ref
+    budget = 50_000 * sl["w_text_acc"] / sl["w_text"]
+    print(f"dense 50k: accumulation loss max {loss.max():.3e} min {loss.min():.3e}, budget {budget:.3e}")
+    assert loss.max() <= budget and loss.min() >= -budget
+
+
+def test_upper_bound_holds_with_subnormal_operands(engine):
+    """Rows whose normalised values fall below 2^-22 (fp16 subnormals after the 2^8 scaling): the
+    relative bound does not cover them, the per-term absolute allowance must."""
+    rng = np.random.default_rng(6)
+    n, v = 256, 4096
+    dense = rng.random((n, v)) * 1e-7        # tiny values ...
+    dense[:, 0] = 1.0                         # ... beside one dominant column: x_k ~ 1e-7 after normalisation
+    text = sp.csr_matrix(dense)
+    u, exact, sl, a = _upper_bound_tile(engine, _only_text(n, text), (0.0, 1.0, 0.0))
+    assert np.all(u >= exact), float((exact - u).max())
+
+
+def test_upper_bound_holds_on_signed_text(engine):
+    """Embedding-like text with negative values: cancellation makes the error large relative to the
+    accumulator, so the library must switch to the absolute (Cauchy-Schwarz) bound."""
+    rng = np.random.default_rng(7)
+    n = 512
+    text = sp.csr_matrix(rng.standard_normal((n, 96)))
+    u, exact, sl, a = _upper_bound_tile(engine, _only_text(n, text), (0.0, 1.0, 0.0), 128, 256)
+    assert sl["w_text_err"] == 0.0 and sl["w_text_acc"] == 0.0
+    assert np.all(u >= exact), float((exact - u).max())
+
+
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+def test_signed_text_top_k_matches_oracle(engine, tuning):
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(1500, 300, nnz=10, seed=8)
+    f = cat.features()
+    rng = np.random.default_rng(9)
+    f["text_features"] = sp.csr_matrix(rng.standard_normal((1500, 64)))
+    top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1, tuning=tuning)
+    assert_topk_matches(top, f)
+    exact = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1, force_exact=True)
+    assert np.array_equal(top.indices, exact.indices)
+
+
+def test_dense_text_50k_certified_equals_exact_and_oracle(engine):
+    """N = 1 024 shows of dense U(0,1) text at V = 50 000 (all cosines within ~1 % of 0.75): whatever
+    the certificate lets through must equal the exact kernel and the float64 oracle."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    n, v = 1024, 50_000
+    cat = make_catalogue(n, 64, nnz=4, seed=10)
+    f = cat.features()
+    rng = np.random.default_rng(11)
+    dense = rng.random((n, v))
+    f["text_features"] = sp.csr_matrix(dense)
+    w = (0.4, 0.5, 0.1)
+    top = engine.compute_top_k(f, w, 20, 0.1)
+    exact = engine.compute_top_k(f, w, 20, 0.1, force_exact=True)
+    assert np.array_equal(top.indices, exact.indices) and np.array_equal(top.counts, exact.counts)
+    m = top.indices >= 0
+    assert np.array_equal(top.hybrid[m], exact.hybrid[m])
+    # float64 oracle with dense BLAS (the CSR product of 51 M entries would take minutes)
+    tn = dense / np.sqrt((dense * dense).sum(axis=1))[:, None]
+    g = normalize_rows(f["genre_features"])
+    ms_ = [normalize_rows(f[k_]) for k_ in ("platform_features", "type_features", "language_features")]
+    h = w[0] * (g @ g.T) + w[1] * (tn @ tn.T) + w[2] * (sum(m_ @ m_.T for m_ in ms_) / 3)
+    np.fill_diagonal(h, -1.0)
+    order = np.argsort(-h, axis=1, kind="stable")[:, :20]
+    ref_scores = np.take_along_axis(h, order, axis=1)
+    got_scores = np.where(m, top.hybrid, 0.0)
+    assert np.abs(got_scores - ref_scores).max() < 1e-12
+    gaps_ok = np.all(np.abs(np.diff(np.take_along_axis(h, np.argsort(-h, axis=1)[:, :21], axis=1), axis=1)) > 1e-10, axis=1)
+    assert gaps_ok.mean() > 0.9
+    assert np.array_equal(top.indices[gaps_ok], order[gaps_ok].astype(np.int32))
+
+
+def test_long_k_moderately_dense_text(engine):
+    """V = 50 000 with ~2 000 terms per show: long K (782 k-blocks), rows two orders of magnitude
+    denser than TF-IDF, candidate pass still discriminating."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(1536, 50_000, nnz=2000, seed=12)
+    w = (0.4, 0.5, 0.1)
+    top = engine.compute_top_k(cat.features(), w, 20, 0.1)
+    exact = engine.compute_top_k(cat.features(), w, 20, 0.1, force_exact=True)
+    assert np.array_equal(top.indices, exact.indices) and np.array_equal(top.counts, exact.counts)
+    assert top.flagged_rows < 1536      # the certificate still passes rows (not everything repaired)
+    assert_topk_matches(top, cat.features(), np.arange(0, 1536, 24), w, 20, 0.1)

@@ -35,6 +35,7 @@ class Features(C.Structure):
         ("meta_mode", c_int32), ("meta_kind", c_int32), ("meta_groups", c_int32),
         ("meta_dims", c_int32 * 3), ("meta_dense", c_void_p * 3),
         ("col_side", c_void_p), ("meta_scale", c_void_p),
+        ("text_signed", c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "tvbf_version": (C.c_int, []),
     "tvbf_last_error": (C.c_char_p, []),
     "tvbf_kernel_launches": (C.c_uint64, []),
+    "tvbf_noncooperative_fallbacks": (C.c_uint64, []),
     "tvbf_device_info": (C.c_int, [C.POINTER(c_int32)] * 3),
     "tvbf_prep_csr_normalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "tvbf_prep_csr_to_operand": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
@@ -106,6 +108,9 @@ SIGNATURES = {
     "tvbf_score_pairs": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_int32, c_void_p, c_void_p]),
     "tvbf_debug_schedule": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                       C.POINTER(c_int32), c_int32]),
+    "tvbf_plan_tiles": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, c_int32, c_int32,
+                                  C.POINTER(c_int64)]),
+    "tvbf_debug_slack": (C.c_int, [C.POINTER(Features), C.POINTER(Params), C.POINTER(C.c_float)]),
     "tvbf_debug_gemm_tile": (C.c_int, [C.POINTER(Features), c_int32, c_int32, c_void_p, c_void_p]),
     "tvbf_debug_gemm_tile_pair": (C.c_int, [C.POINTER(Features), c_int32, c_int32, c_void_p, c_void_p]),
 }

@@ -29,6 +29,10 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ] + os.environ.get("TVBF_EXTRA_NVCC_FLAGS", "").split()   # experiments only (e.g. -DTVBF_MBAR_HINT_NS=1000)
+# The exact fp64 scorers must round like numpy (one rounding per product and per sum): no FMA
+# contraction anywhere in rescore.cu.  (The hybrid expression itself is written with explicit
+# __dmul_rn / __dadd_rn in common.cuh: hybrid_rn.)
+PER_FILE_FLAGS = {"rescore.cu": ["-fmad=false"]}
 
 
 def _nvcc() -> str:
@@ -43,6 +47,7 @@ def _fingerprint() -> str:
     for p in [CSRC / s for s in SOURCES] + HEADERS:
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(PER_FILE_FLAGS.items())).encode())
     return h.hexdigest()
 
 
@@ -57,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(src, []), "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                                  text=True)))
     objs = []

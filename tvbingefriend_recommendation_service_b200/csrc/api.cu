@@ -9,7 +9,10 @@
 static thread_local char g_last_error[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 
+static std::atomic<unsigned long long> g_coop_fallbacks{0};
+
 void tvbf_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void tvbf_count_coop_fallback(void) { g_coop_fallbacks.fetch_add(1, std::memory_order_relaxed); }
 
 void tvbf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -183,27 +186,71 @@ tvbf::ScoreParams score_params(const tvbf_features* f, const tvbf_params* p) {
   return sp;
 }
 
-// Bound on the relative error of one fp16/bf16 x fp16/bf16 product against the exact product of
-// the unrounded operands, plus an allowance for the fp32 accumulation inside the tensor core.
-double default_text_rel_err(int dtype) {
+// ---- slack of the upper bound U >= exact hybrid -------------------------------------------------
+// (1) operand rounding: the product of two fp16/bf16-rounded NORMAL numbers differs from the exact
+//     product by at most (2u + u^2) relative, u = unit roundoff.
+// (2) fp16 subnormal operands (x * 2^s < 2^-14) carry an ABSOLUTE error <= 2^-25 instead; against an
+//     operand of magnitude <= op_max * 2^s that is <= 2^-25 * op_max * 2^s per product.
+// (3) accumulation inside the tensor core: products of two 11-bit significands are exact in fp32;
+//     model of one tcgen05.mma K=16 step: the non-zero addends (products and the running sum) are
+//     aligned to the largest exponent keeping >= 24 significant bits, truncated, summed, and the
+//     sum rounded to fp32 -- each non-zero addend loses < 2^-23 of the largest magnitude, zero
+//     addends lose nothing (adding zeros is exact).  With at most T non-zero products in a pair
+//     (T = non-zero operand entries of the row) the total loss is < (2T + T) * 2^-23 * sum|a_k b_k|.
+//     kAccUnit budgets 4 * 2^-23 per term.  tests/test_gpu_parity.py::test_fp16_error_bound_*
+//     measure the three parts against float64 on sparse and on dense 50k-wide text.
+// Non-negative text (TF-IDF): sum|a_k b_k| == acc, all three are taken relative to |acc| per row.
+// Signed text or folded float groups: cancellation breaks that, so the bound is absolute via
+// Cauchy-Schwarz on the unit rows: sum|a_k b_k| <= ||a|| ||b|| = 2^2s * (w_text + folded weights) / w_text.
+double operand_rel_err(int dtype) {
   const double u = dtype == TVBF_TEXT_BF16 ? 1.0 / 256.0 : 1.0 / 2048.0;  // unit roundoff
-  return (2.0 * u + u * u) * 1.01 + 1.0 / 262144.0;
+  return (2.0 * u + u * u) * 1.01;
+}
+constexpr double kAccUnit = 4.0 / 8388608.0 * 1.01;       // 4 * 2^-23 per term
+constexpr double kSubnormalUnit = 2.0 / 8589934592.0;     // 2 * 2^-33 per term (score units, x <= 1)
+
+struct Slack {
+  float w_text, w_text_err, w_text_acc, eps, eps_term;
+};
+
+Slack make_slack(const tvbf_features* f, double wg, double wt, double wm, double rel_override) {
+  const double inv_scale2 = std::ldexp(1.0, -2 * f->text_scale_log2);
+  const double rel = rel_override > 0 ? rel_override : operand_rel_err(f->text_dtype);
+  double folded_w = 0.0, op_max = 1.0;
+  if (f->genre_mode == TVBF_GROUP_FOLDED) {
+    folded_w += std::fabs(wg);
+    if (wt > 0) op_max = std::fmax(op_max, std::sqrt(std::fabs(wg) / wt));
+  }
+  if (f->meta_mode == TVBF_GROUP_FOLDED) {
+    folded_w += std::fabs(wm);
+    const double per_group = f->meta_kind == TVBF_META_MEAN3 ? std::fabs(wm) / 3.0 : std::fabs(wm);
+    if (wt > 0) op_max = std::fmax(op_max, std::sqrt(per_group / wt));
+  }
+  const double wsum = std::fabs(wg) + std::fabs(wt) + std::fabs(wm);
+  const double eps0 = 4e-6 * (wsum + 1.0);   // fp32 rounding of the epilogue's four FMAs
+  Slack s;
+  s.w_text = static_cast<float>(wt * inv_scale2);
+  const double sub = f->text_dtype == TVBF_TEXT_FP16 ? kSubnormalUnit * std::fabs(wt) * op_max : 0.0;
+  if (folded_w > 0.0 || f->text_signed) {
+    const double mass = std::fabs(wt) + folded_w;      // bound of sum|a_k b_k| in score units
+    s.w_text_err = 0.0f;
+    s.w_text_acc = 0.0f;
+    s.eps = static_cast<float>(eps0 + rel * mass);
+    s.eps_term = static_cast<float>(kAccUnit * mass + sub);
+  } else {
+    s.w_text_err = static_cast<float>(std::fabs(wt) * inv_scale2 * rel);
+    s.w_text_acc = static_cast<float>(std::fabs(wt) * inv_scale2 * kAccUnit);
+    s.eps = static_cast<float>(eps0);
+    s.eps_term = static_cast<float>(sub);
+  }
+  return s;
 }
 
 // Everything the candidate kernel needs besides the launch geometry: pointers into the workspace,
 // the fp32 weights of the epilogue and the slack terms of the upper bound U.
 int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl, uint8_t* ws,
                    tvbf::K1Params* out_kp, int n_sweep = 1) {
-  const int s = f->text_scale_log2;
-  const double inv_scale2 = std::ldexp(1.0, -2 * s);
-  const double rel = p->text_rel_err > 0 ? p->text_rel_err : default_text_rel_err(f->text_dtype);
-  // folded groups live inside the accumulator already weighted; their error is bounded
-  // absolutely (Cauchy-Schwarz on unit rows): |err| <= rel * weight
-  double folded_w = 0.0;
-  if (f->genre_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->genre_weight);
-  if (f->meta_mode == TVBF_GROUP_FOLDED) folded_w += std::fabs(p->metadata_weight);
-  const bool any_folded = folded_w > 0.0;
-  const double wsum = std::fabs(p->genre_weight) + std::fabs(p->text_weight) + std::fabs(p->metadata_weight);
+  const bool any_folded = f->genre_mode == TVBF_GROUP_FOLDED || f->meta_mode == TVBF_GROUP_FOLDED;
   if (any_folded) {
     TVBF_REQUIRE(p->text_weight > 0.0, "folded feature groups need text_weight > 0");
     TVBF_REQUIRE(p->genre_weight >= 0.0 && p->metadata_weight >= 0.0,
@@ -254,16 +301,23 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
   kp.kp = pl.kp;
   kp.exclude_self = p->exclude_self;
-  if (any_folded) {
-    // operand columns were scaled by 2^s * sqrt(w_group / text_weight): acc * text_weight * 2^-2s
-    // is the whole folded part of the hybrid; bound the error absolutely.
-    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
-    kp.w_text_err = 0.0f;
-    kp.eps = static_cast<float>(rel * (std::fabs(p->text_weight) + folded_w) + 4e-6 * (wsum + 1.0));
-  } else {
-    kp.w_text = static_cast<float>(p->text_weight * inv_scale2);
-    kp.w_text_err = static_cast<float>(std::fabs(p->text_weight) * inv_scale2 * rel);
-    kp.eps = static_cast<float>(4e-6 * (wsum + 1.0));
+  {
+    // folded groups: operand columns were scaled by 2^s * sqrt(w_group / text_weight), so
+    // acc * text_weight * 2^-2s is the whole folded part of the hybrid
+    const Slack sl = make_slack(f, p->genre_weight, p->text_weight, p->metadata_weight, p->text_rel_err);
+    kp.w_text = sl.w_text;
+    kp.w_text_err = sl.w_text_err;
+    kp.w_text_acc = sl.w_text_acc;
+    kp.eps = sl.eps;
+    kp.eps_term = sl.eps_term;
+  }
+  kp.text_indptr = f->text_indptr;
+  {
+    int folded = 0;
+    if (f->genre_mode == TVBF_GROUP_FOLDED) folded += f->genre_dim;
+    if (f->meta_mode == TVBF_GROUP_FOLDED)
+      for (int g = 0; g < f->meta_groups; ++g) folded += f->meta_dims[g];
+    kp.folded_cols = folded;
   }
   kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
   kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight) : 0.0f;
@@ -285,10 +339,12 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
     kp.n_weights = n_sweep;
     for (int w = 0; w < n_sweep; ++w) {
       const tvbf_params& q = p[w];
-      const double ws_ = std::fabs(q.genre_weight) + std::fabs(q.text_weight) + std::fabs(q.metadata_weight);
-      kp.mw_text[w] = static_cast<float>(q.text_weight * inv_scale2);
-      kp.mw_text_err[w] = static_cast<float>(std::fabs(q.text_weight) * inv_scale2 * rel);
-      kp.mw_eps[w] = static_cast<float>(4e-6 * (ws_ + 1.0));
+      const Slack sl = make_slack(f, q.genre_weight, q.text_weight, q.metadata_weight, q.text_rel_err);
+      kp.mw_text[w] = sl.w_text;
+      kp.mw_text_err[w] = sl.w_text_err;
+      kp.mw_text_acc[w] = sl.w_text_acc;
+      kp.mw_eps[w] = sl.eps;
+      kp.mw_eps_term[w] = sl.eps_term;
       kp.mw_genre[w] = static_cast<float>(q.genre_weight);
       kp.mw_meta[w] = static_cast<float>(q.metadata_weight);
     }
@@ -305,6 +361,8 @@ int tvbf_version(void) { return TVBF_VERSION; }
 const char* tvbf_last_error(void) { return g_last_error; }
 
 uint64_t tvbf_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t tvbf_noncooperative_fallbacks(void) { return g_coop_fallbacks.load(std::memory_order_relaxed); }
 
 int tvbf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;
@@ -831,6 +889,57 @@ static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float*
   kp.dump_col0 = col0;
   kp.kp = 32;
   return tvbf::k1_launch_dump(f, kp, cg, static_cast<cudaStream_t>(stream));
+}
+
+// host-only: how many tensor-core tiles the candidate pass of this job executes
+int tvbf_plan_tiles(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                    int32_t tile_sharded, int64_t* out4) {
+  int rc = validate_features(f);
+  if (rc != TVBF_OK) return rc;
+  TVBF_REQUIRE(p && out4, "tvbf_plan_tiles: NULL argument");
+  uint8_t* fake_ws = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(4096));   // offsets only, never dereferenced
+  tvbf::K1Params kp;
+  long long t[2] = {0, 0};
+  if (tile_sharded) {
+    SymPlan sp;
+    rc = make_sym_plan(f, p, rank, world, &sp);
+    if (rc != TVBF_OK) return rc;
+    rc = fill_sym_params(f, p, sp, rank, world, fake_ws, nullptr, &kp);
+    if (rc != TVBF_OK) return rc;
+    kp.sym_phase = 0;
+    if (sp.local_sb > 0) tvbf::k1_executed_tiles(kp, sp.pl.grid, t);
+    out4[2] = 256;
+    out4[3] = 1;
+  } else {
+    rc = validate_params(f, p);
+    if (rc != TVBF_OK) return rc;
+    Plan pl;
+    rc = make_plan(f, p, &pl);
+    if (rc != TVBF_OK) return rc;
+    const bool use_k1 = !p->force_exact && pl.entries != 0;
+    if (use_k1) {
+      rc = fill_k1_params(f, p, pl, fake_ws, &kp);
+      if (rc != TVBF_OK) return rc;
+      tvbf::k1_executed_tiles(kp, pl.grid, t);
+    }
+    out4[2] = 128 * pl.cg;
+    out4[3] = pl.sym;
+  }
+  out4[0] = t[0];
+  out4[1] = t[1];
+  return TVBF_OK;
+}
+
+// host-only: the slack constants of the candidate pass' upper bound for this job
+int tvbf_debug_slack(const tvbf_features* f, const tvbf_params* p, float* out5) {
+  TVBF_REQUIRE(f && p && out5, "tvbf_debug_slack: NULL argument");
+  const Slack sl = make_slack(f, p->genre_weight, p->text_weight, p->metadata_weight, p->text_rel_err);
+  out5[0] = sl.w_text;
+  out5[1] = sl.w_text_err;
+  out5[2] = sl.w_text_acc;
+  out5[3] = sl.eps;
+  out5[4] = sl.eps_term;
+  return TVBF_OK;
 }
 
 // host-only: the work items of one K1 launch (no device needed)

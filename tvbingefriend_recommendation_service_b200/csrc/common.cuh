@@ -16,6 +16,7 @@
 // ---------------------------------------------------------------------------------------------
 void tvbf_set_error(const char* fmt, ...);
 void tvbf_count_launch(void);  // every kernel launch of the library is counted (tvbf_kernel_launches)
+void tvbf_count_coop_fallback(void);  // K1 launches that fell back from cooperative to plain
 
 #define TVBF_CUDA_OK(expr)                                                              \
   do {                                                                                  \
@@ -310,6 +311,14 @@ __device__ __forceinline__ uint32_t f32_orderable(float f) {
 __device__ __forceinline__ float f32_from_orderable(uint32_t u) {
   uint32_t b = u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu);
   return __uint_as_float(b);
+}
+
+// The reference's hybrid expression `gw * g + tw * t + mw * m` (scripts/populate_database.py:190-192;
+// ml/similarity_computer.py:122-124) exactly as numpy evaluates it: three rounded products, two
+// rounded sums, left to right, no FMA contraction.  Every fp64 scorer goes through this one
+// function, so a score computed by K5, K6, the pair scorer and the N x N combine agree bit for bit.
+__device__ __forceinline__ double hybrid_rn(double wg, double g, double wt, double t, double wm, double m) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(wg, g), __dmul_rn(wt, t)), __dmul_rn(wm, m));
 }
 
 }  // namespace tvbf

@@ -68,6 +68,13 @@ struct K1Params {
   int exclude_self;
   float w_text;        // text_weight * 2^-2s
   float w_text_err;    // |text_weight| * 2^-2s * rel_err  (multiplies |acc|)
+  // The tensor-core accumulation error grows with the number of non-zero products of a pair, which
+  // is at most the number of non-zero operand entries of the row ("terms" = its text nnz + the
+  // folded columns): per row, w_text_err += terms * w_text_acc and eps += terms * eps_term.
+  const int64_t* text_indptr;
+  int folded_cols;
+  float w_text_acc;    // relative accumulation allowance per term (0 in absolute mode)
+  float eps_term;      // absolute allowance per term: fp16 subnormal operands (+ accumulation in absolute mode)
   float w_genre;
   float w_meta;        // metadata_weight
   int meta_hstack;     // 1: per-column 1/sqrt(#categories) scale is read from meta_scale
@@ -78,6 +85,7 @@ struct K1Params {
   int n_weights;
   int n_pad;
   float mw_text[kMaxSweep], mw_text_err[kMaxSweep], mw_genre[kMaxSweep], mw_meta[kMaxSweep], mw_eps[kMaxSweep];
+  float mw_text_acc[kMaxSweep], mw_eps_term[kMaxSweep];
 };
 
 // parameters of the exact fp64 scorers (rescore.cu)
@@ -94,6 +102,7 @@ int k1_default_candidates(int k);
 int k1_choose_splits(int rb_count, int col_tiles, int sm_count);
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st);
+void k1_executed_tiles(const K1Params& kp, int grid, long long* out2);
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st);
 // candidate list s of shard row r lives in slot  slot_base + r * row_stride + s * list_stride
 struct CandLayout {

@@ -53,7 +53,7 @@ __global__ void hybrid_combine_kernel(const double* __restrict__ g, const double
                                       double wm, long long count, double* __restrict__ out) {
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (; i < count; i += stride) out[i] = wg * g[i] + wt * t[i] + wm * m[i];
+  for (; i < count; i += stride) out[i] = tvbf::hybrid_rn(wg, g[i], wt, t[i], wm, m[i]);
 }
 
 // ---- upper-triangle statistics (similarity_computer.py:171-190) --------------------------------

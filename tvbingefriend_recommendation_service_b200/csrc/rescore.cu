@@ -47,7 +47,7 @@ __device__ __forceinline__ double dense_dot(const double* x, int dim, int i, int
   const double* a = x + static_cast<size_t>(i) * dim;
   const double* b = x + static_cast<size_t>(j) * dim;
   double s = 0.0;
-  for (int c = 0; c < dim; ++c) s += a[c] * b[c];
+  for (int c = 0; c < dim; ++c) s = __dadd_rn(s, __dmul_rn(a[c], b[c]));
   return s;
 }
 
@@ -97,7 +97,7 @@ __device__ __forceinline__ Scores score_pair(const ScoreParams& sp, int i, int j
   s.g = genre_score(sp.f, i, j);
   s.t = text_dot(sp.f, i, j);
   s.m = meta_score(sp.f, i, j);
-  s.h = sp.wg * s.g + sp.wt * s.t + sp.wm * s.m;
+  s.h = hybrid_rn(sp.wg, s.g, sp.wt, s.t, sp.wm, s.m);
   return s;
 }
 
@@ -148,29 +148,31 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   // Several lists (column splits, or the partial lists of several GPUs): only the `keep` largest
   // upper bounds are worth an exact score -- what a single merged list would have kept.  Everything
   // cut here has exact score <= U <= the keep-th largest U, which joins the row's bound theta.
-  // (U bits of positive floats order like unsigned integers.)
+  // (selection on the order-preserving integer image of U: the one-sided sweep admits negative
+  // weights and thresholds, so U may be negative.)
   if (total > keep) {
     uint32_t best = 0u;
 #pragma unroll 1
-    for (int bit = 30; bit >= 0; --bit) {
+    for (int bit = 31; bit >= 0; --bit) {
       const uint32_t t = best | (1u << bit);
       int c = 0;
-      for (int e = lane; e < total; e += 32) c += (su[e] >= t);
+      for (int e = lane; e < total; e += 32) c += (f32_orderable(__uint_as_float(su[e])) >= t);
       c = __reduce_add_sync(kFullMask, c);
       if (c >= keep) best = t;
     }
     int above = 0;
-    for (int e = lane; e < total; e += 32) above += (su[e] > best);
+    for (int e = lane; e < total; e += 32) above += (f32_orderable(__uint_as_float(su[e])) > best);
     above = __reduce_add_sync(kFullMask, above);
     const int quota = keep - above;   // entries equal to the keep-th value that still fit
     int out_n = 0, eq_seen = 0;
     for (int c0 = 0; c0 < total; c0 += 32) {   // ordered in-place compaction (writes trail reads)
       const int e = c0 + lane;
       const uint32_t u = e < total ? su[e] : 0u;
+      const uint32_t uo = f32_orderable(__uint_as_float(u));
       const int j = e < total ? sj[e] : 0;
       const unsigned lt = (1u << lane) - 1u;
-      const unsigned bal_eq = __ballot_sync(kFullMask, e < total && u == best);
-      const bool take = e < total && (u > best || (u == best && eq_seen + __popc(bal_eq & lt) < quota));
+      const unsigned bal_eq = __ballot_sync(kFullMask, e < total && uo == best);
+      const bool take = e < total && (uo > best || (uo == best && eq_seen + __popc(bal_eq & lt) < quota));
       const unsigned bal = __ballot_sync(kFullMask, take);
       if (take) {
         su[out_n + __popc(bal & lt)] = u;
@@ -181,7 +183,7 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
       __syncwarp();
     }
     total = out_n;
-    theta = fmaxf(theta, __uint_as_float(best));
+    theta = fmaxf(theta, f32_from_orderable(best));
     __syncwarp();
   }
   // exact scores
@@ -570,7 +572,7 @@ __device__ __forceinline__ double batch_hybrid(const ScoreParams& sp, const Batc
     g = genre_score(f, br.row[r], j);
     mm = meta_score(f, br.row[r], j);
   }
-  return sp.wg * g + sp.wt * text + sp.wm * mm;
+  return hybrid_rn(sp.wg, g, sp.wt, text, sp.wm, mm);
 }
 
 template <int MAXB>

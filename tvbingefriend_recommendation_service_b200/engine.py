@@ -61,6 +61,7 @@ class StagedCatalogue:
     genre: torch.Tensor                     # uint8 [N,G] (packed) or float64 [N,G] (folded)
     meta_packed: bool
     meta: list                              # 3 x uint8 one-hot (packed) or float64 groups (folded)
+    text_signed: bool = False               # any negative text value (embeddings / SVD instead of TF-IDF)
 
     def h2d_bytes(self) -> int:
         ts = [self.text_indptr, self.text_indices, self.text_values, self.genre, *self.meta]
@@ -108,7 +109,8 @@ def stage(features: dict, metadata_mode: str = "mean3", pin: bool = True) -> Sta
         text_indices=_pin(torch.from_numpy(text.indices.astype(np.int32)), pin),
         text_values=_pin(torch.from_numpy(np.ascontiguousarray(text.data, dtype=np.float64)), pin),
         genre_packed=genre_packed, genre=_pin(g_t, pin),
-        meta_packed=meta_packed, meta=[_pin(m, pin) for m in meta])
+        meta_packed=meta_packed, meta=[_pin(m, pin) for m in meta],
+        text_signed=bool(text.nnz and text.data.min() < 0.0))
 
 
 @dataclass
@@ -141,10 +143,19 @@ class TopK:
     def k(self) -> int:
         return int(self.indices.shape[1])
 
+    def slice(self, begin: int, end: int) -> "TopK":
+        """Rows [begin, end) of this table (positions within the table) as a view."""
+        return TopK(self.indices[begin:end], self.counts[begin:end], self.hybrid[begin:end], self.genre[begin:end],
+                    self.text[begin:end], self.metadata[begin:end], row_begin=self.row_begin + begin)
+
+    @staticmethod
+    def _ids(show_ids) -> np.ndarray:
+        return show_ids if isinstance(show_ids, np.ndarray) else np.asarray(list(show_ids))
+
     def to_dict(self, show_ids, id_key: str = "similar_show_id") -> dict:
         """``all_similarities`` exactly as the hot loop builds it (populate_database.py:208-221):
         shows without a qualifying neighbour are omitted."""
-        ids = np.asarray(list(show_ids))
+        ids = self._ids(show_ids)
         # bulk conversion to Python scalars first: 2 M records of C3 take 2.2 s this way, 3.0 s with
         # per-element float()/int() calls (the dicts themselves are the rest)
         sim = ids[np.where(self.indices >= 0, self.indices, 0)].tolist()
@@ -161,9 +172,9 @@ class TopK:
         return out
 
     def records(self, show_ids) -> dict:
-        """Flat columnar records (one per kept pair) for a bulk sink
+        """Flat columnar records (one per kept pair, in table order) for a bulk sink
         (repos/similarity_repository.py:72-108 row shape) without building N*k dicts."""
-        ids = np.asarray(list(show_ids))
+        ids = self._ids(show_ids)
         mask = np.arange(self.k)[None, :] < self.counts[:, None]
         rows = np.nonzero(mask)[0]
         return {"show_id": ids[self.row_begin + rows],
@@ -272,6 +283,7 @@ class HybridTopKEngine:
             f.operand = operand.data_ptr()
             f.text_indptr, f.text_indices, f.text_values = indptr.data_ptr(), indices.data_ptr(), values.data_ptr()
             f.col_side, f.meta_scale = col_side.data_ptr(), meta_scale.data_ptr()
+            f.text_signed = int(st.text_signed)
             f.meta_kind = _lib.META_MEAN3 if st.metadata_mode == "mean3" else _lib.META_HSTACK
             col = v
             folded = False
@@ -727,6 +739,27 @@ class HybridTopKEngine:
                          "median": 0.5 * (value_at((count - 1) // 2) + value_at(count // 2)),
                          "median_resolution": width}
         return out
+
+    def plan_tiles(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int = 0, world: int = 1,
+                   tile_sharded: bool = False, row_begin: int = 0, row_end: int | None = None, splits: int = 0,
+                   tuning: int = 0) -> dict:
+        """Tensor-core tiles the candidate pass of this job executes (``tvbf_plan_tiles``, host only)."""
+        p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end, splits=splits,
+                         tuning=tuning)
+        out = (C.c_int64 * 4)()
+        with torch.cuda.device(self.device):
+            check(self.lib.tvbf_plan_tiles(C.byref(cat.c), C.byref(p), int(rank), int(world), int(bool(tile_sharded)),
+                                           out), "tvbf_plan_tiles")
+        seed, sweep, rows, sym = (int(x) for x in out)
+        return {"seed_tiles": seed, "sweep_tiles": sweep, "tile_rows": rows, "symmetric": bool(sym),
+                "flops": 2.0 * (seed + sweep) * rows * 256 * int(cat.c.k_pad)}
+
+    def debug_slack(self, cat: DeviceCatalogue, weights) -> dict:
+        """Constants of the candidate pass' upper bound (``tvbf_debug_slack``; tests only)."""
+        p = self._params(cat, weights, 20, 0.1)
+        out = (C.c_float * 5)()
+        check(self.lib.tvbf_debug_slack(C.byref(cat.c), C.byref(p), out), "tvbf_debug_slack")
+        return dict(zip(("w_text", "w_text_err", "w_text_acc", "eps", "eps_term"), (float(x) for x in out)))
 
     def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int, pair: bool = False) -> torch.Tensor:
         """Raw fp32 accumulators of one tensor-core tile (diagnostics / tests): 128 x 256 through

@@ -13,6 +13,8 @@ import logging
 import sys
 from pathlib import Path
 
+import numpy as np
+
 from ..ml.similarity_computer import SimilarityComputer
 from ..services.content_based_service import load_feature_files, load_show_ids
 from ..sinks import InMemorySimilaritySink
@@ -39,46 +41,118 @@ def compute_and_store_similarities(input_dir: Path, genre_weight: float = 0.4, t
                                  exclude_self=True, metadata_mode="mean3", normalize_weights=False,
                                  device_ids=device_ids)
     sink = sink if sink is not None else InMemorySimilaritySink()
-    all_similarities = top.to_dict(show_ids)
+    total_records_stored = store_similarity_batches(top, show_ids, sink)
+    return finish_stats(sink, total_records_stored, top.flagged_rows, top_n_per_show, min_similarity)
+
+
+def store_similarity_batches(top, show_ids, sink) -> int:
+    """The storage half of the reference loop: delete-all up front (reference :156-162), then one
+    ``bulk_store_all_similarities(batch, clear_existing=False)`` per 5000 shows (:223-234).  A sink
+    with ``bulk_store_records`` gets the columnar batch instead of 5000 x k dicts."""
+    ids = np.asarray(list(show_ids))
+    n = len(ids)
+    columnar = getattr(sink, "bulk_store_records", None)
+    if columnar is not None:
+        columnar({c: ids[:0] for c in ("show_id", "similar_show_id", "similarity_score", "genre_score",
+                                       "text_score", "metadata_score")}, clear_existing=True)
+    else:
+        sink.bulk_store_all_similarities({}, clear_existing=True)
     total_records_stored = 0
-    batch = {}
-    clear = getattr(sink, "records", None) is not None
-    if clear:
-        sink.bulk_store_all_similarities({}, clear_existing=True)   # reference :156-162 delete-all up front
-    for n_done, show_id in enumerate(show_ids, start=1):
-        recs = all_similarities.get(show_id)
-        if recs:
-            batch[show_id] = recs
-        if n_done % BATCH_SIZE == 0 or n_done == len(show_ids):    # reference :223-234
+    for b in range(0, n, BATCH_SIZE):
+        e = min(b + BATCH_SIZE, n)
+        part = top.slice(b, e)
+        if columnar is not None:
+            total_records_stored += columnar(part.records(ids), clear_existing=False)
+        else:
+            batch = part.to_dict(ids)
             if batch:
                 total_records_stored += sink.bulk_store_all_similarities(batch, clear_existing=False)
-                batch = {}
-            logger.info(f"  Processed {n_done}/{len(show_ids)} shows... (stored {total_records_stored} records)")
+        logger.info(f"  Processed {e}/{n} shows... (stored {total_records_stored} similarity records)")
+    logger.info(f"✓ Stored {total_records_stored} total similarity records")
+    return total_records_stored
+
+
+def finish_stats(sink, total_records_stored: int, flagged_rows: int, top_n_per_show, min_similarity) -> dict:
+    """reference :243-255"""
     stats = dict(sink.get_similarity_stats())
     stats["total_records"] = total_records_stored
     stats["top_n_per_show"] = top_n_per_show
     stats["min_similarity"] = min_similarity
-    stats["flagged_rows"] = top.flagged_rows
+    stats["flagged_rows"] = flagged_rows
     return stats
 
 
-def main(argv=None):
-    """The similarity-related flags of reference :298-401."""
-    parser = argparse.ArgumentParser(description="Compute top-N similarities on B200 and store them")
+def load_and_sync_metadata(service, input_dir: Path) -> int:
+    """reference :46-82 -- persistence of show metadata is storage (out of scope); the drop-in
+    forwards the CSV records to the service's sink when that offers ``bulk_store_shows``."""
+    import pandas as pd
+
+    metadata_path = Path(input_dir) / "shows_metadata.csv"
+    if not metadata_path.exists():
+        raise FileNotFoundError(f"Metadata file not found: {metadata_path}\n" "Run fetch_and_prepare_data.py first.")
+    shows_df = pd.read_csv(metadata_path)
+    shows_df = shows_df.astype(object).where(pd.notnull(shows_df), None)
+    count = service.sync_metadata_to_db(shows_df.to_dict("records"))
+    logger.info(f"✓ Synced {count} shows to database")
+    return count
+
+
+def verify_recommendations(service, metadata_path: Path, num_tests: int = 3) -> None:
+    """reference :262-295"""
+    import pandas as pd
+
+    shows_df = pd.read_csv(metadata_path)
+    for show_id in shows_df["id"].head(num_tests).tolist():
+        recommendations = service.get_recommendations_from_db(show_id=show_id, n=5)
+        logger.info(f"\nRecommendations for show {show_id}:")
+        if recommendations:
+            for i, rec in enumerate(recommendations, 1):
+                logger.info(f"  {i}. {rec.get('name', rec.get('similar_show_id'))} "
+                            f"(score: {rec['similarity_score']:.3f})")
+        else:
+            logger.warning("  No recommendations found")
+
+
+def main(argv=None, sink=None):
+    """reference :298-401: same flags, same order of steps, ``sys.exit(1)`` on any exception."""
+    parser = argparse.ArgumentParser(description="Populate database with show metadata and similarities")
     parser.add_argument("--input-dir", type=str, default="data/processed")
     parser.add_argument("--top-n", type=int, default=20)
     parser.add_argument("--min-similarity", type=float, default=0.1)
+    parser.add_argument("--skip-metadata", action="store_true", help="Skip metadata sync (only compute similarities)")
+    parser.add_argument("--skip-test", action="store_true", help="Skip recommendation testing")
     parser.add_argument("--genre-weight", type=float, default=0.4)
     parser.add_argument("--text-weight", type=float, default=0.5)
     parser.add_argument("--metadata-weight", type=float, default=0.1)
     args = parser.parse_args(argv)
+    input_dir = Path(args.input_dir)
     try:
-        stats = compute_and_store_similarities(Path(args.input_dir), args.genre_weight, args.text_weight,
-                                               args.metadata_weight, args.top_n, args.min_similarity)
-        logger.info(f"Total records stored: {stats['total_records']}")
+        from ..services.content_based_service import ContentBasedRecommendationService
+
+        sink = sink if sink is not None else InMemorySimilaritySink()
+        service = ContentBasedRecommendationService(processed_data_dir=input_dir, use_blob=False, sink=sink)
+        metadata_count = 0
+        if not args.skip_metadata:
+            if hasattr(sink, "bulk_store_shows"):
+                metadata_count = load_and_sync_metadata(service, input_dir)
+            else:   # metadata persistence is storage: nothing to do without a sink that stores shows
+                logger.info("\n⊘ No metadata store configured (sink has no bulk_store_shows): skipping metadata sync")
+        else:
+            logger.info("\n⊘ Skipping metadata sync")
+        stats = compute_and_store_similarities(input_dir, args.genre_weight, args.text_weight, args.metadata_weight,
+                                               args.top_n, args.min_similarity, sink=sink)
+        if not args.skip_test:
+            verify_recommendations(service, input_dir / "shows_metadata.csv", num_tests=3)
+        else:
+            logger.info("\n⊘ Skipping recommendation testing")
+        if not args.skip_metadata:
+            logger.info(f"Shows synced: {metadata_count}")
+        logger.info(f"Similarity records: {stats['total_records']}")
+        logger.info(f"Unique shows with recommendations: {stats['unique_shows']}")
+        logger.info(f"Average similarities per show: {stats['avg_similarities_per_show']:.1f}")
         return stats
     except Exception as e:  # reference :399-401
-        logger.error(f"Error: {e}", exc_info=True)
+        logger.error(f"Error during database population: {str(e)}", exc_info=True)
         sys.exit(1)
 
 
