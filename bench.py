@@ -330,22 +330,44 @@ def main() -> None:
     rb, re_ = row_shard(n, world, rank)
     peaks = _peaks()
 
-    def step_device(timing: dict | None = None):
-        """prep + top-k (+ candidate exchange and gather when N > 1); optionally brackets K1."""
-        dc = eng.prepare(raw, weights)
+    PHASES = ("prep", "seed", "reduce", "sweep", "exchange", "rescore", "gather")
+    state = {"prev": None}
+
+    def step_device(events: dict | None = None):
+        """prep + top-k (+ threshold all-reduce, candidate all-to-all and table all-gather when N > 1);
+        ``events`` receives CUDA events around every phase."""
+        def mark(name):
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                events.setdefault(name, []).append(ev)
+
+        mark("step0")
+        dc = eng.prepare(raw, weights, recycle=state["prev"])     # the previous step's operand buffer is recycled
+        state["prev"] = dc
         if world > 1:
             return top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
-                                            symmetric=None if not args.one_sided else False,
-                                            k1_events=None if timing is None else timing.setdefault("k1x", []))
-        if timing is None:
+                                            symmetric=None if not args.one_sided else False, events=events)
+        if events is None:
             return eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        mark("seed0")
         t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=1, tuning=args.tuning)
-        e1.record()
+        for name in ("seed1", "reduce1", "sweep1", "exchange1"):   # one launch sequence: seed + sweep = "sweep"
+            mark(name)
         eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=6, out=t, tuning=args.tuning)
-        timing.setdefault("k1", []).append((e0, e1))
+        mark("rescore1")
+        mark("gather1")
         return t
+
+    def phase_ms(events: dict) -> dict:
+        order = ("step0", "seed0", "seed1", "reduce1", "sweep1", "exchange1", "rescore1", "gather1")
+        out = {}
+        for name, a, b in zip(PHASES, order, order[1:]):
+            out[name] = float(np.mean([x.elapsed_time(y) for x, y in zip(events[a], events[b])]))
+        if world == 1:      # seed pass and sweep are one call on a single GPU
+            out["sweep"] += out.pop("seed")
+            out["seed"] = 0.0
+        return out
 
     def sync():
         if world > 1:
@@ -355,43 +377,49 @@ def main() -> None:
     for _ in range(max(args.warmup, 3)):
         out = step_device()
     sync()
-    flagged = int(out["stats"][0].item()) if out is not None else 0
-    pairs = int(out["stats"][1].item()) if out is not None else 0
+    stats_host = out["stats"].cpu().numpy().reshape(-1, 8).sum(axis=0)
+    flagged, pairs = int(stats_host[0]), int(stats_host[1])
 
     # ---- timed region 1: device-resident inputs -------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = eng.kernel_launches
-    timing: dict = {}
+    events: dict = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     ev0.record()
     for _ in range(args.steps):
-        step_device(timing)
+        step_device(events)
     ev1.record()
     sync()
     launches = eng.kernel_launches - launches0
     total_ms = ev0.elapsed_time(ev1)
-    k1_ms = [a.elapsed_time(b) for a, b in timing.get("k1", [])]
-    k1_ms += [sum(a.elapsed_time(b) for a, b in step) for step in timing.get("k1x", [])]
+    ph = phase_ms(events)
     clocks = sampler.stop() if rank == 0 else None
-    t_ms = torch.tensor([total_ms, float(np.mean(k1_ms)) if k1_ms else 0.0], device="cuda", dtype=torch.float64)
+    t_ms = torch.tensor([total_ms, ph["seed"] + ph["sweep"]] + [ph[name] for name in PHASES], device="cuda",
+                        dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_per_step = t_ms[0].item() / args.steps
     k1_ms_mean = t_ms[1].item()
+    phases_max = {name: round(t_ms[2 + i].item(), 4) for i, name in enumerate(PHASES)}
 
     # ---- timed region 2: end to end through the public engine API (H2D + compute + D2H) --------
+    dtk = None
+    if world > 1:
+        from tvbingefriend_recommendation_service_b200.multi_gpu import DistributedTopK
+
+        dtk = DistributedTopK(eng, n, k)
+
     def step_e2e():
-        raw2 = eng.h2d(st)
-        dc = eng.prepare(raw2, weights)
-        if world > 1:
-            t = top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
-                                         symmetric=None if not args.one_sided else False)
-        else:
-            t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
-        return eng.to_host(t, copy=False) if rank == 0 else None
+        if world > 1:     # sliced upload + NVLink replication in, shared pinned host table out
+            return dtk.run(st, weights, 0.1, True, symmetric=None if not args.one_sided else False,
+                           splits=args.splits, tuning=args.tuning)
+        dc = eng.prepare(eng.h2d(st), weights, recycle=state["prev"])
+        state["prev"] = dc
+        t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
+        return eng.to_host(t, copy=False)
 
     step_e2e()
     sync()
@@ -404,11 +432,13 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = e2e_ms.item() / args.steps
-    d2h = 0
-    if host_table is not None:
-        d2h = sum(getattr(host_table, f).nbytes for f in ("indices", "counts", "hybrid", "genre", "text", "metadata"))
+    d2h = sum(getattr(host_table, f).nbytes for f in ("indices", "counts", "hybrid", "genre", "text", "metadata"))
 
-    final_table = single_table = None
+    final_table = single_table = value_table = None
+    if world > 1 and not args.no_parity_check:     # the device-gathered table of the `value` path as well
+        value_table = eng.to_host(step_device())
+    if dtk is not None:
+        sync()
     if rank == 0 and not args.no_parity_check:
         from tvbingefriend_recommendation_service_b200.engine import TopK
 
@@ -475,8 +505,13 @@ def main() -> None:
         "data": "synthetic", "config": bench_config(args, cfg),
         "roofline": roofline,
         "e2e": {"value": n / (e2e_ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": st.h2d_bytes(),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_per_step},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_per_step,
+                "path": "stage()d pinned features -> H2D -> K0..K6 -> D2H of the [N, k] table" if world == 1 else
+                        f"every rank uploads 1/{world} of the pinned feature bytes (h2d_bytes_per_step is the "
+                        f"whole-job total) and NVLink all-gathers them; every rank copies its shard of the table "
+                        f"into one pinned host table in shared memory (d2h_bytes_per_step is the whole table)"},
         "gpu_launches": int(launches),
+        "phases_ms": phases_max,
         "clocks": clocks,
         "flagged_rows": flagged, "rescored_pairs": pairs,
     }
@@ -489,6 +524,14 @@ def main() -> None:
         line["dense_text"] = probe
     if not args.no_parity_check:
         line["parity_check"] = parity_check(eng, cat, cfg, weights, final_table, single_table)
+        if value_table is not None:
+            m = single_table.indices >= 0
+            line["parity_check"]["device_gathered_table_identical_to_single_gpu"] = bool(
+                np.array_equal(single_table.indices, value_table.indices)
+                and np.array_equal(single_table.counts, value_table.counts)
+                and np.array_equal(single_table.hybrid[m], value_table.hybrid[m]))
+            line["parity_check"]["ok"] = bool(line["parity_check"]["ok"] and
+                                              line["parity_check"]["device_gathered_table_identical_to_single_gpu"])
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(cat, cfg, weights, budget_s=20.0)
     print(json.dumps(line), flush=True)

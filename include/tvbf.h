@@ -145,6 +145,13 @@ int tvbf_prep_csr_normalize(const int64_t* indptr, const double* values, int32_t
 int tvbf_prep_csr_to_operand(const int64_t* indptr, const int32_t* indices, const double* values,
                              int32_t n_rows, void* operand, int32_t k_pad, int32_t col_offset,
                              double scale, int32_t dtype, void* stream);
+/* Recycling an operand buffer: store 0 at every position the CSR of the catalogue it held had set
+ * (one 2-byte store per old non-zero instead of a memset of the whole n_pad x k_pad array). */
+int tvbf_prep_clear_csr_positions(const int64_t* indptr, const int32_t* indices, int32_t n_rows,
+                                  void* operand, int32_t k_pad, int32_t col_offset, int32_t dtype,
+                                  void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (fresh operand / column-side buffers). */
+int tvbf_device_zero(void* ptr, size_t bytes, void* stream);
 /* out[r, :] = in[r, :] / ||in[r, :]||_2 (fp64, zero rows stay zero). */
 int tvbf_prep_dense_normalize(const double* in, int32_t n_rows, int32_t dim, double* out,
                               void* stream);
@@ -180,15 +187,19 @@ int tvbf_hybrid_topk_sweep(const tvbf_features* f, const tvbf_params* p, int32_t
 /* ---- the same job tile-sharded over several GPUs (symmetric sweep).  hybrid(i,j) == hybrid(j,i),
  *      so GPU `rank` of `world` computes only the tiles on/above the diagonal of the 256-row super
  *      blocks dealt to it and feeds BOTH shows of every score; it ends with partial candidate lists
- *      for ALL shows.  Call sequence per GPU, with one small collective (done by the caller)
- *      between the calls:
+ *      for ALL shows.  The super blocks are dealt in groups of consecutive blocks (one launch wave
+ *      each), longest group first to the least-loaded GPU.  Call sequence per GPU, with one small
+ *      collective (done by the caller) between the calls:
  *        tvbf_sym_seed       theta[n_pad]                   -> all_reduce(MAX, uint32) of theta
  *        tvbf_sym_sweep      cand[n_shows][L], cnt, bound   -> all_to_all: GPU r receives every GPU's
  *                                                              lists of ITS rows (or all_gather)
  *        tvbf_rescore_lists  rows [row_begin,row_end) of p  -> gather of the result tables
  *      L = tvbf_sym_list_len(); eligibility (packed groups, non-negative weights, positive
  *      min_similarity, k <= 100): tvbf_sym_eligible().  row_begin/row_end of p are ignored by the
- *      first two calls. */
+ *      first two calls.
+ *      Packed rows: with cand_cnt == cand_bound == NULL (tvbf_sym_sweep) / cnt_all == bound_all ==
+ *      NULL (tvbf_rescore_lists) a candidate row is L + 1 entries of 8 bytes, the last one holding
+ *      {int32 count, float bound}, so that ONE all-to-all moves everything. */
 int tvbf_sym_eligible(const tvbf_features* f, const tvbf_params* p);
 int32_t tvbf_sym_list_len(const tvbf_features* f, const tvbf_params* p);
 size_t tvbf_sym_workspace_bytes(const tvbf_features* f, const tvbf_params* p, int32_t world);

@@ -167,20 +167,32 @@ def test_tile_sharded_symmetric_protocol_emulated_on_one_gpu(engine, world, k):
     w, ms = (0.4, 0.5, 0.1), 0.1
     dc = engine.upload(stage(cat.features()), w)
     assert engine.sym_eligible(dc, w, k, ms)
+    from tvbingefriend_recommendation_service_b200.sharding import shard_rows
+
     thetas = [engine.sym_seed(dc, w, k, ms, r, world) for r in range(world)]
     theta = torch.stack(thetas).amax(dim=0)
     parts = [engine.sym_sweep(dc, w, k, ms, r, world, theta.clone()) for r in range(world)]
     cand_all = torch.stack([p[0] for p in parts])
     cnt_all = torch.stack([p[1] for p in parts])
     bound_all = torch.stack([p[2] for p in parts])
+    # the packed form (what the NCCL driver exchanges in one all-to-all): candidate entries + {count, bound}
+    rows = shard_rows(6000, world)
+    packed_all = torch.stack([engine.sym_sweep(dc, w, k, ms, r, world, theta.clone(), packed_rows=world * rows)
+                              for r in range(world)])
+    L = cand_all.shape[2]
+    assert torch.equal(packed_all[:, :6000, L, 0], cnt_all)
+    assert torch.equal(packed_all[:, :6000, L, 1].view(torch.float32), bound_all)
     tabs = []
     for r in range(world):
         b, e = row_shard(6000, world, r)
-        if r % 2 == 0:   # tables after an all-gather: every rank's lists for all shows
+        if r % 3 == 0:   # tables after an all-gather: every rank's lists for all shows
             t = engine.sym_rescore(dc, w, k, ms, cand_all, cnt_all, bound_all, b, e)
-        else:            # tables after the all-to-all: every rank's lists for this rank's rows only
+        elif r % 3 == 1:  # tables after the all-to-all: every rank's lists for this rank's rows only
             t = engine.sym_rescore(dc, w, k, ms, cand_all[:, b:e].contiguous(), cnt_all[:, b:e].contiguous(),
                                    bound_all[:, b:e].contiguous(), b, e, table_row0=b)
+        else:            # packed rows after the all-to-all (padded shard)
+            t = engine.sym_rescore(dc, w, k, ms, packed_all[:, r * rows:(r + 1) * rows].contiguous(), None, None,
+                                   b, e, table_row0=b)
         tabs.append(engine.to_host(t))
     got = TopK(*(np.concatenate([getattr(t, f) for t in tabs]) for f in
                  ("indices", "counts", "hybrid", "genre", "text", "metadata")))

@@ -17,7 +17,8 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from tvbingefriend_recommendation_service_b200.engine import HybridTopKEngine  # noqa: E402
-from tvbingefriend_recommendation_service_b200.multi_gpu import compute_top_k_distributed  # noqa: E402
+from tvbingefriend_recommendation_service_b200.engine import stage  # noqa: E402
+from tvbingefriend_recommendation_service_b200.multi_gpu import DistributedTopK, compute_top_k_distributed  # noqa: E402
 from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue  # noqa: E402
 
 
@@ -29,6 +30,16 @@ def main():
     eng = HybridTopKEngine(local)
     full = compute_top_k_distributed(cat.features(), engine=eng, symmetric=False)
     sym = compute_top_k_distributed(cat.features(), engine=eng, symmetric=True)
+    # end-to-end form: sliced upload + NVLink replication in, shared pinned host table out (twice: the
+    # second run recycles the first run's operand buffer)
+    dtk = DistributedTopK(eng, cat.n_shows, 20)
+    st = stage(cat.features())
+    for sym_flag in (True, False):
+        e2e = dtk.run(st, symmetric=sym_flag)
+        assert np.array_equal(e2e.indices, full.indices) and np.array_equal(e2e.counts, full.counts), sym_flag
+        assert np.array_equal(e2e.hybrid[e2e.indices >= 0], full.hybrid[full.indices >= 0]), sym_flag
+        dist.barrier()
+    dtk.close()
     if dist.get_rank() == 0:
         assert np.array_equal(full.indices, sym.indices), "tile-sharded symmetric sweep: indices differ"
         assert np.array_equal(full.counts, sym.counts)

@@ -278,8 +278,8 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   kp.sync_slack = pl.sync_slack;
   kp.stages = pl.stages;
   kp.sym = pl.sym;
-  kp.sb_world = 1;
-  kp.sb_rank = 0;
+  kp.deal_groups = 0;   // single GPU: local super block == global super block
+  kp.deal_r = 1;
   kp.tile_stride = 1;
   kp.seed_theta = 0;
   if (pl.sym) {
@@ -438,7 +438,7 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (rc != TVBF_OK) return rc;
   }
   if (phases & 2) {
-    const tvbf::CandLayout lay{0, pl.cand_lists, 1};
+    const tvbf::CandLayout lay{0, pl.cand_lists, 1, 0};
     rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, pl.cand_lists, lay, pl.kp,
                          p->row_begin, pl.rows, *out, flagged, floors, st);
     if (rc != TVBF_OK) return rc;
@@ -520,7 +520,7 @@ int tvbf_hybrid_topk_sweep(const tvbf_features* f, const tvbf_params* p, int32_t
   for (int w = 0; w < n_weights; ++w) {
     TVBF_CUDA_OK(cudaMemsetAsync(out[w].stats, 0, 8 * sizeof(int32_t), st));
     const tvbf::ScoreParams sp = score_params(f, &p[w]);
-    const tvbf::CandLayout lay{static_cast<long long>(w) * (n_weights > 1 ? f->n_pad : 0), 1, 1};
+    const tvbf::CandLayout lay{static_cast<long long>(w) * (n_weights > 1 ? f->n_pad : 0), 1, 1, 0};
     rc = tvbf::k5_launch(sp, kp.cand, kp.cand_cnt, kp.cand_theta, 1, lay, pl.kp, 0, pl.rows, out[w], flagged,
                          floors, st);
     if (rc != TVBF_OK) return rc;
@@ -545,6 +545,8 @@ namespace {
 struct SymPlan {
   Plan pl;            // geometry of a full-catalogue symmetric job
   int local_sb;       // super blocks owned by this rank
+  int deal_groups;    // ... in this many dealt groups of pl.sb_per_group consecutive blocks
+  unsigned short gid[tvbf::kMaxDealGroups];
   size_t off_prog, off_scratch, off_gcnt, off_glist, off_flag, off_floor, off_keys, total;
 };
 
@@ -564,16 +566,18 @@ int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int wo
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
   const int clusters = sms / 2;
-  sp->local_sb = tvbf::k1_local_super_blocks(pl.sb_count, world, rank);
-  if (p->splits <= 0 && world >= 4) {
-    // a group's super blocks span R * world tiles of the diagonal; fewer blocks per group (more
-    // column splits) keeps the phantom tiles under the diagonal in check (measured at world = 8:
-    // 12 splits 13.8 ms vs 8 splits 15.0 ms per rank on C3)
-    pl.splits = 12;
-    while (pl.splits > 1 && (clusters / pl.splits < 1 || pl.col_tiles / pl.splits < 8)) --pl.splits;
-  }
+  // One launch wave = one dealt group of R consecutive super blocks x S column splits: the blocks of
+  // a wave then differ by < R diagonal tiles (the phantom tiles every item walks for the pacing).
   pl.sb_per_group = clusters / pl.splits;
-  if (pl.sb_per_group > sp->local_sb) pl.sb_per_group = sp->local_sb > 0 ? sp->local_sb : 1;
+  if (pl.sb_per_group > pl.sb_count) pl.sb_per_group = pl.sb_count;
+  if (pl.sb_per_group < 1) pl.sb_per_group = 1;
+  if (world == 1) {
+    sp->deal_groups = 0;
+    sp->local_sb = pl.sb_count;
+  } else {
+    sp->deal_groups = tvbf::k1_deal_groups(pl.sb_count, pl.sb_per_group, world, rank, sp->gid, &sp->local_sb);
+    TVBF_REQUIRE(sp->deal_groups >= 0, "catalogue too large for the tile-sharded symmetric sweep on %d GPUs", world);
+  }
   pl.grid = pl.sb_per_group * pl.splits * 2;
   size_t off = 0;
   sp->off_prog = off;    off = align_up(off + 256, 256);
@@ -604,8 +608,10 @@ int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan&
   kp->cand_theta = nullptr;
   kp->rb_count = sp.local_sb;
   kp->rb_per_group = sp.pl.sb_per_group;
-  kp->sb_world = world;
-  kp->sb_rank = rank;
+  kp->deal_groups = sp.deal_groups;
+  kp->deal_r = sp.pl.sb_per_group;
+  for (int g = 0; g < sp.deal_groups; ++g) kp->deal_gid[g] = sp.gid[g];
+  (void)rank;
   // a rank that sweeps 1/world of the tiles gets fewer threshold refreshes: seed more densely
   // (measured at world = 8 on C3: stride 48 -> 0.6 + 8.0 ms per rank, stride 96 -> 0.4 + 8.5 ms)
   if (world >= 2 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
@@ -659,7 +665,9 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
                    void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_features(f);
   if (rc != TVBF_OK) return rc;
-  TVBF_REQUIRE(theta && cand && cand_cnt && cand_bound && workspace, "tvbf_sym_sweep: NULL buffer");
+  TVBF_REQUIRE(theta && cand && workspace, "tvbf_sym_sweep: NULL buffer");
+  TVBF_REQUIRE((cand_cnt == nullptr) == (cand_bound == nullptr),
+               "tvbf_sym_sweep: pass both cand_cnt and cand_bound, or neither (packed rows)");
   SymPlan sp;
   rc = make_sym_plan(f, p, rank, world, &sp);
   if (rc != TVBF_OK) return rc;
@@ -676,6 +684,7 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
   kp.cand = static_cast<uint2*>(cand);
   kp.cand_cnt = cand_cnt;
   kp.cand_theta = cand_bound;
+  kp.cand_packed = cand_cnt == nullptr ? 1 : 0;
   TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
   if (sp.local_sb > 0) {
     rc = tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
@@ -694,7 +703,8 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   if (rc != TVBF_OK) return rc;
   rc = validate_params(f, p);
   if (rc != TVBF_OK) return rc;
-  TVBF_REQUIRE(cand_all && cnt_all && bound_all && lists >= 1, "tvbf_rescore_lists: bad candidate tables");
+  TVBF_REQUIRE(cand_all && lists >= 1 && (cnt_all == nullptr) == (bound_all == nullptr),
+               "tvbf_rescore_lists: bad candidate tables");
   TVBF_REQUIRE(table_row0 >= 0 && table_row0 <= p->row_begin &&
                    static_cast<int64_t>(table_row0) + table_rows >= p->row_end,
                "tvbf_rescore_lists: the candidate tables do not cover rows [row_begin, row_end)");
@@ -717,7 +727,7 @@ int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void*
   const tvbf::ScoreParams scp = score_params(f, p);
   const int rows = p->row_end - p->row_begin;
   // table layout: [lists][table_rows][kp]
-  const tvbf::CandLayout lay{p->row_begin - table_row0, 1, table_rows};
+  const tvbf::CandLayout lay{p->row_begin - table_row0, 1, table_rows, cnt_all == nullptr ? 1 : 0};
   rc = tvbf::k5_launch(scp, static_cast<const uint2*>(cand_all), cnt_all, bound_all, lists, lay, sp.pl.kp,
                        p->row_begin, rows, *out, flagged, floors, st);
   if (rc != TVBF_OK) return rc;
@@ -884,7 +894,7 @@ static int debug_tile(const tvbf_features* f, int32_t row0, int32_t col0, float*
   kp.rb_per_group = 1;
   kp.tiles_per_split = 1;
   kp.tile_stride = 1;
-  kp.sb_world = 1;
+  kp.deal_r = 1;
   kp.stages = cg == 2 ? 6 : 4;
   kp.dump_col0 = col0;
   kp.kp = 32;
@@ -954,11 +964,19 @@ int32_t tvbf_debug_schedule(int32_t col_tiles, int32_t super_blocks, int32_t sb_
   memset(&kp, 0, sizeof(kp));
   kp.col_tiles = col_tiles;
   kp.splits = splits;
-  kp.rb_count = tvbf::k1_local_super_blocks(super_blocks, world, rank);
+  kp.rb_count = super_blocks;
   kp.rb_per_group = sb_per_group;
   kp.tiles_per_split = (col_tiles + splits - 1) / splits;
-  kp.sb_world = world;
-  kp.sb_rank = rank;
+  kp.deal_r = 1;
+  if (world > 1) {
+    kp.deal_r = sb_per_group;
+    kp.deal_groups = tvbf::k1_deal_groups(super_blocks, sb_per_group, world, rank, kp.deal_gid, &kp.rb_count);
+    if (kp.deal_groups < 0) {
+      tvbf_set_error("tvbf_debug_schedule: too many groups per GPU");
+      return TVBF_ERR_INVALID;
+    }
+    if (kp.deal_groups == 0) return 0;   // nothing dealt to this GPU
+  }
   kp.sym = symmetric ? 1 : 0;
   return tvbf::k1_debug_schedule(kp, out, max_items);
 }

@@ -19,6 +19,7 @@
 #include "internal.cuh"
 
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
+#include <cstdlib>
 
 namespace tvbf {
 
@@ -148,10 +149,12 @@ struct ItemCoord {
   int real0, real1;  // ... of which [real0, real1) are computed, the rest are phantom
 };
 
-// Super blocks are dealt to the GPUs in zigzag order (0..W-1, W-1..0, ...) so that in symmetric
-// mode, where block G costs (T - G) tiles, every GPU gets the same work to within one block.
-__host__ __device__ __forceinline__ int global_super_block(int local, int world, int rank) {
-  return local * world + ((local & 1) ? (world - 1 - rank) : rank);
+// local super block number of this launch -> global super block (see K1Params::deal_*)
+__host__ __device__ __forceinline__ int global_super_block(const K1Params& p, int local) {
+  if (p.deal_groups == 0) return local;
+  const int g = local / p.deal_r;
+  if (g >= p.deal_groups) return 0x3fffffff;
+  return static_cast<int>(p.deal_gid[g]) * p.deal_r + (local - g * p.deal_r);
 }
 
 __host__ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int item) {
@@ -161,10 +164,11 @@ __host__ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int 
   ItemCoord c;
   c.split = w / p.rb_per_group;
   const int local = g * p.rb_per_group + (w - c.split * p.rb_per_group);
-  c.sb = global_super_block(local, p.sb_world, p.sb_rank);
+  c.sb = global_super_block(p, local);
   if (p.sym) {
     // the group's super blocks lie at or right of tile i0 on the diagonal; only columns >= i0 matter
-    const int i0 = g * p.rb_per_group * p.sb_world;
+    // (with several GPUs a wave is one dealt group: rb_per_group == deal_r)
+    const int i0 = global_super_block(p, g * p.rb_per_group);
     const int span = p.col_tiles > i0 ? p.col_tiles - i0 : 0;
     const int tps = (span + p.splits - 1) / p.splits;
     c.tile0 = i0 + c.split * tps;
@@ -831,7 +835,7 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   const int n_all = static_cast<int>(total < static_cast<unsigned>(p.sym_cap) ? total : p.sym_cap);
   uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
   const int kp = p.kp;
-  uint2* dst = p.cand + static_cast<size_t>(r) * kp;
+  uint2* dst = p.cand + static_cast<size_t>(r) * (p.cand_packed ? kp + 1 : kp);
   // Lists of up to 1024 entries are selected in one go from registers (32 per lane).  Longer ones
   // (kp > 64) in windows: the kp survivors so far, parked at the head of the list, plus the next
   // 1024 - kp entries; the kp-th value only rises from window to window, so the last one bounds
@@ -892,8 +896,12 @@ sym_compact_kernel(const K1Params p, int n_rows) {
     if (th_bits > __float_as_uint(p.theta_init)) bound = __uint_as_float(th_bits);  // elements were rejected
     if (n_all > kp) bound = fmaxf(bound, __uint_as_float(best));     // list entries cut here
     if (total > static_cast<unsigned>(p.sym_cap)) bound = __int_as_float(0x7f800000);  // overflow: send to K6
-    p.cand_cnt[r] = kept;
-    p.cand_theta[r] = bound;
+    if (p.cand_packed) {
+      dst[kp] = make_uint2(static_cast<unsigned>(kept), __float_as_uint(bound));
+    } else {
+      p.cand_cnt[r] = kept;
+      p.cand_theta[r] = bound;
+    }
   }
 }
 
@@ -943,10 +951,29 @@ static int make_operand_map(const tvbf_features* f, int box_rows, CUtensorMap* o
   return TVBF_OK;
 }
 
-int k1_local_super_blocks(int total_super_blocks, int world, int rank) {
-  int n = 0;
-  while (global_super_block(n, world, rank) < total_super_blocks) ++n;
-  return n;
+int k1_deal_groups(int total_super_blocks, int r, int world, int rank, unsigned short* gid, int* local_sb) {
+  // cost of group g = tiles on/above the diagonal of its super blocks; groups are visited in cost
+  // order (ascending g) and each goes to the GPU with the least work so far (lowest rank on ties)
+  const int groups = (total_super_blocks + r - 1) / r;
+  long long load[64] = {0};
+  int mine = 0, sbs = 0;
+  if (world > 64) return -1;
+  for (int g = 0; g < groups; ++g) {
+    const int b = g * r, e = (b + r < total_super_blocks) ? b + r : total_super_blocks;
+    long long cost = 0;
+    for (int sb = b; sb < e; ++sb) cost += total_super_blocks - sb;
+    int best = 0;
+    for (int w = 1; w < world; ++w)
+      if (load[w] < load[best]) best = w;
+    load[best] += cost;
+    if (best == rank) {
+      if (mine >= kMaxDealGroups || g > 0xFFFF) return -1;
+      gid[mine++] = static_cast<unsigned short>(g);
+      sbs += e - b;
+    }
+  }
+  *local_sb = sbs;
+  return mine;
 }
 
 // Host copy of the kernel's work decomposition (tests check coverage without a GPU): item i ->
@@ -1003,6 +1030,28 @@ int k1_choose_splits(int rb_count, int col_tiles, int sm_count) {
   return best;
 }
 
+// Profilers that serialise and replay kernels (Nsight Compute) make the driver fail a cooperative
+// cluster launch outright -- the error is raised inside the profiler and ends the process before the
+// runtime could report it to us.  Their injection library is visible in the process map, so K1 is
+// launched plainly under them (the grid never exceeds one CTA per SM: co-resident on an idle device).
+// TVBF_COOPERATIVE=0 / 1 overrides the detection.
+static bool profiler_attached() {
+  static const int cached = [] {
+    if (const char* env = getenv("TVBF_COOPERATIVE")) return env[0] == '0' ? 1 : 0;
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr) return 1;
+    FILE* maps = fopen("/proc/self/maps", "r");
+    if (maps == nullptr) return 0;
+    char line[1024];
+    int found = 0;
+    while (!found && fgets(line, sizeof(line), maps) != nullptr)
+      found = strstr(line, "nsight-compute") != nullptr || strstr(line, "libcuda-injection") != nullptr ||
+              strstr(line, "libnvperf_host") != nullptr || strstr(line, "libInterceptorInjectionTarget") != nullptr;
+    fclose(maps);
+    return found;
+  }();
+  return cached != 0;
+}
+
 template <int E, bool kDump, int CG, int kMode>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
   using L = Smem<CG>;
@@ -1029,6 +1078,10 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   // the pacing counter makes CTAs wait on one another: require co-residency of the whole grid
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = (kp.sync_kb > 0 && kp.cooperative) ? 1 : 0;
+  if (attr[1].val.cooperative && profiler_attached()) {
+    attr[1].val.cooperative = 0;
+    tvbf_count_coop_fallback();
+  }
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   cudaError_t err = cudaLaunchKernelEx(&cfg, kern, ta, tb, kp, idesc);

@@ -23,6 +23,7 @@ struct StatsAccum {
 };
 
 // parameters of the tcgen05 candidate kernel (hybrid_topk.cu)
+constexpr int kMaxDealGroups = 192;
 constexpr int kMaxSweep = 5;   // weight triples that can share one symmetric tensor-core sweep
 
 struct K1Params {
@@ -54,8 +55,13 @@ struct K1Params {
   StatsAccum* stats;       // statistics sweep only
   float inv_scale2;        // 2^-2s: accumulator -> text cosine
   float w_text_plain;      // text weight without the error inflation (statistics sweep)
-  int sb_world;            // super blocks are dealt to `sb_world` GPUs in zigzag order ...
-  int sb_rank;             // ... and this launch owns those of `sb_rank` (1 / 0 on a single GPU)
+  // Several GPUs (symmetric sweep): the super blocks are dealt in GROUPS of deal_r consecutive
+  // blocks (what one launch wave sweeps together, so a wave's blocks differ by < deal_r diagonal
+  // tiles), longest group to the least-loaded GPU.  deal_groups == 0: single GPU, local == global.
+  int deal_groups;         // groups owned by this launch
+  int deal_r;              // super blocks per dealt group
+  unsigned short deal_gid[kMaxDealGroups];   // global group number of each local group, cost descending
+  int cand_packed;         // K4s writes {count, bound bits} as entry kp of each row, row stride kp + 1
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
   int seed_theta;          // one-sided sweep only seeds g_theta with the kp-th best sampled score
   int sym_phase;           // 0: init + seed + sweep in one call; 1: init + seed only; 2: sweep only
@@ -104,14 +110,20 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
               int grid, cudaStream_t st);
 void k1_executed_tiles(const K1Params& kp, int grid, long long* out2);
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st);
-// candidate list s of shard row r lives in slot  slot_base + r * row_stride + s * list_stride
+// candidate list s of shard row r lives in slot  slot_base + r * row_stride + s * list_stride;
+// packed: a slot is kp + 1 entries, the last one holding {count, bound bits}, and cand_cnt /
+// cand_theta are not used
 struct CandLayout {
   long long slot_base, row_stride, list_stride;
+  int packed;
 };
 int k5_launch(const ScoreParams& sp, const uint2* cand, const int* cand_cnt,
               const float* cand_theta, int splits, CandLayout lay, int kp, int row_begin, int n_rows,
               const tvbf_topk_out& out, int* flagged_rows, double* flagged_floor, cudaStream_t st);
-int k1_local_super_blocks(int total_super_blocks, int world, int rank);
+// deal the ceil(total / r) groups of r consecutive super blocks to `world` GPUs; fills gid[] with the
+// groups of `rank` (cost descending) and returns {groups, super blocks} of that rank, or -1 when a
+// rank would own more than kMaxDealGroups groups
+int k1_deal_groups(int total_super_blocks, int r, int world, int rank, unsigned short* gid, int* local_sb);
 int k1_debug_schedule(const K1Params& p, int* out, int max_items);
 int k4s_launch(const K1Params& kp, int n_rows, cudaStream_t st);
 int k1_launch_stats(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st);

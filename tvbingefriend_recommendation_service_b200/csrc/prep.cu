@@ -55,6 +55,20 @@ __global__ void csr_to_operand_kernel(const int64_t* __restrict__ indptr,
   for (int64_t i = b + lane; i < e; i += 32) dst[indices[i]] = cvt_operand<T>(values[i] * scale);
 }
 
+// un-scatter: zero the operand entries a previous catalogue's CSR had set (recycling an operand
+// buffer costs one 2-byte store per old non-zero instead of a memset of the whole N x V array)
+template <typename T>
+__global__ void csr_clear_operand_kernel(const int64_t* __restrict__ indptr,
+                                         const int32_t* __restrict__ indices, int n_rows,
+                                         T* __restrict__ operand, int k_pad, int col_offset) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  int64_t b = indptr[row], e = indptr[row + 1];
+  T* dst = operand + static_cast<size_t>(row) * k_pad + col_offset;
+  for (int64_t i = b + lane; i < e; i += 32) dst[indices[i]] = T(0.0f);
+}
+
 __global__ void dense_normalize_kernel(const double* __restrict__ in, int n_rows, int dim,
                                        double* __restrict__ out) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,6 +188,33 @@ int tvbf_prep_csr_to_operand(const int64_t* indptr, const int32_t* indices, cons
         indptr, indices, values, n_rows, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset,
         scale);
   TVBF_LAUNCH_OK("csr_to_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_clear_csr_positions(const int64_t* indptr, const int32_t* indices, int32_t n_rows,
+                                  void* operand, int32_t k_pad, int32_t col_offset, int32_t dtype,
+                                  void* stream) {
+  TVBF_REQUIRE(indptr && operand && n_rows >= 0 && k_pad > 0 && col_offset >= 0,
+               "tvbf_prep_clear_csr_positions: bad arguments");
+  TVBF_REQUIRE(dtype == TVBF_TEXT_FP16 || dtype == TVBF_TEXT_BF16,
+               "tvbf_prep_clear_csr_positions: dtype must be TVBF_TEXT_FP16 or TVBF_TEXT_BF16");
+  if (n_rows == 0) return TVBF_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  unsigned grid = blocks_for(static_cast<size_t>(n_rows) * 32, 256);
+  if (dtype == TVBF_TEXT_FP16)
+    csr_clear_operand_kernel<__half><<<grid, 256, 0, st>>>(indptr, indices, n_rows, static_cast<__half*>(operand),
+                                                           k_pad, col_offset);
+  else
+    csr_clear_operand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        indptr, indices, n_rows, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset);
+  TVBF_LAUNCH_OK("csr_clear_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_device_zero(void* ptr, size_t bytes, void* stream) {
+  TVBF_REQUIRE(ptr != nullptr || bytes == 0, "tvbf_device_zero: NULL pointer");
+  if (bytes == 0) return TVBF_OK;
+  TVBF_CUDA_OK(cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream)));
   return TVBF_OK;
 }
 

@@ -135,10 +135,18 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   float theta = __int_as_float(0xff800000);
   for (int s = 0; s < splits; ++s) {
     const size_t slot = static_cast<size_t>(lay.slot_base + r * lay.row_stride + s * lay.list_stride);
-    const int n = cand_cnt[slot];
-    theta = fmaxf(theta, cand_theta[slot]);
+    const uint2* list = cand + slot * (lay.packed ? kp + 1 : kp);
+    int n;
+    if (lay.packed) {
+      const uint2 tail = list[kp];
+      n = static_cast<int>(tail.x);
+      theta = fmaxf(theta, __uint_as_float(tail.y));
+    } else {
+      n = cand_cnt[slot];
+      theta = fmaxf(theta, cand_theta[slot]);
+    }
     for (int e = lane; e < n; e += 32) {
-      const uint2 c = cand[slot * kp + e];
+      const uint2 c = list[e];
       su[total + e] = c.x;
       sj[total + e] = static_cast<int>(c.y);
     }

@@ -122,6 +122,9 @@ class DeviceCatalogue:
     folded: bool
     weights_baked: tuple | None            # folded groups bake sqrt(w/w_text) into the operand
     keep: list = field(default_factory=list)
+    operand: torch.Tensor | None = None    # [n_pad, k_pad] fp16 / bf16
+    text_indptr: torch.Tensor | None = None
+    text_indices: torch.Tensor | None = None
 
 
 @dataclass
@@ -241,13 +244,23 @@ class HybridTopKEngine:
                     "genre": st.genre.to(dev, non_blocking=True),
                     "meta": [m.to(dev, non_blocking=True) for m in st.meta]}
 
-    def upload(self, st: StagedCatalogue, weights: tuple[float, float, float] = (0.4, 0.5, 0.1)) -> DeviceCatalogue:
+    def upload(self, st: StagedCatalogue, weights: tuple[float, float, float] = (0.4, 0.5, 0.1),
+               recycle: DeviceCatalogue | None = None) -> DeviceCatalogue:
         """H2D copies + K0 prep kernels."""
-        return self.prepare(self.h2d(st), weights)
+        return self.prepare(self.h2d(st), weights, recycle)
 
-    def prepare(self, raw: dict, weights: tuple[float, float, float] = (0.4, 0.5, 0.1)) -> DeviceCatalogue:
+    def _zero(self, t: torch.Tensor) -> None:
+        check(self.lib.tvbf_device_zero(t.data_ptr(), t.numel() * t.element_size(), self._stream()),
+              "tvbf_device_zero")
+
+    def prepare(self, raw: dict, weights: tuple[float, float, float] = (0.4, 0.5, 0.1),
+                recycle: DeviceCatalogue | None = None) -> DeviceCatalogue:
         """K0 prep kernels on device-resident raw features.  ``weights`` matter only when a group
-        is folded into the tensor-core operand (general float features)."""
+        is folded into the tensor-core operand (general float features).
+
+        ``recycle``: a catalogue this engine prepared earlier and the caller no longer needs.  Its
+        operand buffer is taken over -- the positions its CSR had set are zeroed (one store per old
+        non-zero) instead of clearing a fresh N x V array -- and the old catalogue becomes unusable."""
         lib, dev, stream = self.lib, self.device, None
         st: StagedCatalogue = raw["st"]
         gw, tw, mw = (float(w) for w in weights)
@@ -266,9 +279,24 @@ class HybridTopKEngine:
                 indices = torch.zeros((1,), dtype=torch.int32, device=dev)
                 rawv = torch.zeros((1,), dtype=torch.float64, device=dev)
             values = torch.empty_like(rawv)
-            operand = torch.zeros((n_pad, k_pad), dtype=tdt, device=dev)
-            col_side = torch.zeros((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
-            meta_scale = torch.zeros((n_pad,), dtype=torch.float32, device=dev)
+            operand = None
+            if (recycle is not None and recycle.operand is not None and not recycle.folded and folded_dims == 0
+                    and tuple(recycle.operand.shape) == (n_pad, k_pad) and recycle.operand.dtype == tdt
+                    and recycle.operand.device == dev):
+                operand = recycle.operand
+                check(lib.tvbf_prep_clear_csr_positions(recycle.text_indptr.data_ptr(), recycle.text_indices.data_ptr(),
+                                                        recycle.n_shows, operand.data_ptr(), k_pad, 0, code, stream),
+                      "tvbf_prep_clear_csr_positions")
+                recycle.operand = None          # ownership moved: the old catalogue must not be used again
+                recycle.c.operand = None
+                recycle.keep.clear()
+            if operand is None:
+                operand = torch.empty((n_pad, k_pad), dtype=tdt, device=dev)
+                self._zero(operand)
+            col_side = torch.empty((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
+            meta_scale = torch.empty((n_pad,), dtype=torch.float32, device=dev)
+            self._zero(col_side)
+            self._zero(meta_scale)
             keep += [indptr, indices, values, operand, col_side, meta_scale]
             check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), rawv.data_ptr(), n, values.data_ptr(), stream),
                   "tvbf_prep_csr_normalize")
@@ -333,7 +361,8 @@ class HybridTopKEngine:
                     f.meta_dense[gi] = fold(m, per_group_w, "metadata")
             keep.append(raw)
         return DeviceCatalogue(c=f, n_shows=n, folded=folded,
-                               weights_baked=(gw, tw, mw) if folded else None, keep=keep)
+                               weights_baked=(gw, tw, mw) if folded else None, keep=keep,
+                               operand=operand, text_indptr=indptr, text_indices=indices)
 
     # ------------------------------------------------------------------------------------ top-k
     _TABLE_FIELDS = ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")
@@ -346,7 +375,7 @@ class HybridTopKEngine:
              "counts": torch.empty((rows,), dtype=torch.int32, device=dev)}
         for name in ("hybrid", "genre", "text", "metadata"):
             t[name] = torch.empty((rows, k), dtype=torch.float64, device=dev)
-        t["stats"] = torch.zeros((8,), dtype=torch.int32, device=dev)
+        t["stats"] = torch.empty((8,), dtype=torch.int32, device=dev)     # zeroed by the library calls
         if row_begin is not None:
             t["row_begin"] = row_begin
         return t
@@ -460,6 +489,8 @@ class HybridTopKEngine:
                 host[n] = buf
             torch.cuda.current_stream(self.device).synchronize()
         host = {n: (v.numpy().copy() if copy else v.numpy()) for n, v in host.items()}
+        if host["stats"].ndim == 2:            # gathered [world, 8]: per-rank counters
+            host["stats"] = host["stats"].sum(axis=0)
         return TopK(indices=host["indices"], counts=host["counts"], hybrid=host["hybrid"], genre=host["genre"],
                     text=host["text"], metadata=host["metadata"], row_begin=int(t.get("row_begin", 0)),
                     flagged_rows=int(host["stats"][0]), rescored_pairs=int(host["stats"][1]))
@@ -505,14 +536,23 @@ class HybridTopKEngine:
         return theta
 
     def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
-                  theta: torch.Tensor, splits: int = 0, tuning: int = 0):
-        """Phase 2: sweep this rank's tiles; returns (cand int32[N, L, 2], cnt int32[N], bound f32[N]),
-        partial candidate lists for ALL shows, to be all-gathered."""
+                  theta: torch.Tensor, splits: int = 0, tuning: int = 0, packed_rows: int = 0):
+        """Phase 2: sweep this rank's tiles; returns partial candidate lists for ALL shows:
+        (cand int32[N, L, 2], cnt int32[N], bound f32[N]), or -- with ``packed_rows`` >= N -- one
+        int32[packed_rows, L + 1, 2] tensor whose entry L of each row holds {count, bound bits}
+        (what ``sharding.exchange_packed`` moves in one all-to-all)."""
         p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
         dev, n = self.device, cat.n_shows
         with torch.cuda.device(dev):
             ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
             L = int(self.lib.tvbf_sym_list_len(C.byref(cat.c), C.byref(p)))
+            if packed_rows:
+                assert packed_rows >= n
+                packed = torch.empty((packed_rows, L + 1, 2), dtype=torch.int32, device=dev)
+                check(self.lib.tvbf_sym_sweep(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(),
+                                              packed.data_ptr(), None, None, ws.data_ptr(), ws.numel(), self._stream()),
+                      "tvbf_sym_sweep")
+                return packed
             cand = torch.empty((n, L, 2), dtype=torch.int32, device=dev)
             cnt = torch.empty((n,), dtype=torch.int32, device=dev)
             bound = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -522,55 +562,65 @@ class HybridTopKEngine:
         return cand, cnt, bound
 
     def sym_rescore(self, cat: DeviceCatalogue, weights, k, min_similarity, cand_all: torch.Tensor,
-                    cnt_all: torch.Tensor, bound_all: torch.Tensor, row_begin: int, row_end: int,
-                    splits: int = 0, tuning: int = 0, table_row0: int = 0) -> dict:
+                    cnt_all: torch.Tensor | None, bound_all: torch.Tensor | None, row_begin: int, row_end: int,
+                    splits: int = 0, tuning: int = 0, table_row0: int = 0, out: dict | None = None) -> dict:
         """Phase 3: fp64 rescoring + certificate + exact repair of rows [row_begin, row_end) from the
-        exchanged candidate tables ([world, R, L, 2] / [world, R]) that cover the shows
-        [table_row0, table_row0 + R): R = N after an all-gather, R = this rank's rows after an
-        all-to-all."""
+        exchanged candidate tables ([world, R, L, 2] / [world, R], or packed [world, R, L + 1, 2] with
+        ``cnt_all = bound_all = None``) that cover the shows [table_row0, table_row0 + R): R = N after
+        an all-gather, R = this rank's (padded) shard after an all-to-all.  ``out``: tables to write
+        (e.g. ``sharding.shard_views`` of the gather buffer); allocated when omitted."""
         dev, rows, world = self.device, row_end - row_begin, int(cand_all.shape[0])
         table_rows = int(cand_all.shape[1])
         with torch.cuda.device(dev):
-            t = self._alloc_tables(rows, k, row_begin)
+            t = out if out is not None else self._alloc_tables(rows, k, row_begin)
+            t["row_begin"] = row_begin
             if rows > 0:
                 p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end,
                                  splits=splits, tuning=tuning)
                 ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
                 cout = self._c_tables(t)
-                check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(), cnt_all.data_ptr(),
-                                                  bound_all.data_ptr(), world, int(table_row0), table_rows,
+                check(self.lib.tvbf_rescore_lists(C.byref(cat.c), C.byref(p), cand_all.data_ptr(),
+                                                  None if cnt_all is None else cnt_all.data_ptr(),
+                                                  None if bound_all is None else bound_all.data_ptr(), world,
+                                                  int(table_row0), table_rows,
                                                   C.byref(cout), ws.data_ptr(),
                                                   ws.numel(), self._stream()), "tvbf_rescore_lists")
+            else:
+                self._zero(t["stats"])
         return t
 
     def top_k_device_sym_sharded(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
                                  all_reduce_max, exchange, row_range, splits: int = 0, tuning: int = 0,
-                                 k1_events: list | None = None) -> dict:
+                                 events: dict | None = None, out: dict | None = None,
+                                 padded_rows: int | None = None) -> dict:
         """This GPU's part of the tile-sharded symmetric job: the three phases with the two
         collectives between them passed in as callables: ``all_reduce_max(int32 tensor)`` in place,
-        and ``exchange(tensor [N, ...]) -> tensor [world, rows, ...]`` holding every rank's entries
-        for THIS rank's rows ``row_range`` (an all-to-all over the row shards)."""
-        def mark():
-            if k1_events is None:
-                return None
-            ev = torch.cuda.Event(enable_timing=True)
-            with torch.cuda.device(self.device):
-                ev.record()
-            return ev
+        and ``exchange(packed [world * shard_rows, L + 1, 2]) -> [world, shard_rows, L + 1, 2]``
+        holding every rank's lists for THIS rank's rows ``row_range`` (one all-to-all over the row
+        shards).  ``events``: dict that receives CUDA events around every phase (bench.py)."""
+        def mark(name):
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                with torch.cuda.device(self.device):
+                    ev.record()
+                events.setdefault(name, []).append(ev)
 
-        e0 = mark()
-        theta = self.sym_seed(cat, weights, k, min_similarity, rank, world, splits, tuning)
-        e1 = mark()
-        all_reduce_max(theta)            # raw bits of positive floats order like integers
-        e2 = mark()
-        cand, cnt, bound = self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning)
-        e3 = mark()
-        if k1_events is not None:
-            k1_events.append(((e0, e1), (e2, e3)))
-        cand_all, cnt_all, bound_all = exchange(cand), exchange(cnt), exchange(bound)
         b, e = row_range
-        return self.sym_rescore(cat, weights, k, min_similarity, cand_all, cnt_all, bound_all, b, e, splits, tuning,
-                                table_row0=b)
+        padded_rows = padded_rows or cat.n_shows
+        mark("seed0")
+        theta = self.sym_seed(cat, weights, k, min_similarity, rank, world, splits, tuning)
+        mark("seed1")
+        all_reduce_max(theta)            # raw bits of positive floats order like integers
+        mark("reduce1")
+        packed = self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning,
+                                packed_rows=padded_rows)
+        mark("sweep1")
+        packed_all = exchange(packed)
+        mark("exchange1")
+        t = self.sym_rescore(cat, weights, k, min_similarity, packed_all, None, None, b, e, splits, tuning,
+                             table_row0=b, out=out)
+        mark("rescore1")
+        return t
 
     # ------------------------------------------------------------------------------------ exact
     def exact_rows(self, cat: DeviceCatalogue, rows, weights=(0.4, 0.5, 0.1), k: int = 10,

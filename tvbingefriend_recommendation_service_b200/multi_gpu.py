@@ -1,8 +1,13 @@
-"""Several GPUs of one box: features replicated, source rows sharded in 128-row tiles, result
-tables gathered.  Two drivers over the same shard arithmetic:
+"""Several GPUs of one box: features replicated, result rows sharded, tables gathered
+(SURVEY.md section 8e).  Drivers over the shard arithmetic of ``sharding.py``:
 
-* ``compute_top_k_distributed`` -- one process per GPU under ``torch.distributed`` (NCCL over
-  NVLink); the gather is ``sharding.gather_tables``.  This is what ``bench.py --gpus N`` runs.
+* ``top_k_device_distributed``  -- one process per GPU under ``torch.distributed`` (NCCL over
+  NVLink), device-resident features in, gathered device tables out.  Per job: one all-reduce(MAX) of
+  the seeded thresholds, one all-to-all of the packed candidate rows, one coalesced in-place
+  all-gather of the result tables.  This is what ``bench.py --gpus N`` times as ``value``.
+* ``DistributedTopK``           -- the end-to-end form of the same job (host features in, host table
+  out): every rank uploads 1/world of the feature bytes and NVLink replicates them; every rank copies
+  its shard of the result into ONE pinned host table in shared memory.  ``bench.py``'s ``e2e``.
 * ``compute_top_k_multi_gpu``   -- a single process driving ``device_ids`` (kernels are launched
   asynchronously on every device, tables are read back per shard); convenience for the drop-in
   API's ``device_ids`` argument.
@@ -14,21 +19,14 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .engine import HybridTopKEngine, TopK, stage
-from .sharding import empty_tables, exchange_row_shards, gather_tables, row_shard
+from .engine import HybridTopKEngine, StagedCatalogue, TopK, stage
+from .sharding import (ShardedUpload, SharedHostTable, alloc_full_tables, exchange_packed, gather_full_tables,
+                       row_shard, shard_rows, shard_views)
 
 
-def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float,
-                             exclude_self: bool = True, group=None, symmetric: bool | None = None,
-                             splits: int = 0, tuning: int = 0, k1_events: list | None = None) -> dict:
-    """One job over all ranks of ``group``; every rank returns the full gathered device table.
-
-    * symmetric (default when eligible): tile sharding -- every rank sweeps the tiles on/above the
-      diagonal of its zigzag-dealt 256-row super blocks and feeds both shows of each score; the
-      partial candidate lists go through one all-to-all over the row shards (N x 32 x 8 B sent per
-      rank) and each rank rescores its row shard.  Halves the tensor-core work.
-    * one-sided: row sharding, no exchange before the final gather.
-    """
+def _local_tables(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float, exclude_self: bool, group,
+                  symmetric: bool | None, splits: int, tuning: int, events: dict | None, mine: dict) -> dict:
+    """This rank's rows of the job, written into ``mine`` (views of the gather buffer)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = cat.n_shows
     b, e = row_shard(n, world, rank)
@@ -38,30 +36,99 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
         def all_reduce_max(t):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
 
-        def exchange(t):
-            return exchange_row_shards(t[:n], n, group)
+        def exchange(packed):
+            return exchange_packed(packed, group)
 
-        local = eng.top_k_device_sym_sharded(cat, weights, k, min_similarity, rank, world, all_reduce_max,
-                                             exchange, (b, e), splits=splits, tuning=tuning, k1_events=k1_events)
-    elif e > b:
+        return eng.top_k_device_sym_sharded(cat, weights, k, min_similarity, rank, world, all_reduce_max, exchange,
+                                            (b, e), splits=splits, tuning=tuning, events=events, out=mine,
+                                            padded_rows=world * shard_rows(n, world))
+    if e > b:
         tun = tuning | (1 << 20)
-        if k1_events is None:
-            local = eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e,
-                                     splits=splits, tuning=tun)
-        else:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            local = eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e,
-                                     splits=splits, tuning=tun, phases=1)
-            e1.record()
-            eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e,
-                             splits=splits, tuning=tun, phases=6, out=local)
-            k1_events.append(((e0, e1),))
-    else:
-        local = empty_tables(k, eng.device)
-    full = gather_tables(local, n, k, group)
-    full["row_begin"] = 0
-    return full
+        if events is None:
+            return eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e,
+                                    splits=splits, tuning=tun, out=mine)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e, splits=splits,
+                         tuning=tun, phases=1, out=mine)
+        e1.record()
+        eng.top_k_device(cat, weights, k, min_similarity, exclude_self, row_begin=b, row_end=e, splits=splits,
+                         tuning=tun, phases=6, out=mine)
+        e2.record()
+        for name, ev in (("seed0", e0), ("seed1", e0), ("reduce1", e0), ("sweep1", e1), ("exchange1", e1),
+                         ("rescore1", e2)):
+            events.setdefault(name, []).append(ev)
+        return mine
+    eng._zero(mine["stats"])
+    return mine
+
+
+def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float,
+                             exclude_self: bool = True, group=None, symmetric: bool | None = None,
+                             splits: int = 0, tuning: int = 0, events: dict | None = None) -> dict:
+    """One job over all ranks of ``group``; every rank returns the full gathered device table.
+
+    * symmetric (default when eligible): tile sharding -- every rank sweeps the tiles on/above the
+      diagonal of the super-block groups dealt to it and feeds both shows of each score; the packed
+      partial candidate lists go through ONE all-to-all over the row shards (N x 33 x 8 B sent per
+      rank) and each rank rescores its row shard.  Halves the tensor-core work.
+    * one-sided: row sharding, no exchange before the final gather.
+    """
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = cat.n_shows
+    with torch.cuda.device(eng.device):
+        full = alloc_full_tables(n, k, world, eng.device)
+        mine = shard_views(full, n, world, rank)
+        _local_tables(eng, cat, weights, k, min_similarity, exclude_self, group, symmetric, splits, tuning, events, mine)
+        out = gather_full_tables(full, n, group)
+        if events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            events.setdefault("gather1", []).append(ev)
+    out["row_begin"] = 0
+    return out
+
+
+class DistributedTopK:
+    """End-to-end multi-GPU job with its host-side resources (a shared pinned result table) set up
+    once and reused per call: ``run(staged)`` -> full host ``TopK`` on every rank."""
+
+    def __init__(self, eng: HybridTopKEngine, n_shows: int, k: int, group=None):
+        self.eng, self.group, self.n, self.k = eng, group, n_shows, k
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.upload = ShardedUpload(group)
+        self.table = SharedHostTable(n_shows, k, group)
+        self._prev = None
+
+    def h2d(self, st: StagedCatalogue) -> dict:
+        """1/world of every feature buffer over this rank's PCIe link + one all-gather over NVLink."""
+        dev = self.eng.device
+        with torch.cuda.device(dev):
+            host = [st.text_indptr, st.text_indices, st.text_values, st.genre, *st.meta]
+            d = self.upload(host, dev)
+        return {"st": st, "indptr": d[0], "indices": d[1], "values": d[2], "genre": d[3], "meta": d[4:]}
+
+    def run(self, st: StagedCatalogue, weights=(0.4, 0.5, 0.1), min_similarity: float = 0.1,
+            exclude_self: bool = True, symmetric: bool | None = None, splits: int = 0, tuning: int = 0) -> TopK:
+        eng, n, k = self.eng, self.n, self.k
+        assert st.n_shows == n
+        with torch.cuda.device(eng.device):
+            cat = eng.prepare(self.h2d(st), weights, recycle=self._prev)
+            self._prev = cat
+            full = alloc_full_tables(n, k, self.world, eng.device)
+            mine = shard_views(full, n, self.world, self.rank)
+            _local_tables(eng, cat, weights, k, min_similarity, exclude_self, self.group, symmetric, splits, tuning,
+                          None, mine)
+            self.table.store_shard(mine)
+            torch.cuda.current_stream(eng.device).synchronize()
+        dist.barrier(group=self.group)          # every shard has landed in the shared table
+        h = self.table.numpy()
+        stats = h["stats"].sum(axis=0)
+        return TopK(indices=h["indices"], counts=h["counts"], hybrid=h["hybrid"], genre=h["genre"], text=h["text"],
+                    metadata=h["metadata"], row_begin=0, flagged_rows=int(stats[0]), rescored_pairs=int(stats[1]))
+
+    def close(self) -> None:
+        self.table.close()
 
 
 def compute_top_k_distributed(features: dict, weights=(0.4, 0.5, 0.1), k: int = 20,
