@@ -259,6 +259,85 @@ def dense_text_probe(eng, dc, weights, k, tuning, steps: int = 3) -> dict:
             "operand": "U(0,1) fp16 in every entry (dense), same [N_pad, K_pad] shape"}
 
 
+def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 2) -> dict:
+    """One more BASELINE.json shape in the same run (same kernels, same drivers, device-resident
+    inputs, ``steps`` timed steps after one warm-up): ms per catalogue, K1 ms and executed TFLOP/s."""
+    import torch
+    import torch.distributed as dist
+
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.multi_gpu import top_k_device_distributed
+    from tvbingefriend_recommendation_service_b200.sharding import row_shard
+    from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, make_config
+
+    cfg = CONFIGS[name]
+    cat = make_config(name)
+    n, k = cat.n_shows, cfg["k"]
+    st = stage(cat.features(), "mean3", pin=True)
+    raw = eng.h2d(st)
+    prev = [None]
+
+    def step(events=None):
+        def mark(key):
+            if events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                events.setdefault(key, []).append(ev)
+
+        dc = eng.prepare(raw, weights, recycle=prev[0])
+        prev[0] = dc
+        if world > 1:
+            return top_k_device_distributed(eng, dc, weights, k, 0.1, True, events=events)
+        mark("seed0")
+        t = eng.top_k_device(dc, weights, k, 0.1, True, phases=1)
+        mark("sweep1")
+        eng.top_k_device(dc, weights, k, 0.1, True, phases=6, out=t)
+        return t
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = step()
+    sync()
+    events: dict = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step(events)
+    e1.record()
+    sync()
+    if world > 1:
+        k1 = float(np.mean([a.elapsed_time(b) + c.elapsed_time(d) for a, b, c, d in
+                            zip(events["seed0"], events["seed1"], events["reduce1"], events["sweep1"])]))
+    else:
+        k1 = float(np.mean([a.elapsed_time(b) for a, b in zip(events["seed0"], events["sweep1"])]))
+    t_ms = torch.tensor([e0.elapsed_time(e1) / steps, k1], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dc = prev[0]
+    if world > 1:
+        sharded = n >= 40_000 and eng.sym_eligible(dc, weights, k, 0.1)
+        rb, re_ = row_shard(n, world, 0)
+        plan = eng.plan_tiles(dc, weights, k, 0.1, rank=0, world=world, tile_sharded=True) if sharded else \
+            eng.plan_tiles(dc, weights, k, 0.1, row_begin=rb, row_end=re_, tuning=1 << 20)
+    else:
+        plan = eng.plan_tiles(dc, weights, k, 0.1)
+    stats = out["stats"].cpu().numpy().reshape(-1, 8).sum(axis=0)
+    ms, k1 = t_ms[0].item(), t_ms[1].item()
+    tf = plan["flops"] / (k1 * 1e-3) / 1e12 if k1 > 0 else 0.0
+    res = {"workload": f"{n} shows x vocab {cfg['vocab']} (~{cfg['nnz']} nnz/row), top-{k}, metadata {cfg['meta']}",
+           "ms_per_step": ms, "shows_per_s": n / (ms * 1e-3), "k1_ms": k1, "executed_tflops": tf,
+           "frac": tf / peaks["bf16_tflops_sustained"], "symmetric_sweep": plan["symmetric"],
+           "tiles": plan["seed_tiles"] + plan["sweep_tiles"], "tile": f"{plan['tile_rows']}x256x{int(dc.c.k_pad)}",
+           "flagged_rows": int(stats[0]), "steps": steps}
+    del raw, st, cat, out, dc
+    prev[0] = None
+    eng.release()
+    return res
+
+
 def bench_config(args, cfg) -> dict:
     return {"workload": f"{args.config}: {cfg['n_shows']} synthetic shows, TF-IDF vocab {cfg['vocab']} "
                         f"(~{cfg['nnz']} nnz/row), {cfg['n_genres']} genres, metadata one-hot {cfg['meta']}, "
@@ -282,6 +361,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-dense-probe", action="store_true")
+    ap.add_argument("--extra", default="P80k,C4,C5", help="comma-separated extra configs timed in the same run ('' = none)")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--one-sided", action="store_true", help="disable the symmetric sweep at N > 1")
     ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
@@ -399,11 +479,14 @@ def main() -> None:
     clocks = sampler.stop() if rank == 0 else None
     t_ms = torch.tensor([total_ms, ph["seed"] + ph["sweep"]] + [ph[name] for name in PHASES], device="cuda",
                         dtype=torch.float64)
+    t_min = t_ms.clone()
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
     ms_per_step = t_ms[0].item() / args.steps
     k1_ms_mean = t_ms[1].item()
     phases_max = {name: round(t_ms[2 + i].item(), 4) for i, name in enumerate(PHASES)}
+    phases_min = {name: round(t_min[2 + i].item(), 4) for i, name in enumerate(PHASES)}
 
     # ---- timed region 2: end to end through the public engine API (H2D + compute + D2H) --------
     dtk = None
@@ -433,6 +516,19 @@ def main() -> None:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms_per_step = e2e_ms.item() / args.steps
     d2h = sum(getattr(host_table, f).nbytes for f in ("indices", "counts", "hybrid", "genre", "text", "metadata"))
+
+    extra = {}
+    if args.extra and not args.n_shows:
+        state["prev"] = None
+        del raw
+        if dtk is None:
+            eng.release()
+        for name in [x for x in args.extra.split(",") if x and x != args.config]:
+            try:
+                extra[name] = run_extra(name, eng, args, world, rank, weights, peaks)
+            except Exception as exc:   # an extra must never take the headline down with it
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        raw = eng.h2d(st)
 
     final_table = single_table = value_table = None
     if world > 1 and not args.no_parity_check:     # the device-gathered table of the `value` path as well
@@ -511,9 +607,11 @@ def main() -> None:
                         f"whole-job total) and NVLink all-gathers them; every rank copies its shard of the table "
                         f"into one pinned host table in shared memory (d2h_bytes_per_step is the whole table)"},
         "gpu_launches": int(launches),
-        "phases_ms": phases_max,
+        "phases_ms": phases_max,                 # max over ranks: a collective's entry includes waiting for the slowest rank
+        "phases_ms_min_over_ranks": phases_min,  # ... the minimum is the collective itself
         "clocks": clocks,
         "flagged_rows": flagged, "rescored_pairs": pairs,
+        "extra": extra,
     }
     if not args.no_dense_probe and world == 1:
         dc = eng.prepare(raw, weights)

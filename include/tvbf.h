@@ -263,7 +263,20 @@ int tvbf_matrix_stats_f64(const double* mat, int32_t n, double* out5_host, void*
  *      tvbf_score_pairs).  Text values come from the fp16 operand (relative error <= 1e-3 per
  *      element, correlated per vocabulary column): mean / std agree with float64 to ~1e-5
  *      relative, the median to one bin. */
+/*        ...; double sum_gm (sum of genre * metadata)
+ *      The fp16 text operand limits mean / std of text and hybrid to ~1e-5; tvbf_text_moments below
+ *      delivers the text-dependent sums exactly (float64), from which the caller assembles mean and
+ *      std of text and hybrid to ~1e-9 (engine.similarity_stats). */
 size_t tvbf_stats_accum_bytes(void);
+/* exact float64 moments over ALL (i, j) pairs, no N x N:
+ *   out8 = { sum t, sum t^2 (0 unless with_gram), sum g*t, sum m*t,
+ *            diagonal: sum_i t_ii, sum_i t_ii^2, sum_i g_ii t_ii, sum_i m_ii t_ii }
+ * (t / g / m = text / genre / metadata cosine; strict upper triangle = (all - diagonal) / 2).
+ * with_gram needs a [vocab, vocab] float64 Gram matrix in the workspace (800 MB at V = 10 000).
+ * Packed genre / metadata only.  out8 is a DEVICE pointer. */
+size_t tvbf_text_moments_workspace_bytes(const tvbf_features* f, int32_t with_gram);
+int tvbf_text_moments(const tvbf_features* f, int32_t with_gram, double* out8, void* workspace,
+                      size_t workspace_bytes, void* stream);
 int tvbf_similarity_stats(const tvbf_features* f, const tvbf_params* p, void* accum, void* workspace,
                           size_t workspace_bytes, void* stream);
 /* exact float64 scores of explicit pairs: out4[p] = {hybrid, genre, text, metadata} of

@@ -247,3 +247,42 @@ def test_long_k_moderately_dense_text(engine):
     assert np.array_equal(top.indices, exact.indices) and np.array_equal(top.counts, exact.counts)
     assert top.flagged_rows < 1536      # the certificate still passes rows (not everything repaired)
     assert_topk_matches(top, cat.features(), np.arange(0, 1536, 24), w, 20, 0.1)
+
+
+# ---- scripts/compute_similarities.main against the reference class' golden statistics ----------------------
+@pytest.mark.parametrize("streaming", [False, True], ids=["matrices", "streaming"])
+def test_compute_similarities_main_matches_golden_statistics(engine, tmp_path, caplog, streaming):
+    """The driver of reference scripts/compute_similarities.py:180-262 on the files of the golden
+    catalogue: with the N x N matrices (small catalogue) and with ``--max-matrix-bytes 0``, which
+    forces the streaming statistics that large catalogues get (no N x N anywhere)."""
+    import logging
+
+    from tvbingefriend_recommendation_service_b200.scripts import compute_similarities as cs
+
+    z, cat = load_golden("similarity_computer_n64")
+    cat.save(tmp_path)
+    gw, tw, mw = z["w1_weights"].tolist()
+    argv = ["--input-dir", str(tmp_path), "--output-dir", str(tmp_path / "out"), "--genre-weight", str(gw),
+            "--text-weight", str(tw), "--metadata-weight", str(mw)]
+    with caplog.at_level(logging.INFO):
+        sims = cs.main(argv + (["--max-matrix-bytes", "0"] if streaming else []))
+    names = ("genre_similarity", "text_similarity", "metadata_similarity", "hybrid_similarity")
+    if streaming:
+        assert all(sims[name] is None for name in names)
+        stats = sims["statistics"]
+    else:
+        from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+
+        comp = SimilarityComputer(gw, tw, mw, engine=engine)
+        stats = {name: comp.get_similarity_statistics(sims[name]) for name in names}
+        for name in names:
+            assert np.abs(sims[name] - z[f"w1_{name}"]).max() < 1e-12
+    for name in names:
+        want = dict(zip(("mean", "std", "min", "max", "median"), z[f"w1_{name}_stats"].tolist()))
+        got = stats[name]
+        for key in ("mean", "std", "min", "max"):
+            assert got[key] == pytest.approx(want[key], rel=1e-6, abs=2e-7), (name, key)
+        res = got.get("median_resolution", 0.0) * 1.01 + 1e-12
+        assert abs(got["median"] - want["median"]) <= res, (name, got["median"], want["median"])
+        assert f"{name}:" in caplog.text       # the reference logs the five statistics per matrix (:119-131)
+    assert not (tmp_path / "out").exists()     # nothing saved unless --save-similarities

@@ -106,6 +106,8 @@ SIGNATURES = {
     "tvbf_matrix_stats_f64": (C.c_int, [c_void_p, c_int32, C.POINTER(c_double), c_void_p, c_size_t,
                                         c_void_p]),
     "tvbf_stats_accum_bytes": (c_size_t, []),
+    "tvbf_text_moments_workspace_bytes": (c_size_t, [C.POINTER(Features), c_int32]),
+    "tvbf_text_moments": (C.c_int, [C.POINTER(Features), c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tvbf_similarity_stats": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_void_p, c_size_t,
                                         c_void_p]),
     "tvbf_score_pairs": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_int32, c_void_p, c_void_p]),

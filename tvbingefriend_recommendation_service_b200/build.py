@@ -19,7 +19,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtvbf.so"
 STAMP = PKG / "csrc" / ".build_stamp"
-SOURCES = ["api.cu", "prep.cu", "hybrid_topk.cu", "rescore.cu", "matrix.cu"]
+SOURCES = ["api.cu", "prep.cu", "hybrid_topk.cu", "rescore.cu", "matrix.cu", "moments.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "internal.cuh", PKG.parent / "include" / "tvbf.h"]
 
 NVCC_FLAGS = [

@@ -566,6 +566,12 @@ int make_sym_plan(const tvbf_features* f, const tvbf_params* p, int rank, int wo
   rc = sm_count_cached(&sms);
   if (rc != TVBF_OK) return rc;
   const int clusters = sms / 2;
+  if (p->splits <= 0 && world >= 4) {
+    // 12 column splits x 6 super blocks per wave: the per-GPU walks differ by < 1 % on C3 at 8 GPUs
+    // (8 x 9: 3.5 %); the symmetric sweep keeps one list per show, so more splits cost nothing later
+    pl.splits = 12;
+    while (pl.splits > 1 && (clusters / pl.splits < 1 || pl.col_tiles / pl.splits < 8)) --pl.splits;
+  }
   // One launch wave = one dealt group of R consecutive super blocks x S column splits: the blocks of
   // a wave then differ by < R diagonal tiles (the phantom tiles every item walks for the pacing).
   pl.sb_per_group = clusters / pl.splits;
@@ -614,7 +620,7 @@ int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan&
   (void)rank;
   // a rank that sweeps 1/world of the tiles gets fewer threshold refreshes: seed more densely
   // (measured at world = 8 on C3: stride 48 -> 0.6 + 8.0 ms per rank, stride 96 -> 0.4 + 8.5 ms)
-  if (world >= 2 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
+  if (world >= 4 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
   return TVBF_OK;
 }
 

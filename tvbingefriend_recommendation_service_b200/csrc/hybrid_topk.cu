@@ -430,7 +430,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t it = 0;
     // ---- statistics sweep state (kStats): per-thread fp64 sums, extrema, argmax of text / hybrid,
     // and a CTA-wide histogram in the shared memory of the (unused) last ring stage
-    double st_sum[4] = {0, 0, 0, 0}, st_sq[4] = {0, 0, 0, 0};
+    double st_sum[4] = {0, 0, 0, 0}, st_sq[4] = {0, 0, 0, 0}, st_gm = 0.0;
     float st_min[4] = {3e38f, 3e38f, 3e38f, 3e38f}, st_max[4] = {-1.f, -1.f, -1.f, -1.f};
     unsigned long long st_zero[4] = {0, 0, 0, 0};
     int st_arg_i[2] = {-1, -1}, st_arg_j[2] = {-1, -1};
@@ -568,7 +568,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // off-diagonal tiles also feed the column shows (their mirror tile is never computed)
         const bool do_col = kSym && row_valid && jt != c.sb;
 
-        float tile_sum[4] = {0.f, 0.f, 0.f, 0.f}, tile_sq[4] = {0.f, 0.f, 0.f, 0.f};
+        float tile_sum[4] = {0.f, 0.f, 0.f, 0.f}, tile_sq[4] = {0.f, 0.f, 0.f, 0.f}, tile_gm = 0.f;
         float stat_scale[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) stat_scale[q] = kStats ? static_cast<float>(kStatsBins) / p.stats->hi[q] : 0.f;
@@ -596,6 +596,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   v[1] = a * p.inv_scale2;
                   v[2] = mdot * ci_wm;
                   v[3] = fmaf(p.w_genre, v[0], fmaf(p.w_text_plain, v[1], p.w_meta * v[2]));
+                  tile_gm = fmaf(v[0], v[2], tile_gm);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
                     tile_sum[q] += v[q];
@@ -733,6 +734,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (kStats) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) { st_sum[q] += tile_sum[q]; st_sq[q] += tile_sq[q]; }
+          st_gm += tile_gm;
         }
       }
 
@@ -788,6 +790,12 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             atomicMax(&sa->max_bits[q], __float_as_uint(mx));
           }
         }
+      }
+      {
+        double s = st_gm;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFullMask, s, o);
+        if (lane == 0) atomicAdd(&sa->sum_gm, s);
       }
       // argmax candidates of text (0) and hybrid (1): best of the warp -> one slot per warp
 #pragma unroll
@@ -848,11 +856,16 @@ sym_compact_kernel(const K1Params p, int n_rows) {
     uint32_t v[32], cidx[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
-      const int idx = q * 32 + lane;
-      uint2 e = make_uint2(0u, 0u);
-      if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
-      v[q] = idx < n ? e.x : 0u;
-      cidx[q] = e.y;
+      v[q] = 0u;
+      cidx[q] = 0u;
+      if (q * 32 < n) {   // warp-uniform: short lists (the usual case, and all partial lists of a
+                          // multi-GPU job) touch only the registers they fill
+        const int idx = q * 32 + lane;
+        uint2 e = make_uint2(0u, 0u);
+        if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
+        v[q] = idx < n ? e.x : 0u;
+        cidx[q] = e.y;
+      }
     }
     done += fresh;
     const bool last = done >= n_all;
@@ -864,7 +877,8 @@ sym_compact_kernel(const K1Params p, int n_rows) {
         const uint32_t t = best | (1u << bit);
         int c = 0;
 #pragma unroll
-        for (int q = 0; q < 32; ++q) c += (v[q] >= t);
+        for (int q = 0; q < 32; ++q)
+          if (q * 32 < n) c += (v[q] >= t);
         c = __reduce_add_sync(kFullMask, c);
         if (c >= kp) best = t;
       }
@@ -876,12 +890,14 @@ sym_compact_kernel(const K1Params p, int n_rows) {
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const int idx = q * 32 + lane;
-        const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
-        const unsigned bal = __ballot_sync(kFullMask, take);
-        const int pos = out + __popc(bal & ((1u << lane) - 1u));
-        if (take && pos < kp) out_p[pos] = make_uint2(v[q], cidx[q]);
-        out += __popc(bal);
+        if (q * 32 < n) {
+          const int idx = q * 32 + lane;
+          const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
+          const unsigned bal = __ballot_sync(kFullMask, take);
+          const int pos = out + __popc(bal & ((1u << lane) - 1u));
+          if (take && pos < kp) out_p[pos] = make_uint2(v[q], cidx[q]);
+          out += __popc(bal);
+        }
       }
       if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
     }

@@ -20,6 +20,7 @@ struct StatsAccum {
   int n_cand;                             // reserved
   int cand_ij[2][kStatsCand][2];          // argmax candidates of {text, hybrid}: one slot per epilogue warp
   float cand_val[2][kStatsCand];
+  double sum_gm;                          // sum of genre * metadata (cross moment of the hybrid's variance)
 };
 
 // parameters of the tcgen05 candidate kernel (hybrid_topk.cu)

@@ -729,16 +729,23 @@ class HybridTopKEngine:
     _STATS_DTYPE = np.dtype([("sum", "<f8", 4), ("sumsq", "<f8", 4), ("zeros", "<u8", 4),
                              ("hist", "<u8", (4, 1024)), ("min_bits", "<u4", 4), ("max_bits", "<u4", 4),
                              ("hi", "<f4", 4), ("n_cand", "<i4"), ("cand_ij", "<i4", (2, 2048, 2)),
-                             ("cand_val", "<f4", (2, 2048))], align=True)
+                             ("cand_val", "<f4", (2, 2048)), ("sum_gm", "<f8")], align=True)
 
-    def similarity_stats(self, cat: DeviceCatalogue, weights) -> dict:
+    def similarity_stats(self, cat: DeviceCatalogue, weights, exact_moments: bool = True,
+                         gram_bytes_limit: int | None = None) -> dict:
         """Upper-triangle statistics of the genre / text / metadata / hybrid similarity matrices
         (ml/similarity_computer.py:171-190) WITHOUT materialising them: one symmetric tensor-core
         sweep accumulates sums, extrema, zero counts and 1024-bin histograms on the device; the
-        largest text and hybrid elements are rescored exactly in float64.  mean / std agree with
-        float64 to ~1e-5 relative (the fp16 rounding of the text operand is correlated per vocabulary
-        column; genre / metadata are exact to fp32, so their min / max carry fp32 rounding, +-1.2e-7),
-        median to one histogram bin (range / 1024)."""
+        largest text and hybrid elements are rescored exactly in float64.
+
+        The fp16 text operand alone would limit mean / std of text and hybrid to ~1e-5 (its rounding
+        is correlated per vocabulary column).  With ``exact_moments`` every text-dependent sum --
+        sum t, sum t^2, sum g*t, sum m*t -- is computed exactly in float64 from small Gram-type
+        matrices (``tvbf_text_moments``: column sums, [64, V], [32, V] and, memory permitting, the
+        [V, V] vocabulary Gram matrix) and the hybrid's moments are assembled from them, so mean and
+        std agree with the reference's float64 to ~1e-9 (genre / metadata elements are fp32 values
+        summed in float64: ~1e-8).  min / max: exact zeros and exactly rescored maxima; otherwise the
+        fp32 / fp16 element value.  median to one histogram bin (``median_resolution``)."""
         gw, tw, mw = (float(w) for w in weights)
         p = self._params(cat, (gw, tw, mw), 20, 0.5)
         lib, dev = self.lib, self.device
@@ -764,12 +771,39 @@ class HybridTopKEngine:
                                            self._stream()), "tvbf_score_pairs")
                 o = out4.cpu().numpy()
                 exact_max = {"text_similarity": float(o[:, 2].max()), "hybrid_similarity": float(o[:, 0].max())}
+            moments = None
+            if exact_moments:
+                v = int(cat.c.vocab)
+                free, _tot = torch.cuda.mem_get_info()
+                limit = int(free * 0.5) if gram_bytes_limit is None else int(gram_bytes_limit)
+                with_gram = 1 if 8 * v * v <= limit else 0
+                mb = int(lib.tvbf_text_moments_workspace_bytes(C.byref(cat.c), with_gram))
+                mws = torch.empty((mb,), dtype=torch.uint8, device=dev)
+                out8 = torch.empty((8,), dtype=torch.float64, device=dev)
+                check(lib.tvbf_text_moments(C.byref(cat.c), with_gram, out8.data_ptr(), mws.data_ptr(), mb,
+                                            self._stream()), "tvbf_text_moments")
+                moments = out8.cpu().numpy()
+                del mws
         count = n * (n - 1) // 2
         names = ("genre_similarity", "text_similarity", "metadata_similarity", "hybrid_similarity")
+        s1 = [float(x) for x in raw["sum"]]
+        s2 = [float(x) for x in raw["sumsq"]]
+        exact = {"text_mean": False, "text_std": False}
+        if moments is not None:
+            # strict upper triangle = (all pairs - diagonal) / 2
+            st_, st2, sgt, smt = ((moments[a] - moments[a + 4]) / 2 for a in range(4))
+            s1[1] = st_
+            s1[3] = gw * s1[0] + tw * st_ + mw * s1[2]
+            exact["text_mean"] = True
+            if with_gram:
+                s2[1] = st2
+                s2[3] = (gw * gw * s2[0] + tw * tw * st2 + mw * mw * s2[2] + 2 * gw * tw * sgt
+                         + 2 * gw * mw * float(raw["sum_gm"]) + 2 * tw * mw * smt)
+                exact["text_std"] = True
         out = {}
         for q, name in enumerate(names):
-            mean = float(raw["sum"][q]) / count
-            var = max(0.0, float(raw["sumsq"][q]) / count - mean * mean)
+            mean = s1[q] / count
+            var = max(0.0, s2[q] / count - mean * mean)
             zeros = int(raw["zeros"][q])
             hist = raw["hist"][q].astype(np.int64)
             width = float(raw["hi"][q]) / 1024.0
@@ -787,7 +821,8 @@ class HybridTopKEngine:
             out[name] = {"mean": mean, "std": float(np.sqrt(var)), "min": vmin,
                          "max": exact_max.get(name, vmax),
                          "median": 0.5 * (value_at((count - 1) // 2) + value_at(count // 2)),
-                         "median_resolution": width}
+                         "median_resolution": width,
+                         "exact_moments": dict(exact) if q in (1, 3) else {"text_mean": True, "text_std": True}}
         return out
 
     def plan_tiles(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int = 0, world: int = 1,

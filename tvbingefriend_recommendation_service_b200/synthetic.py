@@ -29,6 +29,10 @@ CONFIGS: dict[str, dict] = {
     "C3": dict(n_shows=100_000, vocab=10_000, nnz=50, n_genres=40, meta=(5, 3, 2), k=20, seed=20263),
     "C4": dict(n_shows=250_000, vocab=10_000, nnz=50, n_genres=40, meta=(21, 5, 6), k=20, seed=20264),
     "C5": dict(n_shows=200_000, vocab=50_000, nnz=60, n_genres=40, meta=(21, 5, 6), k=100, seed=20265),
+    # the reference's real production run: ~80 k shows, max_text_features default 500
+    # (scripts/compute_features.py:174; README.md:254-258 "60-90 min"), ~96 % sparse text (notebook 02),
+    # reference default metadata widths 21 / 5 / 6
+    "P80k": dict(n_shows=80_000, vocab=500, nnz=20, n_genres=40, meta=(21, 5, 6), k=20, seed=20266),
 }
 
 # Weight schemes of the reference's notebook (notebooks/03_content_similarity cell 6), used by C5.
