@@ -168,6 +168,24 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
                        const uint8_t* language, int32_t l_dim, int32_t n_rows, int32_t n_pad,
                        int32_t meta_kind, void* col_side, float* meta_scale, void* stream);
 
+/* ---- device-side ingest of the raw arrays of compute_features.py:115-129 (what np.load / load_npz
+ *      hand over: int64 multi-hot genres, float64 / bool one-hots, a scipy CSR with int32 or int64
+ *      index arrays): classification and narrowing happen on the GPU, the host only copies bytes.
+ *      dtype codes: 0 uint8 / bool, 1 int32, 2 int64, 3 float32, 4 float64.  `flags` is one device
+ *      int32 the kernels OR into: 1 genre not {0,1}-valued, 2 metadata not one-hot, 4 CSR rows not
+ *      strictly ascending (unsorted / duplicates), 8 negative text values.  With 1 or 2 set the
+ *      packed words are meaningless and the caller takes the general (folded float) path. */
+int tvbf_ingest_genre(const void* raw, int32_t dtype, int32_t n_rows, int32_t n_pad, int32_t dim, void* col_side,
+                      int32_t* flags, void* stream);
+int tvbf_ingest_meta(const void* platform, int32_t p_dtype, int32_t p_dim, const void* type, int32_t t_dtype,
+                     int32_t t_dim, const void* language, int32_t l_dtype, int32_t l_dim, int32_t n_rows,
+                     int32_t n_pad, int32_t meta_kind, void* col_side, float* meta_scale, int32_t* flags,
+                     void* stream);
+/* raw CSR -> int64 indptr[n_rows + 1], int32 indices, float64 values (not yet normalised) */
+int tvbf_ingest_csr(const void* indptr_raw, int32_t indptr64, const void* indices_raw, int32_t indices64,
+                    const void* values_raw, int32_t values64, int32_t n_rows, int64_t* indptr, int32_t* indices,
+                    double* values, int32_t* flags, void* stream);
+
 /* ---- K1+K4+K5(+K6): hybrid all-pairs score -> per-row top-K
  *      (replaces the loop populate_database.py:170-218 and content_based_service.py:293-308) - */
 size_t tvbf_topk_workspace_bytes(const tvbf_features* f, const tvbf_params* p);

@@ -286,3 +286,75 @@ def test_compute_similarities_main_matches_golden_statistics(engine, tmp_path, c
         assert abs(got["median"] - want["median"]) <= res, (name, got["median"], want["median"])
         assert f"{name}:" in caplog.text       # the reference logs the five statistics per matrix (:119-131)
     assert not (tmp_path / "out").exists()     # nothing saved unless --save-similarities
+
+
+# ---- device-side ingest -----------------------------------------------------------
+def test_ingest_equals_host_staging(engine):
+    """Raw arrays classified / narrowed / packed on the GPU == the host-staged catalogue, for the dtypes
+    compute_features.py writes and the variations numpy / scipy can hand over."""
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(2500, 700, nnz=15, seed=21)
+    base = cat.features()
+    ref = engine.upload(stage(base, "mean3"))
+    variants = {"as written": base}
+    v2 = dict(base)
+    v2["genre_features"] = base["genre_features"].astype(np.float32)
+    v2["platform_features"] = base["platform_features"].astype(np.int32)
+    v2["type_features"] = base["type_features"].astype(np.uint8)
+    t = base["text_features"].astype(np.float32).astype(np.float64)      # values exactly representable in fp32
+    v2["text_features"] = sp.csr_matrix((t.data.astype(np.float32), t.indices.astype(np.int64), t.indptr.astype(np.int64)),
+                                        shape=t.shape)
+    base32 = dict(base)
+    base32["text_features"] = t
+    ref32 = engine.upload(stage(base32, "mean3"))
+    variants["other dtypes"] = v2
+    for name, f in variants.items():
+        dc = engine.ingest(f, "mean3")
+        want = ref if name == "as written" else ref32
+        for i in (0, 1, 2, 3, 4, 5):          # indptr, indices, values, operand, col_side, meta_scale
+            a, b = dc.keep[i].cpu().numpy(), want.keep[i].cpu().numpy()
+            assert a.dtype == b.dtype and np.array_equal(a, b), (name, i)
+        assert dc.c.text_signed == 0 and not dc.folded
+
+
+def test_ingest_falls_back_for_inputs_the_packed_path_cannot_take(engine):
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(900, 300, nnz=10, seed=22)
+    f = cat.features()
+    # (1) a genre value that is not 0/1 -> general float path (folded into the operand)
+    g = dict(f)
+    g["genre_features"] = f["genre_features"].astype(np.float64)
+    g["genre_features"][5, 3] = 0.5
+    dc = engine.ingest(g, "mean3")
+    assert dc.folded
+    assert_topk_matches(engine.compute_top_k(g, (0.4, 0.5, 0.1), 20, 0.1), g)
+    # (2) two ones in a one-hot row -> general float path
+    m = dict(f)
+    m["platform_features"] = f["platform_features"].copy()
+    m["platform_features"][7, :2] = 1.0
+    assert engine.ingest(m, "mean3").folded
+    assert_topk_matches(engine.compute_top_k(m, (0.4, 0.5, 0.1), 20, 0.1), m)
+    # (3) CSR with unsorted indices and duplicates -> canonicalised on the host, same table
+    t = f["text_features"].tocoo()
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(t.nnz)
+    rows, cols, vals = t.row[perm], t.col[perm], t.data[perm]
+    rows = np.concatenate([rows, rows[:50]])
+    cols = np.concatenate([cols, cols[:50]])
+    vals = np.concatenate([vals * 1.0, np.zeros(50)])
+    order = np.argsort(rows, kind="stable")
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=900))])
+    messy = sp.csr_matrix((vals[order], cols[order], indptr), shape=t.shape)
+    assert not messy.has_canonical_format
+    u = dict(f)
+    u["text_features"] = messy
+    a = engine.compute_top_k(u, (0.4, 0.5, 0.1), 20, 0.1)
+    b = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.1)
+    assert np.array_equal(a.indices, b.indices) and np.allclose(a.hybrid[a.indices >= 0], b.hybrid[b.indices >= 0], rtol=1e-14)
+    # (4) negative text values are detected on the device
+    s_ = dict(f)
+    s_["text_features"] = sp.csr_matrix(np.random.default_rng(4).standard_normal((900, 48)))
+    assert engine.ingest(s_, "mean3").c.text_signed == 1

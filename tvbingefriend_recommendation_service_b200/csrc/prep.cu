@@ -138,6 +138,116 @@ __global__ void meta_bits_kernel(const uint8_t* __restrict__ platform, int p_dim
   meta_scale[row] = s;
 }
 
+// ---- device-side ingest of the raw feature arrays (any of the dtypes numpy hands over) --------------
+// dtype codes of the raw arrays: 0 uint8 / bool, 1 int32, 2 int64, 3 float32, 4 float64
+__device__ __forceinline__ double load_raw(const void* p, int dtype, size_t i) {
+  switch (dtype) {
+    case 0: return static_cast<double>(static_cast<const uint8_t*>(p)[i]);
+    case 1: return static_cast<double>(static_cast<const int32_t*>(p)[i]);
+    case 2: return static_cast<double>(static_cast<const int64_t*>(p)[i]);
+    case 3: return static_cast<double>(static_cast<const float*>(p)[i]);
+    default: return static_cast<const double*>(p)[i];
+  }
+}
+
+enum { INGEST_NOT_BINARY = 1, INGEST_NOT_ONE_HOT = 2, INGEST_NOT_CANONICAL = 4, INGEST_NEGATIVE_TEXT = 8 };
+
+// genre multi-hot of any dtype -> col_side[].genre_bits / genre_rnorm; flags |= NOT_BINARY when a
+// value is neither 0 nor 1 (the caller then takes the general float path)
+__global__ void ingest_genre_kernel(const void* __restrict__ raw, int dtype, int n_rows, int n_pad, int dim,
+                                    TvbfColSide* __restrict__ col_side, int* __restrict__ flags) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_pad) return;
+  unsigned long long bits = 0ull;
+  bool bad = false;
+  if (row < n_rows)
+    for (int c = 0; c < dim; ++c) {
+      const double v = load_raw(raw, dtype, static_cast<size_t>(row) * dim + c);
+      bad |= !(v == 0.0 || v == 1.0);
+      if (v != 0.0) bits |= 1ull << c;
+    }
+  const int pc = __popcll(bits);
+  col_side[row].genre_bits = bits;
+  col_side[row].genre_rnorm = pc ? 1.0f / sqrtf(static_cast<float>(pc)) : 0.0f;
+  if (bad) atomicOr(flags, INGEST_NOT_BINARY);
+}
+
+__device__ __forceinline__ uint32_t ingest_group(const void* raw, int dtype, int dim, int row, int offset, bool* bad) {
+  uint32_t bits = 0u;
+  int ones = 0;
+  for (int c = 0; c < dim; ++c) {
+    const double v = load_raw(raw, dtype, static_cast<size_t>(row) * dim + c);
+    *bad |= !(v == 0.0 || v == 1.0);
+    if (v != 0.0) { bits |= 1u << (offset + c); ++ones; }
+  }
+  *bad |= ones > 1;
+  return bits;
+}
+
+// platform / type / language one-hot rows of any dtype -> col_side[].meta_bits and meta_scale[];
+// flags |= NOT_ONE_HOT when a row is not {0,1}-valued with at most one 1 per group
+__global__ void ingest_meta_kernel(const void* __restrict__ platform, int p_dtype, int p_dim,
+                                   const void* __restrict__ type, int t_dtype, int t_dim,
+                                   const void* __restrict__ language, int l_dtype, int l_dim, int n_rows,
+                                   int n_pad, int meta_kind, TvbfColSide* __restrict__ col_side,
+                                   float* __restrict__ meta_scale, int* __restrict__ flags) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_pad) return;
+  uint32_t bits = 0u;
+  bool bad = false;
+  if (row < n_rows)
+    bits = ingest_group(platform, p_dtype, p_dim, row, 0, &bad) |
+           ingest_group(type, t_dtype, t_dim, row, p_dim, &bad) |
+           ingest_group(language, l_dtype, l_dim, row, p_dim + t_dim, &bad);
+  col_side[row].meta_bits = bits;
+  const int valid = __popc(bits);
+  float s;
+  if (row >= n_rows) s = 0.0f;
+  else if (meta_kind == TVBF_META_MEAN3) s = 0.57735026918962576f;
+  else s = valid ? 1.0f / sqrtf(static_cast<float>(valid)) : 0.0f;
+  meta_scale[row] = s;
+  if (bad) atomicOr(flags, INGEST_NOT_ONE_HOT);
+}
+
+// text CSR as scipy hands it over (int32 or int64 indptr / indices, float32 or float64 data) ->
+// int64 indptr, int32 indices, float64 values; flags |= NOT_CANONICAL when a row's column indices
+// are not strictly ascending (unsorted or duplicated), NEGATIVE_TEXT when a value is negative
+__global__ void ingest_csr_kernel(const void* __restrict__ indptr_raw, int indptr64,
+                                  const void* __restrict__ indices_raw, int indices64,
+                                  const void* __restrict__ values_raw, int values64, int n_rows,
+                                  int64_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                                  double* __restrict__ values, int* __restrict__ flags) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row > n_rows) return;
+  auto ptr_at = [&](int r) -> int64_t {
+    return indptr64 ? static_cast<const int64_t*>(indptr_raw)[r]
+                    : static_cast<int64_t>(static_cast<const int32_t*>(indptr_raw)[r]);
+  };
+  if (row == n_rows) {
+    if (lane == 0) indptr[n_rows] = ptr_at(n_rows);
+    return;
+  }
+  const int64_t b = ptr_at(row), e = ptr_at(row + 1);
+  if (lane == 0) indptr[row] = b;
+  int bad = 0;
+  for (int64_t i = b + lane; i < e; i += 32) {
+    const int64_t c = indices64 ? static_cast<const int64_t*>(indices_raw)[i]
+                                : static_cast<int64_t>(static_cast<const int32_t*>(indices_raw)[i]);
+    const double v = values64 ? static_cast<const double*>(values_raw)[i]
+                              : static_cast<double>(static_cast<const float*>(values_raw)[i]);
+    if (i > b) {
+      const int64_t prev = indices64 ? static_cast<const int64_t*>(indices_raw)[i - 1]
+                                     : static_cast<int64_t>(static_cast<const int32_t*>(indices_raw)[i - 1]);
+      if (prev >= c) bad |= INGEST_NOT_CANONICAL;
+    }
+    if (v < 0.0) bad |= INGEST_NEGATIVE_TEXT;
+    indices[i] = static_cast<int32_t>(c);
+    values[i] = v;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
 __global__ void csr_to_dense_kernel(const int64_t* __restrict__ indptr,
                                     const int32_t* __restrict__ indices,
                                     const double* __restrict__ values, int n_rows, int dim,
@@ -274,6 +384,46 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
       platform, p_dim, type, t_dim, language, l_dim, n_rows, n_pad, meta_kind,
       static_cast<TvbfColSide*>(col_side), meta_scale);
   TVBF_LAUNCH_OK("meta_bits_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_ingest_genre(const void* raw, int32_t dtype, int32_t n_rows, int32_t n_pad, int32_t dim, void* col_side,
+                      int32_t* flags, void* stream) {
+  TVBF_REQUIRE(raw && col_side && flags && n_rows >= 0 && n_pad >= n_rows, "tvbf_ingest_genre: bad arguments");
+  TVBF_REQUIRE(dim >= 1 && dim <= 64, "tvbf_ingest_genre: dim %d outside 1..64", dim);
+  TVBF_REQUIRE(dtype >= 0 && dtype <= 4, "tvbf_ingest_genre: bad dtype code %d", dtype);
+  if (n_pad == 0) return TVBF_OK;
+  ingest_genre_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      raw, dtype, n_rows, n_pad, dim, static_cast<TvbfColSide*>(col_side), flags);
+  TVBF_LAUNCH_OK("ingest_genre_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_ingest_meta(const void* platform, int32_t p_dtype, int32_t p_dim, const void* type, int32_t t_dtype,
+                     int32_t t_dim, const void* language, int32_t l_dtype, int32_t l_dim, int32_t n_rows,
+                     int32_t n_pad, int32_t meta_kind, void* col_side, float* meta_scale, int32_t* flags,
+                     void* stream) {
+  TVBF_REQUIRE(platform && type && language && col_side && meta_scale && flags && n_rows >= 0 && n_pad >= n_rows,
+               "tvbf_ingest_meta: bad arguments");
+  TVBF_REQUIRE(p_dim >= 0 && t_dim >= 0 && l_dim >= 0 && p_dim + t_dim + l_dim <= 32,
+               "tvbf_ingest_meta: the three one-hot groups must fit 32 bits together");
+  TVBF_REQUIRE(meta_kind == TVBF_META_MEAN3 || meta_kind == TVBF_META_HSTACK, "tvbf_ingest_meta: bad meta_kind");
+  if (n_pad == 0) return TVBF_OK;
+  ingest_meta_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      platform, p_dtype, p_dim, type, t_dtype, t_dim, language, l_dtype, l_dim, n_rows, n_pad, meta_kind,
+      static_cast<TvbfColSide*>(col_side), meta_scale, flags);
+  TVBF_LAUNCH_OK("ingest_meta_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_ingest_csr(const void* indptr_raw, int32_t indptr64, const void* indices_raw, int32_t indices64,
+                    const void* values_raw, int32_t values64, int32_t n_rows, int64_t* indptr, int32_t* indices,
+                    double* values, int32_t* flags, void* stream) {
+  TVBF_REQUIRE(indptr_raw && indptr && flags && n_rows >= 0, "tvbf_ingest_csr: bad arguments");
+  ingest_csr_kernel<<<blocks_for((static_cast<size_t>(n_rows) + 1) * 32, 256), 256, 0,
+                      static_cast<cudaStream_t>(stream)>>>(indptr_raw, indptr64, indices_raw, indices64, values_raw,
+                                                           values64, n_rows, indptr, indices, values, flags);
+  TVBF_LAUNCH_OK("ingest_csr_kernel");
   return TVBF_OK;
 }
 

@@ -178,7 +178,13 @@ class TopK:
         """Flat columnar records (one per kept pair, in table order) for a bulk sink
         (repos/similarity_repository.py:72-108 row shape) without building N*k dicts."""
         ids = self._ids(show_ids)
-        mask = np.arange(self.k)[None, :] < self.counts[:, None]
+        n, k = self.indices.shape
+        if n and int(self.counts.min()) == k:      # every show has k neighbours: plain reshapes, no masks
+            return {"show_id": np.repeat(ids[self.row_begin:self.row_begin + n], k),
+                    "similar_show_id": ids[self.indices.reshape(-1)],
+                    "similarity_score": self.hybrid.reshape(-1), "genre_score": self.genre.reshape(-1),
+                    "text_score": self.text.reshape(-1), "metadata_score": self.metadata.reshape(-1)}
+        mask = np.arange(k)[None, :] < self.counts[:, None]
         rows = np.nonzero(mask)[0]
         return {"show_id": ids[self.row_begin + rows],
                 "similar_show_id": ids[self.indices[mask]],
@@ -278,32 +284,14 @@ class HybridTopKEngine:
                 # a catalogue without any text: the C ABI wants non-NULL arrays, which are never read
                 indices = torch.zeros((1,), dtype=torch.int32, device=dev)
                 rawv = torch.zeros((1,), dtype=torch.float64, device=dev)
-            values = torch.empty_like(rawv)
-            operand = None
-            if (recycle is not None and recycle.operand is not None and not recycle.folded and folded_dims == 0
-                    and tuple(recycle.operand.shape) == (n_pad, k_pad) and recycle.operand.dtype == tdt
-                    and recycle.operand.device == dev):
-                operand = recycle.operand
-                check(lib.tvbf_prep_clear_csr_positions(recycle.text_indptr.data_ptr(), recycle.text_indices.data_ptr(),
-                                                        recycle.n_shows, operand.data_ptr(), k_pad, 0, code, stream),
-                      "tvbf_prep_clear_csr_positions")
-                recycle.operand = None          # ownership moved: the old catalogue must not be used again
-                recycle.c.operand = None
-                recycle.keep.clear()
-            if operand is None:
-                operand = torch.empty((n_pad, k_pad), dtype=tdt, device=dev)
-                self._zero(operand)
+            values, operand = self._text_operand(indptr, indices, rawv, n, n_pad, k_pad, recycle,
+                                                 folded=folded_dims > 0)
             col_side = torch.empty((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
             meta_scale = torch.empty((n_pad,), dtype=torch.float32, device=dev)
             self._zero(col_side)
             self._zero(meta_scale)
             keep += [indptr, indices, values, operand, col_side, meta_scale]
-            check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), rawv.data_ptr(), n, values.data_ptr(), stream),
-                  "tvbf_prep_csr_normalize")
             scale = float(2 ** TEXT_SCALE_LOG2)
-            check(lib.tvbf_prep_csr_to_operand(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n,
-                                               operand.data_ptr(), k_pad, 0, scale, code, stream),
-                  "tvbf_prep_csr_to_operand")
 
             f = Features()
             f.n_shows, f.n_pad, f.k_pad, f.text_dtype = n, n_pad, k_pad, code
@@ -363,6 +351,143 @@ class HybridTopKEngine:
         return DeviceCatalogue(c=f, n_shows=n, folded=folded,
                                weights_baked=(gw, tw, mw) if folded else None, keep=keep,
                                operand=operand, text_indptr=indptr, text_indices=indices)
+
+    # ------------------------------------------------------------------------------------ device-side ingest
+    _RAW_DTYPES = {np.dtype(np.bool_): 0, np.dtype(np.uint8): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2,
+                   np.dtype(np.float32): 3, np.dtype(np.float64): 4}
+
+    def _stage_bytes(self, name: str, arr: np.ndarray) -> torch.Tensor:
+        """Copy ``arr``'s bytes into a cached pinned buffer and start the H2D copy; returns the device
+        bytes (uint8).  The pinned buffers are reused from call to call (no page-locking per job)."""
+        import warnings
+
+        a = np.ascontiguousarray(arr)
+        nbytes = a.nbytes
+        buf = self._pinned.get(("raw", name))
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty((max(nbytes, 1),), dtype=torch.uint8, pin_memory=True)
+            self._pinned[("raw", name)] = buf
+        dev = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=self.device)
+        if nbytes:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")          # read-only arrays (np.load with mmap_mode) are fine here
+                src = torch.from_numpy(a.reshape(-1).view(np.uint8))
+            buf[:nbytes].copy_(src)
+            dev[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+        return dev
+
+    def ingest(self, features: dict, metadata_mode: str = "mean3",
+               weights: tuple[float, float, float] = (0.4, 0.5, 0.1),
+               recycle: DeviceCatalogue | None = None) -> DeviceCatalogue:
+        """features dict (as ``np.load`` / ``load_npz`` hand it over) -> device catalogue with the
+        classification and narrowing done ON THE GPU: the host only copies
+        the raw bytes -- int64 multi-hot genres, float64 / bool one-hots, the CSR arrays in whatever
+        index width scipy chose -- through cached pinned buffers; kernels check {0,1}-valuedness /
+        one-hotness / sortedness / sign while they pack, and one int32 of flags comes back.  Inputs
+        the packed path cannot take (general float groups, more than 64 genre or 32 metadata
+        columns, exotic dtypes) go through the host ``stage()`` as before."""
+        if metadata_mode not in ("mean3", "hstack"):
+            raise ValueError(f"metadata_mode must be 'mean3' or 'hstack', got {metadata_mode!r}")
+        genre = np.asarray(features["genre_features"])
+        text = features["text_features"]
+        groups = [np.asarray(features[k_]) for k_ in ("platform_features", "type_features", "language_features")]
+
+        def slow():
+            return self.upload(stage(features, metadata_mode), weights, recycle)
+
+        if not (sp.issparse(text) and text.format == "csr"):
+            return slow()
+        ok = genre.ndim == 2 and 1 <= genre.shape[1] <= 64 and genre.dtype in self._RAW_DTYPES
+        ok = ok and all(a.ndim == 2 and a.dtype in self._RAW_DTYPES for a in groups)
+        ok = ok and sum(a.shape[1] for a in groups) <= 32 and all(a.shape[1] >= 1 for a in groups)
+        ok = ok and text.data.dtype in (np.float32, np.float64) and text.indptr.dtype in (np.int32, np.int64) \
+            and text.indices.dtype in (np.int32, np.int64)
+        if not ok:
+            return slow()
+        n = int(genre.shape[0])
+        for name, a in (("text", text), ("platform", groups[0]), ("type", groups[1]), ("language", groups[2])):
+            if a.shape[0] != n:
+                raise ValueError(f"{name}_features has {a.shape[0]} rows, genre_features has {n}")
+        lib, dev = self.lib, self.device
+        v = int(text.shape[1])
+        nnz = int(text.indptr[-1])
+        n_pad = (n + 255) // 256 * 256
+        kind = _lib.META_MEAN3 if metadata_mode == "mean3" else _lib.META_HSTACK
+        with torch.cuda.device(dev):
+            stream = self._stream()
+            d_indptr = self._stage_bytes("indptr", text.indptr)
+            d_indices = self._stage_bytes("indices", text.indices[:nnz])
+            d_values = self._stage_bytes("values", text.data[:nnz])
+            d_genre = self._stage_bytes("genre", genre)
+            d_groups = [self._stage_bytes(f"meta{g}", a) for g, a in enumerate(groups)]
+            flags = torch.empty((1,), dtype=torch.int32, device=dev)
+            self._zero(flags)
+            indptr = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+            indices = torch.empty((max(nnz, 1),), dtype=torch.int32, device=dev)
+            rawv = torch.empty((max(nnz, 1),), dtype=torch.float64, device=dev)
+            col_side = torch.empty((n_pad, 2), dtype=torch.int64, device=dev)
+            meta_scale = torch.empty((n_pad,), dtype=torch.float32, device=dev)
+            check(lib.tvbf_ingest_csr(d_indptr.data_ptr(), int(text.indptr.dtype == np.int64), d_indices.data_ptr(),
+                                      int(text.indices.dtype == np.int64), d_values.data_ptr(),
+                                      int(text.data.dtype == np.float64), n, indptr.data_ptr(), indices.data_ptr(),
+                                      rawv.data_ptr(), flags.data_ptr(), stream), "tvbf_ingest_csr")
+            check(lib.tvbf_ingest_genre(d_genre.data_ptr(), self._RAW_DTYPES[genre.dtype], n, n_pad, int(genre.shape[1]),
+                                        col_side.data_ptr(), flags.data_ptr(), stream), "tvbf_ingest_genre")
+            g0, g1, g2 = groups
+            check(lib.tvbf_ingest_meta(d_groups[0].data_ptr(), self._RAW_DTYPES[g0.dtype], int(g0.shape[1]),
+                                       d_groups[1].data_ptr(), self._RAW_DTYPES[g1.dtype], int(g1.shape[1]),
+                                       d_groups[2].data_ptr(), self._RAW_DTYPES[g2.dtype], int(g2.shape[1]), n, n_pad,
+                                       kind, col_side.data_ptr(), meta_scale.data_ptr(), flags.data_ptr(), stream),
+                  "tvbf_ingest_meta")
+            bits = int(flags.item())           # the one synchronisation of the ingest
+            if bits & 7:
+                # not binary / not one-hot -> general float path; unsorted or duplicated CSR entries ->
+                # scipy canonicalises on the host (both rare: compute_features.py writes neither)
+                return slow()
+            code, tdt = _DTYPES[self.text_dtype]
+            k_pad = max(64, (v + 63) // 64 * 64)
+            values, operand = self._text_operand(indptr, indices, rawv, n, n_pad, k_pad, recycle)
+            f = Features()
+            f.n_shows, f.n_pad, f.k_pad, f.text_dtype = n, n_pad, k_pad, code
+            f.text_scale_log2, f.vocab = TEXT_SCALE_LOG2, v
+            f.operand = operand.data_ptr()
+            f.text_indptr, f.text_indices, f.text_values = indptr.data_ptr(), indices.data_ptr(), values.data_ptr()
+            f.col_side, f.meta_scale = col_side.data_ptr(), meta_scale.data_ptr()
+            f.meta_kind = kind
+            f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(genre.shape[1])
+            f.meta_mode = _lib.GROUP_PACKED
+            f.text_signed = int(bool(bits & 8))
+        return DeviceCatalogue(c=f, n_shows=n, folded=False, weights_baked=None,
+                               keep=[indptr, indices, values, operand, col_side, meta_scale],
+                               operand=operand, text_indptr=indptr, text_indices=indices)
+
+    def _text_operand(self, indptr, indices, rawv, n: int, n_pad: int, k_pad: int,
+                      recycle: DeviceCatalogue | None, folded: bool = False):
+        """fp64 row normalisation of the CSR values + the fp16 / bf16 tensor-core operand (fresh and
+        zeroed, or ``recycle``'s with its old positions cleared)."""
+        lib, dev, stream = self.lib, self.device, self._stream()
+        code, tdt = _DTYPES[self.text_dtype]
+        values = torch.empty_like(rawv)
+        operand = None
+        if (recycle is not None and recycle.operand is not None and not recycle.folded and not folded
+                and tuple(recycle.operand.shape) == (n_pad, k_pad) and recycle.operand.dtype == tdt
+                and recycle.operand.device == dev):
+            operand = recycle.operand
+            check(lib.tvbf_prep_clear_csr_positions(recycle.text_indptr.data_ptr(), recycle.text_indices.data_ptr(),
+                                                    recycle.n_shows, operand.data_ptr(), k_pad, 0, code, stream),
+                  "tvbf_prep_clear_csr_positions")
+            recycle.operand = None          # ownership moved: the old catalogue must not be used again
+            recycle.c.operand = None
+            recycle.keep.clear()
+        if operand is None:
+            operand = torch.empty((n_pad, k_pad), dtype=tdt, device=dev)
+            self._zero(operand)
+        check(lib.tvbf_prep_csr_normalize(indptr.data_ptr(), rawv.data_ptr(), n, values.data_ptr(), stream),
+              "tvbf_prep_csr_normalize")
+        check(lib.tvbf_prep_csr_to_operand(indptr.data_ptr(), indices.data_ptr(), values.data_ptr(), n,
+                                           operand.data_ptr(), k_pad, 0, float(2 ** TEXT_SCALE_LOG2), code, stream),
+              "tvbf_prep_csr_to_operand")
+        return values, operand
 
     # ------------------------------------------------------------------------------------ top-k
     _TABLE_FIELDS = ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")
@@ -462,9 +587,9 @@ class HybridTopKEngine:
         triples = [tuple(float(x) for x in w) for w in weight_list]
         if not triples:
             return []
-        st = stage(features, metadata_mode)
-        cat = self.upload(st, triples[0])
+        cat = self.ingest(features, metadata_mode, triples[0])
         if cat.folded:   # weights are baked into the operand: one upload per triple
+            st = stage(features, metadata_mode)
             return [self.to_host(self.top_k_device(self.upload(st, w), w, k, min_similarity, exclude_self, **kw))
                     for w in triples]
         return [self.to_host(t) for t in self.top_k_sweep_device(cat, triples, k, min_similarity, exclude_self, **kw)]
@@ -497,8 +622,9 @@ class HybridTopKEngine:
 
     def compute_top_k(self, features: dict, weights=(0.4, 0.5, 0.1), k: int = 20, min_similarity: float = 0.1,
                       metadata_mode: str = "mean3", exclude_self: bool = True, **kw) -> TopK:
-        """features dict -> TopK for all rows on this GPU."""
-        cat = self.upload(stage(features, metadata_mode), weights)
+        """features dict -> TopK for all rows on this GPU (raw bytes up, classified and packed on the
+        device: ``ingest``)."""
+        cat = self.ingest(features, metadata_mode, weights)
         return self.to_host(self.top_k_device(cat, weights, k, min_similarity, exclude_self, **kw))
 
     # ------------------------------------------------------------------------------------ several GPUs

@@ -102,11 +102,9 @@ class SimilarityComputer:
         this class' conventions: hstack metadata, normalised weights).  mean / std / min / max as
         the reference's, median to ``median_resolution``.  Needs binary genre and one-hot metadata
         features."""
-        from ..engine import stage
-
         weights = self._normalized_weights() if normalize_weights else \
             (self.genre_weight, self.text_weight, self.metadata_weight)
-        cat = self.engine.upload(stage(features, metadata_mode), weights)
+        cat = self.engine.ingest(features, metadata_mode, weights)
         return self.engine.similarity_stats(cat, weights)
 
     # ---- production variant: no N x N ------------------------------------------------------------

@@ -22,7 +22,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from ..engine import HybridTopKEngine, default_engine, stage
+from ..engine import HybridTopKEngine, default_engine
 from ..sinks import InMemorySimilaritySink
 
 logger = logging.getLogger(__name__)
@@ -111,7 +111,7 @@ class ContentBasedRecommendationService:
             logger.info(f"✓ Loaded similarity matrices: {tuple(g.shape)}")
         elif all((data_dir / f).exists() for f in _FEATURE_FILES):
             feats = load_feature_files(data_dir)
-            self._catalogue = self.engine.upload(stage(feats, "hstack"), self._weights())
+            self._catalogue = self.engine.ingest(feats, "hstack", self._weights())
             self._mode = "features"
             logger.info(f"✓ Prepared features for {self._catalogue.n_shows} shows on {self.engine.device}")
         else:
