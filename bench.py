@@ -259,7 +259,50 @@ def dense_text_probe(eng, dc, weights, k, tuning, steps: int = 3) -> dict:
             "operand": "U(0,1) fp16 in every entry (dense), same [N_pad, K_pad] shape"}
 
 
-def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 2) -> dict:
+def nxn_variant(eng, weights, names=("C1", "C2")) -> dict:
+    """The reference's full-matrix variant (SimilarityComputer.compute_all_similarities,
+    ml/similarity_computer.py:132-169: four N x N float64 matrices) on the GPU, beside the survey's
+    CPU figures for the same shapes (0.08 s at N = 1 000, 30.6 s at N = 20 000)."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+    comp = SimilarityComputer(*weights, engine=eng)
+    out = {}
+    for name in names:
+        cat = make_config(name)
+        f = cat.features()
+        n = cat.n_shows
+        free, _ = torch.cuda.mem_get_info()
+        if 32 * n * n > 0.5 * free:
+            out[name] = {"skipped": "4 N x N float64 matrices do not fit"}
+            continue
+        res = {}
+        for it in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            g = eng.cosine_matrix(f["genre_features"])
+            t = eng.cosine_matrix(f["text_features"])
+            m = eng.cosine_matrix(np.hstack([f["platform_features"], f["type_features"], f["language_features"]]))
+            gw, tw, mw = comp._normalized_weights()
+            h = eng.hybrid_combine(g, t, m, gw, tw, mw)
+            e1.record()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            res = {"n_shows": n, "device_ms": e0.elapsed_time(e1), "wall_ms_incl_upload": 1e3 * (t1 - t0),
+                   "matrices_gb": 32 * n * n / 1e9}
+            del g, t, m, h
+        out[name] = res
+        eng.release()
+    out["survey_cpu_seconds"] = {"C1": 0.08, "C2": 30.6}
+    return out
+
+
+def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 2,
+              tuning: int = 0, config: str | None = None) -> dict:
     """One more BASELINE.json shape in the same run (same kernels, same drivers, device-resident
     inputs, ``steps`` timed steps after one warm-up): ms per catalogue, K1 ms and executed TFLOP/s."""
     import torch
@@ -270,8 +313,8 @@ def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict,
     from tvbingefriend_recommendation_service_b200.sharding import row_shard
     from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, make_config
 
-    cfg = CONFIGS[name]
-    cat = make_config(name)
+    cfg = CONFIGS[config or name]
+    cat = make_config(config or name)
     n, k = cat.n_shows, cfg["k"]
     st = stage(cat.features(), "mean3", pin=True)
     raw = eng.h2d(st)
@@ -287,11 +330,12 @@ def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict,
         dc = eng.prepare(raw, weights, recycle=prev[0])
         prev[0] = dc
         if world > 1:
-            return top_k_device_distributed(eng, dc, weights, k, 0.1, True, events=events)
+            return top_k_device_distributed(eng, dc, weights, k, 0.1, True, events=events, tuning=tuning,
+                                            symmetric=False if (tuning >> 20) & 3 == 1 else None)
         mark("seed0")
-        t = eng.top_k_device(dc, weights, k, 0.1, True, phases=1)
+        t = eng.top_k_device(dc, weights, k, 0.1, True, phases=1, tuning=tuning)
         mark("sweep1")
-        eng.top_k_device(dc, weights, k, 0.1, True, phases=6, out=t)
+        eng.top_k_device(dc, weights, k, 0.1, True, phases=6, out=t, tuning=tuning)
         return t
 
     def sync():
@@ -318,12 +362,12 @@ def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict,
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dc = prev[0]
     if world > 1:
-        sharded = n >= 40_000 and eng.sym_eligible(dc, weights, k, 0.1)
+        sharded = n >= 40_000 and eng.sym_eligible(dc, weights, k, 0.1) and (tuning >> 20) & 3 != 1
         rb, re_ = row_shard(n, world, 0)
         plan = eng.plan_tiles(dc, weights, k, 0.1, rank=0, world=world, tile_sharded=True) if sharded else \
             eng.plan_tiles(dc, weights, k, 0.1, row_begin=rb, row_end=re_, tuning=1 << 20)
     else:
-        plan = eng.plan_tiles(dc, weights, k, 0.1)
+        plan = eng.plan_tiles(dc, weights, k, 0.1, tuning=tuning)
     stats = out["stats"].cpu().numpy().reshape(-1, 8).sum(axis=0)
     ms, k1 = t_ms[0].item(), t_ms[1].item()
     tf = plan["flops"] / (k1 * 1e-3) / 1e12 if k1 > 0 else 0.0
@@ -361,7 +405,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-dense-probe", action="store_true")
-    ap.add_argument("--extra", default="P80k,C4,C5", help="comma-separated extra configs timed in the same run ('' = none)")
+    ap.add_argument("--extra", default="P80k,C4,C5,one_sided,nxn", help="comma-separated extra configs timed in the same run ('' = none)")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--one-sided", action="store_true", help="disable the symmetric sweep at N > 1")
     ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
@@ -525,7 +569,14 @@ def main() -> None:
             eng.release()
         for name in [x for x in args.extra.split(",") if x and x != args.config]:
             try:
-                extra[name] = run_extra(name, eng, args, world, rank, weights, peaks)
+                if name == "one_sided":     # the sweep every job that is not eligible for the symmetric one gets
+                    extra[f"{args.config}_one_sided"] = run_extra(name, eng, args, world, rank, weights, peaks,
+                                                                  tuning=1 << 20, config=args.config)
+                elif name == "nxn":
+                    if world == 1:
+                        extra["nxn_variant"] = nxn_variant(eng, weights)
+                else:
+                    extra[name] = run_extra(name, eng, args, world, rank, weights, peaks)
             except Exception as exc:   # an extra must never take the headline down with it
                 extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
         raw = eng.h2d(st)

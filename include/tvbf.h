@@ -286,9 +286,12 @@ int tvbf_matrix_stats_f64(const double* mat, int32_t n, double* out5_host, void*
  *      delivers the text-dependent sums exactly (float64), from which the caller assembles mean and
  *      std of text and hybrid to ~1e-9 (engine.similarity_stats). */
 size_t tvbf_stats_accum_bytes(void);
-/* exact float64 moments over ALL (i, j) pairs, no N x N:
- *   out8 = { sum t, sum t^2 (0 unless with_gram), sum g*t, sum m*t,
- *            diagonal: sum_i t_ii, sum_i t_ii^2, sum_i g_ii t_ii, sum_i m_ii t_ii }
+#define TVBF_MOMENTS 24
+/* exact float64 moments over ALL (i, j) pairs, no N x N; out8 has TVBF_MOMENTS entries:
+ *   [0..7]   sum t, sum t^2 (0 unless with_gram), sum g*t, sum m*t,
+ *            diagonal: sum_i t_ii, sum_i t_ii^2, sum_i g_ii t_ii, sum_i m_ii t_ii
+ *   [8..12]  sum g, sum g^2, sum m, sum m^2, sum g*m
+ *   [13..17] diagonal: sum_i g_ii, g_ii^2, m_ii, m_ii^2, g_ii m_ii
  * (t / g / m = text / genre / metadata cosine; strict upper triangle = (all - diagonal) / 2).
  * with_gram needs a [vocab, vocab] float64 Gram matrix in the workspace (800 MB at V = 10 000).
  * Packed genre / metadata only.  out8 is a DEVICE pointer. */

@@ -210,8 +210,18 @@ def test_symmetric_request_on_ineligible_job_is_refused(engine, cat2k):
 
     with pytest.raises(TvbfError):   # k = 150 needs more candidates per show than the shared lists keep
         engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 150, 0.1, tuning=SYM_ON)
-    with pytest.raises(TvbfError):   # non-positive threshold
-        engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.0, tuning=SYM_ON)
+    # a non-positive threshold IS eligible when every score is >= 0 (round 2: thresholds start at +0) ...
+    top = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, 0.0, tuning=SYM_ON)
+    assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 9), (0.4, 0.5, 0.1), 20, 0.0)
+    top = engine.compute_top_k(cat2k.features(), (0.4, 0.5, 0.1), 20, -0.25, tuning=SYM_ON)
+    assert_topk_matches(top, cat2k.features(), np.arange(0, 2000, 9), (0.4, 0.5, 0.1), 20, -0.25)
+    # ... but not with signed text (scores, and so thresholds, may be negative)
+    f = dict(cat2k.features())
+    f["text_features"] = sp.csr_matrix(np.random.default_rng(1).standard_normal((2000, 32)))
+    with pytest.raises(TvbfError):
+        engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.0, tuning=SYM_ON)
+    assert_topk_matches(engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 0.0), f, np.arange(0, 2000, 9),
+                        (0.4, 0.5, 0.1), 20, 0.0)        # auto: one-sided sweep
 
 
 @pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
@@ -239,8 +249,7 @@ def test_degenerate_rows(engine, tuning):
         t.rows[r], t.data[r] = [], []
     f["text_features"] = t.tocsr()
     for ms in (0.1, 0.75, 0.0):
-        # min_similarity <= 0 is not eligible for the symmetric sweep: the library falls back
-        top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, ms, tuning=tuning if ms > 0 else SYM_OFF)
+        top = engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, ms, tuning=tuning)
         assert_topk_matches(top, f, None, (0.4, 0.5, 0.1), 20, ms)
     assert (engine.compute_top_k(f, (0.4, 0.5, 0.1), 20, 5.0, tuning=tuning).counts == 0).all()
 

@@ -358,3 +358,35 @@ def test_ingest_falls_back_for_inputs_the_packed_path_cannot_take(engine):
     s_ = dict(f)
     s_["text_features"] = sp.csr_matrix(np.random.default_rng(4).standard_normal((900, 48)))
     assert engine.ingest(s_, "mean3").c.text_signed == 1
+
+
+# ---- float32 inputs (sklearn's dtype rule, SURVEY.md section 3.6 ii) ---------------------------------------
+def test_float32_inputs_follow_sklearns_dtype_rule(engine):
+    """With every input float32 the reference computes in float32 and returns float32 matrices; the
+    drop-in computes in float64 and returns float32: values within 1e-6 of the reference's float32
+    run (its own rounding), top-k equal under the comparator at that tolerance."""
+    from oracle.cosine import cosine_similarity
+    from tvbingefriend_recommendation_service_b200.ml.similarity_computer import SimilarityComputer
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(700, 400, nnz=12, seed=33)
+    f = cat.features()
+    f32 = {"genre_features": f["genre_features"].astype(np.float32),
+           "text_features": f["text_features"].astype(np.float32),
+           "platform_features": f["platform_features"].astype(np.float32),
+           "type_features": f["type_features"].astype(np.float32),
+           "language_features": f["language_features"].astype(np.float32)}
+    comp = SimilarityComputer(engine=engine)
+    g = comp.compute_genre_similarity(f32["genre_features"])
+    t = comp.compute_text_similarity(f32["text_features"])
+    m = comp.compute_metadata_similarity(f32["platform_features"], f32["type_features"], f32["language_features"])
+    for got, ref in ((g, cosine_similarity(f32["genre_features"])), (t, cosine_similarity(f32["text_features"])),
+                     (m, cosine_similarity(np.hstack([f32["platform_features"], f32["type_features"],
+                                                      f32["language_features"]])))):
+        assert got.dtype == np.float32 and ref.dtype == np.float32
+        assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() < 2e-6
+    assert comp.compute_genre_similarity(f["genre_features"]).dtype == np.float64     # mixed / float64 -> float64
+    # top-k from float32 features: the float32 values are promoted exactly, scores are float64
+    top = comp.compute_top_k(f32, k=20, min_similarity=0.1)
+    f64 = {k_: (v.astype(np.float64) if not sp.issparse(v) else sp.csr_matrix(v, dtype=np.float64)) for k_, v in f32.items()}
+    assert_topk_matches(top, f64)

@@ -131,14 +131,16 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl, int sweep 
     pl->tiles_per_split = (pl->col_tiles + pl->splits - 1) / pl->splits;
     // Symmetric mode: hybrid(i,j) == hybrid(j,i), so only tiles on or above the diagonal are
     // computed and each score is offered to both shows.  Needs the whole catalogue in one shard,
-    // CTA pairs (256-row super block == 256-column tile), packed groups with non-negative weights
-    // and a positive threshold (so that every dropped U <= theta_init is below min_similarity).
+    // CTA pairs (256-row super block == 256-column tile), packed groups with non-negative weights,
+    // and thresholds that are positive floats (the shared thresholds are raised with atomicMax on
+    // their raw bits): a positive min_similarity, or -- for min_similarity <= 0 -- non-negative text,
+    // so that every upper bound U is > 0 and the initial threshold can be +0 ("everything passes").
     if (pl->kp > 64) pl->sym_cap = 4096;
     const int sym_req = (tune >> 20) & 0x3;
     const bool eligible = pl->cg == 2 && p->row_begin == 0 && p->row_end == f->n_shows &&
                           f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED &&
                           p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0 &&
-                          p->min_similarity > 1e-30 && pl->kp <= 128 && p->exclude_self;
+                          (p->min_similarity > 1e-30 || !f->text_signed) && pl->kp <= 128 && p->exclude_self;
     if (sym_req == 2) TVBF_REQUIRE(eligible, "symmetric mode requested but the job is not eligible");
     // auto: worth it once the triangle is large (measured: C2, 79 tiles, is 15 % slower; C3, 391
     // tiles, 1.5x faster)
@@ -329,6 +331,9 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
     if (!(ms > -3.0e38)) th = -3.0e38f;
     th = std::nextafterf(th, -INFINITY);
     if (static_cast<double>(th) >= ms) th = std::nextafterf(th, -INFINITY);
+    // symmetric sweep with min_similarity <= 0: every U is > 0 (non-negative weights and features,
+    // eps > 0), so +0 drops nothing and keeps the thresholds' raw bits ordered like unsigned integers
+    if (pl.sym && th < 0.0f) th = 0.0f;
     kp.theta_init = th;
   }
   kp.n_weights = 1;

@@ -905,7 +905,7 @@ class HybridTopKEngine:
                 with_gram = 1 if 8 * v * v <= limit else 0
                 mb = int(lib.tvbf_text_moments_workspace_bytes(C.byref(cat.c), with_gram))
                 mws = torch.empty((mb,), dtype=torch.uint8, device=dev)
-                out8 = torch.empty((8,), dtype=torch.float64, device=dev)
+                out8 = torch.empty((24,), dtype=torch.float64, device=dev)
                 check(lib.tvbf_text_moments(C.byref(cat.c), with_gram, out8.data_ptr(), mws.data_ptr(), mb,
                                             self._stream()), "tvbf_text_moments")
                 moments = out8.cpu().numpy()
@@ -918,13 +918,15 @@ class HybridTopKEngine:
         if moments is not None:
             # strict upper triangle = (all pairs - diagonal) / 2
             st_, st2, sgt, smt = ((moments[a] - moments[a + 4]) / 2 for a in range(4))
+            sg_, sg2, sm_, sm2, sgm = ((moments[8 + a] - moments[13 + a]) / 2 for a in range(5))
+            s1[0], s2[0], s1[2], s2[2] = sg_, sg2, sm_, sm2       # genre / metadata: exact as well
             s1[1] = st_
-            s1[3] = gw * s1[0] + tw * st_ + mw * s1[2]
+            s1[3] = gw * sg_ + tw * st_ + mw * sm_
             exact["text_mean"] = True
             if with_gram:
                 s2[1] = st2
-                s2[3] = (gw * gw * s2[0] + tw * tw * st2 + mw * mw * s2[2] + 2 * gw * tw * sgt
-                         + 2 * gw * mw * float(raw["sum_gm"]) + 2 * tw * mw * smt)
+                s2[3] = (gw * gw * sg2 + tw * tw * st2 + mw * mw * sm2 + 2 * gw * tw * sgt
+                         + 2 * gw * mw * sgm + 2 * tw * mw * smt)
                 exact["text_std"] = True
         out = {}
         for q, name in enumerate(names):

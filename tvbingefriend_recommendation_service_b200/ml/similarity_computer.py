@@ -43,19 +43,27 @@ class SimilarityComputer:
         logger.info(f" {label.capitalize()} similarity: {tuple(sim.shape)}")
         return sim
 
+    @staticmethod
+    def _out_dtype(*arrays):
+        """sklearn's dtype rule (check_pairwise_arrays / _return_float_dtype):
+        the result is float32 only when EVERY input is float32, else float64.  The arithmetic here is
+        float64 either way (more precise than the reference's float32 run, within 1e-6 of it)."""
+        return np.float32 if all(getattr(a, "dtype", None) == np.float32 for a in arrays) else np.float64
+
     def compute_genre_similarity(self, genre_features: np.ndarray) -> np.ndarray:
         """cosine_similarity(genre_features) -> (n_shows, n_shows) float64 (reference :30-45)."""
-        return self._cosine(genre_features, "genre").cpu().numpy()
+        return self._cosine(genre_features, "genre").cpu().numpy().astype(self._out_dtype(genre_features), copy=False)
 
     def compute_text_similarity(self, text_features) -> np.ndarray:
         """cosine_similarity on TF-IDF vectors, dense or scipy sparse (reference :47-62)."""
-        return self._cosine(text_features, "text").cpu().numpy()
+        return self._cosine(text_features, "text").cpu().numpy().astype(self._out_dtype(text_features), copy=False)
 
     def compute_metadata_similarity(self, platform_features: np.ndarray, type_features: np.ndarray,
                                     language_features: np.ndarray) -> np.ndarray:
         """cosine of the hstack of platform/type/language (reference :64-90)."""
         metadata_features = np.hstack([platform_features, type_features, language_features])
-        return self._cosine(metadata_features, "metadata").cpu().numpy()
+        return self._cosine(metadata_features, "metadata").cpu().numpy().astype(
+            self._out_dtype(metadata_features), copy=False)
 
     def _normalized_weights(self) -> tuple[float, float, float]:
         total_weight = self.genre_weight + self.text_weight + self.metadata_weight  # reference :112-115
