@@ -301,7 +301,7 @@ def nxn_variant(eng, weights, names=("C1", "C2")) -> dict:
     return out
 
 
-def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 2,
+def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 3,
               tuning: int = 0, config: str | None = None) -> dict:
     """One more BASELINE.json shape in the same run (same kernels, same drivers, device-resident
     inputs, ``steps`` timed steps after one warm-up): ms per catalogue, K1 ms and executed TFLOP/s."""
@@ -343,7 +343,8 @@ def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict,
             dist.barrier()
         torch.cuda.synchronize()
 
-    out = step()
+    for _ in range(2):       # warm-up (allocations, clocks)
+        out = step()
     sync()
     events: dict = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -520,6 +521,11 @@ def main() -> None:
     launches = eng.kernel_launches - launches0
     total_ms = ev0.elapsed_time(ev1)
     ph = phase_ms(events)
+    if os.environ.get("BENCH_DEBUG") and rank == 0:     # per-step phase times (averages hide host-side gaps)
+        order = ("step0", "seed0", "seed1", "reduce1", "sweep1", "exchange1", "rescore1", "gather1")
+        for i in range(args.steps):
+            print("step", i, [round(events[a][i].elapsed_time(events[b][i]), 2) for a, b in zip(order, order[1:])],
+                  file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     t_ms = torch.tensor([total_ms, ph["seed"] + ph["sweep"]] + [ph[name] for name in PHASES], device="cuda",
                         dtype=torch.float64)

@@ -108,7 +108,9 @@ typedef struct tvbf_params {
                           /* 1 off, 2 on: compute only tiles on/above the diagonal and feed     */
                           /* both shows of every score); bits 22-27: column-tile stride of the  */
                           /* symmetric sweep's threshold seed pass (0 auto, 1..48 as given,     */
-                          /* 49..62 -> 48 + 8 per step, 63 none); bit 30: non-cooperative launch */
+                          /* 49..62 -> 48 + 8 per step, 63 none); bits 28-29: 16 epilogue warps in the  */
+                          /* symmetric sweep (0 auto: k_pad <= 6144, 1 off, 2 on); bit 30:           */
+                          /* non-cooperative launch                                                 */
 } tvbf_params;
 
 /* Result table of the shard rows [row_begin, row_end): the a9 record stream of

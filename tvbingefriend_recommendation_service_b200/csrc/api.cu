@@ -300,6 +300,12 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   kp.g_cnt = reinterpret_cast<unsigned int*>(ws + pl.off_gcnt);
   kp.g_list = reinterpret_cast<uint2*>(ws + pl.off_glist);
   kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
+  // 16 epilogue warps when the tile's MMAs (~0.27 us per 64-wide k-block) cannot hide the epilogue
+  // (~30 us per tile with 8 warps); bits 28-29 of tuning: 0 auto, 1 off, 2 on
+  {
+    const int wide_req = (p->tuning >> 28) & 0x3;
+    kp.wide_epilogue = (wide_req == 2 || (wide_req == 0 && f->k_pad / 64 <= 96)) && pl.kp <= 64 ? 1 : 0;
+  }
   kp.progress = reinterpret_cast<unsigned int*>(ws + pl.off_count);
   kp.kp = pl.kp;
   kp.exclude_self = p->exclude_self;

@@ -38,8 +38,13 @@ constexpr int SYMQ = 4;     // pending appends a thread can hold between two flu
 // Symmetric sweep: 8 epilogue warps, two per lane quarter, each scoring half of the tile's columns
 // -- its epilogue does twice the compares plus the shared-list traffic and, with one warp per
 // scheduler, was latency-bound (tensor pipe 74 % active); two warps per scheduler hide it.
-template <bool kSym> struct Roles {
-  static constexpr int EPI = kSym ? 8 : 4;
+// Small vocabularies (K_pad of a few hundred): the MMAs of a tile take ~2 us while its epilogue --
+// 65 536 scores through popcounts, FMAs, two compares and the shared-list traffic -- takes ~30 us
+// and is LATENCY-bound with 8 warps (ncu: 15 % of the warp slots active, 80 % of the issue slots
+// empty).  kWide doubles the epilogue to 16 warps (four per lane quarter, 64 columns each); the
+// registers then cap at 112 per thread and one ring stage is given up for the append queues.
+template <bool kSym, bool kWide = false> struct Roles {
+  static constexpr int EPI = kSym ? (kWide ? 16 : 8) : 4;
   static constexpr int PRODUCER = EPI;
   static constexpr int MMA = EPI + 1;
   static constexpr int THREADS = 32 * (EPI + 2);
@@ -48,9 +53,10 @@ template <bool kSym> struct Roles {
 // Shared-memory plan.  CG = CTAs cooperating on one MMA (tcgen05 cta_group): with CG = 2 the pair
 // computes a 256 x 256 tile, each CTA stages its own 128 rows of A and HALF of the B tile, so the
 // L2 -> SM operand traffic per MAC drops by a third and the ring gets two more stages.
-template <int CG>
+template <int CG, bool kWide = false>
 struct Smem {
-  static constexpr int STAGES = CG == 2 ? 6 : 4;
+  static constexpr int STAGES = CG == 2 ? (kWide ? 5 : 6) : 4;
+  static constexpr int QTHREADS = kWide ? 512 : 256;   // epilogue threads of the symmetric sweep
   static constexpr uint32_t B_ROWS = BN / CG;
   static constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
   static constexpr uint32_t OFF_A = 0;
@@ -60,7 +66,7 @@ struct Smem {
   static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
   // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][256] words
   static constexpr uint32_t OFF_Q = OFF_TH + 2 * kMaxSweep * MS_BYTES;   // (one slice per triple of a weight sweep)
-  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * 256 * 4;
+  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * QTHREADS * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr uint32_t USED = OFF_TMEM + 16;
@@ -247,17 +253,19 @@ struct Pacer {
 
 // kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep,
 // 5 symmetric top-k sweep for p.n_weights weight triples at once (one shared list per triple and show)
-template <int E, bool kDump, int CG, int kMode>
-__global__ void __launch_bounds__(Roles<(kMode != 0)>::THREADS, 1)
+template <int E, bool kDump, int CG, int kMode, bool kWide = false>
+__global__ void __launch_bounds__(Roles<(kMode != 0), kWide>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
                    const uint32_t idesc) {
-  using L = Smem<CG>;
-  constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 epilogue warps
+  using L = Smem<CG, kWide>;
+  constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 (kWide: 16) epilogue warps
   constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
   constexpr bool kMulti = kMode == 5;    // weight sweep
   constexpr int STAGES = L::STAGES;
-  constexpr int EPI = Roles<kSym>::EPI, PRODUCER_WARP = Roles<kSym>::PRODUCER, MMA_WARP = Roles<kSym>::MMA;
+  using R = Roles<kSym, kWide>;
+  constexpr int EPI = R::EPI, PRODUCER_WARP = R::PRODUCER, MMA_WARP = R::MMA;
+  constexpr int QT = L::QTHREADS;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
   const uint32_t nstages = static_cast<uint32_t>(p.stages);
   extern __shared__ uint8_t smem_raw[];
@@ -498,8 +506,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // memory (per-thread FIFO) and flushed every 64 columns with the atomics of a whole batch in
       // flight together.  A later append only delays a candidate, it never loses one.
       uint32_t* q_show = reinterpret_cast<uint32_t*>(smem + L::OFF_Q) + (warp * 32 + lane);
-      uint32_t* q_score = q_show + SYMQ * 256;
-      uint32_t* q_other = q_score + SYMQ * 256;
+      uint32_t* q_score = q_show + SYMQ * QT;
+      uint32_t* q_other = q_score + SYMQ * QT;
       int qn = 0;
       auto sym_commit = [&](int show, uint32_t ubits, uint32_t other, unsigned pos) {
         if (pos < sym_cap) {
@@ -514,9 +522,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       };
       auto sym_append = [&](int show, float u, int other) {
         if (qn < SYMQ) {
-          q_show[qn * 256] = static_cast<uint32_t>(show);
-          q_score[qn * 256] = __float_as_uint(u);
-          q_other[qn * 256] = static_cast<uint32_t>(other);
+          q_show[qn * QT] = static_cast<uint32_t>(show);
+          q_score[qn * QT] = __float_as_uint(u);
+          q_other[qn * QT] = static_cast<uint32_t>(other);
           ++qn;
         } else {  // queue full (rare): pay the round trip now
           sym_commit(show, __float_as_uint(u), static_cast<uint32_t>(other), atomicAdd(p.g_cnt + show, 1u));
@@ -532,14 +540,14 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             sh[j] = 0u;
             pos[j] = 0xFFFFFFFFu;
             if (base + j < qn) {
-              sh[j] = q_show[(base + j) * 256];
+              sh[j] = q_show[(base + j) * QT];
               pos[j] = atomicAdd(p.g_cnt + sh[j], 1u);
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (base + j < qn)
-              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * 256], q_other[(base + j) * 256], pos[j]);
+              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * QT], q_other[(base + j) * QT], pos[j]);
         }
         qn = 0;
       };
@@ -1068,22 +1076,22 @@ static bool profiler_attached() {
   return cached != 0;
 }
 
-template <int E, bool kDump, int CG, int kMode>
+template <int E, bool kDump, int CG, int kMode, bool kWide = false>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
-  using L = Smem<CG>;
+  using L = Smem<CG, kWide>;
   CUtensorMap ta, tb;
   int rc = make_operand_map(f, BM, &ta);
   if (rc != TVBF_OK) return rc;
   rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode, kWide>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(L::BYTES)));
   const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  cfg.blockDim = dim3(Roles<(kMode != 0)>::THREADS);
+  cfg.blockDim = dim3(Roles<(kMode != 0), kWide>::THREADS);
   cfg.dynamicSmemBytes = L::BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1201,7 +1209,12 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, n_virtual * kp.sym_cap * 8, st));
     K1Params sweep = kp;
     sweep.tile_stride = 1;
-    return nw > 1 ? launch_k1<4, false, 2, 5>(f, sweep, grid, st) : launch_k1<4, false, 2, 1>(f, sweep, grid, st);
+    if (nw > 1) return launch_k1<4, false, 2, 5>(f, sweep, grid, st);
+    if (kp.wide_epilogue) {
+      if (sweep.stages > Smem<2, true>::STAGES) sweep.stages = Smem<2, true>::STAGES;
+      return launch_k1<4, false, 2, 1, true>(f, sweep, grid, st);
+    }
+    return launch_k1<4, false, 2, 1>(f, sweep, grid, st);
   }
   if (cta_group == 2) {
     switch (entries_per_lane) {

@@ -62,6 +62,7 @@ struct K1Params {
   int deal_groups;         // groups owned by this launch
   int deal_r;              // super blocks per dealt group
   unsigned short deal_gid[kMaxDealGroups];   // global group number of each local group, cost descending
+  int wide_epilogue;       // symmetric sweep with 16 epilogue warps (small vocabularies: epilogue-bound)
   int cand_packed;         // K4s writes {count, bound bits} as entry kp of each row, row stride kp + 1
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
   int seed_theta;          // one-sided sweep only seeds g_theta with the kp-th best sampled score
