@@ -172,7 +172,23 @@ def cpu_baseline(cat, cfg, weights, budget_s: float = 20.0, use_sklearn: bool = 
         threads = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
     if limiter is not None:
         limiter.restore_original_limits()
-    return {"value": rows / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+    # variant A (SimilarityComputer.compute_all_similarities, ml/similarity_computer.py:132-169) where the four
+    # N x N float64 matrices fit comfortably: BASELINE.json configs[0] (C1) with the same sklearn cosine
+    variant_a = None
+    try:
+        from oracle.reference_paths import SimilarityComputerOracle
+        from tvbingefriend_recommendation_service_b200.synthetic import make_config
+
+        c1 = make_config("C1")
+        comp = SimilarityComputerOracle(*weights, **kw)
+        t0 = time.perf_counter()
+        sims = comp.compute_all_similarities(c1.features())
+        variant_a = {"config": "C1 (1000 shows x 5000 vocab)", "seconds": time.perf_counter() - t0,
+                     "what": "compute_all_similarities: 3 cosine_similarity calls + weighted sum, four N x N float64"}
+        del sims
+    except Exception as exc:
+        variant_a = {"error": str(exc)}
+    return {"value": rows / dt, "unit": UNIT, "cores": int(threads), "kind": "port", "variant_a": variant_a,
             "sample": f"{rows} evenly spaced source rows of {n} through the verbatim production loop "
                       f"(5 cosine_similarity calls + argsort per row; {label}); "
                       f"host has {os.cpu_count()} logical cpus; scipy CSR product and argsort are single-threaded",

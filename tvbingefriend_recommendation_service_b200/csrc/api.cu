@@ -625,10 +625,17 @@ int fill_sym_params(const tvbf_features* f, const tvbf_params* p, const SymPlan&
   kp->cand_theta = nullptr;
   kp->rb_count = sp.local_sb;
   kp->rb_per_group = sp.pl.sb_per_group;
+  kp->seed_world = world;
+  kp->seed_rank = rank;
+  {
+    int sms = 0;
+    rc = sm_count_cached(&sms);
+    if (rc != TVBF_OK) return rc;
+    kp->seed_clusters = sms / 2;
+  }
   kp->deal_groups = sp.deal_groups;
   kp->deal_r = sp.pl.sb_per_group;
   for (int g = 0; g < sp.deal_groups; ++g) kp->deal_gid[g] = sp.gid[g];
-  (void)rank;
   // a rank that sweeps 1/world of the tiles gets fewer threshold refreshes: seed more densely
   // (measured at world = 8 on C3: stride 48 -> 0.6 + 8.0 ms per rank, stride 96 -> 0.4 + 8.5 ms)
   if (world >= 4 && ((p->tuning >> 22) & 0x3F) == 0 && kp->tile_stride > 48) kp->tile_stride = 48;
@@ -707,6 +714,8 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
     rc = tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
     if (rc != TVBF_OK) return rc;
   } else {
+    rc = tvbf::k1_join_pending_clear(kp.g_list, st);
+    if (rc != TVBF_OK) return rc;
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(f->n_pad) * 4, st));
   }
   return tvbf::k4s_launch(kp, f->n_shows, st);

@@ -20,6 +20,7 @@
 
 #include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
 #include <cstdlib>
+#include <mutex>
 
 namespace tvbf {
 
@@ -157,6 +158,7 @@ struct ItemCoord {
 
 // local super block number of this launch -> global super block (see K1Params::deal_*)
 __host__ __device__ __forceinline__ int global_super_block(const K1Params& p, int local) {
+  if (p.seed_theta && p.seed_world > 1) return local * p.seed_world + p.seed_rank;
   if (p.deal_groups == 0) return local;
   const int g = local / p.deal_r;
   if (g >= p.deal_groups) return 0x3fffffff;
@@ -1143,8 +1145,11 @@ static K1Params make_seed_params(const K1Params& kp, int grid, int w) {
     seed.eps_term = kp.mw_eps_term[w];
     seed.g_theta = kp.g_theta + static_cast<size_t>(w) * kp.n_pad;
   }
-  const int clusters = grid / 2;
-  seed.rb_per_group = clusters < kp.rb_count ? clusters : kp.rb_count;
+  if (kp.seed_world > 1)   // blocks seed_rank, seed_rank + seed_world, ... of the col_tiles super blocks
+    seed.rb_count = kp.col_tiles > kp.seed_rank ? (kp.col_tiles - kp.seed_rank + kp.seed_world - 1) / kp.seed_world : 0;
+  // all SMs, whatever the sweep's wave shape
+  const int clusters = kp.seed_world > 1 ? kp.seed_clusters : grid / 2;
+  seed.rb_per_group = clusters < seed.rb_count ? clusters : seed.rb_count;
   if (seed.rb_per_group < 1) seed.rb_per_group = 1;
   return seed;
 }
@@ -1178,6 +1183,50 @@ void k1_executed_tiles(const K1Params& kp, int grid, long long* out) {
   }
 }
 
+// The shared lists must read as zeros before the sweep (a reserved-but-unwritten entry counts as
+// -inf); clearing them (820 MB at C3) is independent of the threshold seed pass that precedes the
+// sweep, so it runs on a side stream beside it.  One side stream + event pair per device, created on
+// first use; `pending` remembers a clear started by a seed-only call (multi-GPU: the caller's
+// all-reduce sits between the two calls) for the sweep-only call that follows.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  const void* pending = nullptr;
+};
+static std::mutex g_side_mutex;
+static SideStream g_side[64];
+
+static int side_stream(SideStream** out) {
+  int dev = 0;
+  TVBF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    tvbf_set_error("device ordinal %d out of range", dev);
+    return TVBF_ERR_INVALID;
+  }
+  SideStream& s = g_side[dev];
+  if (s.stream == nullptr) {
+    TVBF_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    TVBF_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    TVBF_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return TVBF_OK;
+}
+
+// a sweep-only call that launches nothing (a GPU without super blocks) still has to absorb the clear
+// its seed-only call started
+int k1_join_pending_clear(const void* g_list, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream* side = nullptr;
+  int rc = side_stream(&side);
+  if (rc != TVBF_OK) return rc;
+  if (side->pending == g_list && g_list != nullptr) {
+    TVBF_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+    side->pending = nullptr;
+  }
+  return TVBF_OK;
+}
+
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st) {
   if (kp.sym) {
@@ -1188,6 +1237,21 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
     const int n_pad = f->n_pad;
     const int nw = kp.n_weights > 1 ? kp.n_weights : 1;   // weight sweep: nw * n_pad virtual shows
     const size_t n_virtual = static_cast<size_t>(nw) * n_pad;
+    std::lock_guard<std::mutex> lock(g_side_mutex);
+    SideStream* side = nullptr;
+    int rcs = side_stream(&side);
+    if (rcs != TVBF_OK) return rcs;
+    bool cleared = false;
+    if (kp.sym_phase != 2 && kp.tile_stride > 1) {
+      // a seed pass follows: clear the lists beside it
+      TVBF_CUDA_OK(cudaEventRecord(side->fork, st));
+      TVBF_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, n_virtual * 4, side->stream));
+      TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, n_virtual * kp.sym_cap * 8, side->stream));
+      TVBF_CUDA_OK(cudaEventRecord(side->join, side->stream));
+      side->pending = kp.g_list;
+      cleared = true;
+    }
     if (kp.sym_phase != 2) {
       sym_init_kernel<<<static_cast<unsigned>((n_virtual + 255) / 256), 256, 0, st>>>(
           kp.g_theta, f->n_shows, n_pad, static_cast<int>(n_virtual), kp.theta_init);
@@ -1203,10 +1267,16 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
           TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
         }
       }
-      if (kp.sym_phase == 1) return TVBF_OK;
+      if (kp.sym_phase == 1) return TVBF_OK;   // the sweep-only call joins the clear
     }
-    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, n_virtual * 4, st));
-    TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, n_virtual * kp.sym_cap * 8, st));
+    if (!cleared && side->pending == kp.g_list) cleared = true;   // started by the preceding seed-only call
+    if (cleared) {
+      TVBF_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+      side->pending = nullptr;
+    } else {
+      TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, n_virtual * 4, st));
+      TVBF_CUDA_OK(cudaMemsetAsync(kp.g_list, 0, n_virtual * kp.sym_cap * 8, st));
+    }
     K1Params sweep = kp;
     sweep.tile_stride = 1;
     if (nw > 1) return launch_k1<4, false, 2, 5>(f, sweep, grid, st);

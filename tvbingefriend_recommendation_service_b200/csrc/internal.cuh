@@ -62,6 +62,10 @@ struct K1Params {
   int deal_groups;         // groups owned by this launch
   int deal_r;              // super blocks per dealt group
   unsigned short deal_gid[kMaxDealGroups];   // global group number of each local group, cost descending
+  // The threshold seed pass of a multi-GPU job is dealt by super-block COUNT (block b to GPU b mod
+  // seed_world), not by the sweep's tile-balanced groups: its cost is per block, and the seeded
+  // thresholds are MAX-reduced over the GPUs anyway.
+  int seed_world, seed_rank, seed_clusters;
   int wide_epilogue;       // symmetric sweep with 16 epilogue warps (small vocabularies: epilogue-bound)
   int cand_packed;         // K4s writes {count, bound bits} as entry kp of each row, row stride kp + 1
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
@@ -110,6 +114,7 @@ int k1_default_candidates(int k);
 int k1_choose_splits(int rb_count, int col_tiles, int sm_count);
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st);
+int k1_join_pending_clear(const void* g_list, cudaStream_t st);
 void k1_executed_tiles(const K1Params& kp, int grid, long long* out2);
 int k1_launch_dump(const tvbf_features* f, const K1Params& kp, int cta_group, cudaStream_t st);
 // candidate list s of shard row r lives in slot  slot_base + r * row_stride + s * list_stride;

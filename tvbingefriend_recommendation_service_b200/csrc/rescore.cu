@@ -43,6 +43,45 @@ __device__ __forceinline__ double text_dot(const tvbf_features& f, int i, int j)
   return s;
 }
 
+// Same sum as text_dot(i, j) -- products of the common columns in ascending column order, one rounding
+// per product and per add, so the result is bit-identical -- for a source row i whose entries are
+// staged in shared memory: the entries of row j are independent loads (several in flight) and each
+// is looked up in row i by binary search, instead of a serial merge whose every step waits for a
+// dependent global load.
+constexpr int K5_ROWNNZ = 160;   // entries of the source row staged per warp (longer rows: serial merge)
+
+__device__ __forceinline__ double text_dot_staged(const tvbf_features& f, const int* icols, const double* ivals,
+                                                  int ilen, int j) {
+  const int64_t bj = f.text_indptr[j], ej = f.text_indptr[j + 1];
+  if (ilen == 0 || bj == ej) return 0.0;
+  double s = 0.0;
+  for (int64_t e0 = bj; e0 < ej; e0 += 4) {
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = e0 + u;
+      c[u] = e < ej ? f.text_indices[e] : -1;
+      v[u] = e < ej ? f.text_values[e] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c[u] < 0) break;
+      int lo = 0, hi = ilen;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int cm = icols[mid];
+        if (cm == c[u]) {
+          s = __dadd_rn(s, __dmul_rn(ivals[mid], v[u]));
+          break;
+        }
+        if (cm < c[u]) lo = mid + 1; else hi = mid;
+      }
+    }
+  }
+  return s;
+}
+
 __device__ __forceinline__ double dense_dot(const double* x, int dim, int i, int j) {
   const double* a = x + static_cast<size_t>(i) * dim;
   const double* b = x + static_cast<size_t>(j) * dim;
@@ -129,6 +168,17 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   int* sj = reinterpret_cast<int*>(sm + max_cand);
   uint32_t* su = reinterpret_cast<uint32_t*>(sj + max_cand);
   __shared__ double s_kth[K5_WARPS];
+  // the source row's text entries, staged once for all its candidate pairs
+  __shared__ double s_ivals[K5_WARPS][K5_ROWNNZ];
+  __shared__ int s_icols[K5_WARPS][K5_ROWNNZ];
+  const int64_t ib = sp.f.text_indptr[i];
+  const int ilen = static_cast<int>(sp.f.text_indptr[i + 1] - ib);
+  const bool staged = ilen <= K5_ROWNNZ;
+  if (staged)
+    for (int e = lane; e < ilen; e += 32) {
+      s_icols[warp][e] = sp.f.text_indices[ib + e];
+      s_ivals[warp][e] = sp.f.text_values[ib + e];
+    }
 
   // gather the candidate columns (and their upper bounds U) of all lists
   int total = 0;
@@ -198,7 +248,15 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   int valid = 0;
   for (int e = lane; e < total; e += 32) {
     const int j = sj[e];
-    const Scores s = score_pair(sp, i, j);
+    Scores s;
+    if (staged) {
+      s.g = genre_score(sp.f, i, j);
+      s.t = text_dot_staged(sp.f, s_icols[warp], s_ivals[warp], ilen, j);
+      s.m = meta_score(sp.f, i, j);
+      s.h = hybrid_rn(sp.wg, s.g, sp.wt, s.t, sp.wm, s.m);
+    } else {
+      s = score_pair(sp, i, j);
+    }
     const bool ok = (s.h >= sp.min_similarity) && !(sp.exclude_self && j == i);
     sh[e] = ok ? s.h : -INFINITY;
     sg[e] = s.g;
