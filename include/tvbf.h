@@ -228,6 +228,16 @@ int tvbf_sym_seed(const tvbf_features* f, const tvbf_params* p, int32_t rank, in
 int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
                    uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* tvbf_sym_sweep with the exchange FUSED into the compaction: every finished candidate row (packed,
+ * L + 1 entries) is stored straight into the receive buffer of the GPU that rescores that show, over
+ * NVLink peer mappings -- no all-to-all.  peer_ptrs: HOST array of `world` device addresses, entry r =
+ * GPU r's receive buffer laid out [world][shard_rows][L + 1] x 8 bytes as mapped into THIS process
+ * (e.g. torch symmetric memory's buffer_ptrs); show s is owned by GPU s / shard_rows and lands in
+ * slice `rank` of its buffer.  The caller runs a cross-GPU barrier before tvbf_rescore_lists reads
+ * its own buffer (cnt_all = bound_all = NULL, table_rows = shard_rows). */
+int tvbf_sym_sweep_peer(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                        uint32_t* theta, const uint64_t* peer_ptrs, int32_t shard_rows, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* fp64 rescoring + certificate + exact repair of rows [p->row_begin, p->row_end) from `lists`
  * candidate tables laid out [lists][table_rows][L] that cover the shows
  * [table_row0, table_row0 + table_rows): (0, n_shows) after an all_gather, (row_begin, rows) after

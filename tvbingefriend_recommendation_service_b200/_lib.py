@@ -95,6 +95,8 @@ SIGNATURES = {
                                 c_size_t, c_void_p]),
     "tvbf_sym_sweep": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tvbf_sym_sweep_peer": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_int32, c_int32, c_void_p,
+                                      C.POINTER(C.c_uint64), c_int32, c_void_p, c_size_t, c_void_p]),
     "tvbf_rescore_lists": (C.c_int, [C.POINTER(Features), C.POINTER(Params), c_void_p, c_void_p, c_void_p, c_int32,
                                      c_int32, c_int32, C.POINTER(TopKOut), c_void_p, c_size_t, c_void_p]),
     "tvbf_exact_workspace_bytes": (c_size_t, [C.POINTER(Features), c_int32]),

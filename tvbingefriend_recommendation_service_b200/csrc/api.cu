@@ -684,12 +684,13 @@ int tvbf_sym_seed(const tvbf_features* f, const tvbf_params* p, int32_t rank, in
   return tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
 }
 
-int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
-                   uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
-                   void* workspace, size_t workspace_bytes, void* stream) {
+static int sym_sweep_impl(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                          uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
+                          const uint64_t* peer_ptrs, int32_t shard_rows, void* workspace, size_t workspace_bytes,
+                          void* stream) {
   int rc = validate_features(f);
   if (rc != TVBF_OK) return rc;
-  TVBF_REQUIRE(theta && cand && workspace, "tvbf_sym_sweep: NULL buffer");
+  TVBF_REQUIRE(theta && workspace && (cand || peer_ptrs), "tvbf_sym_sweep: NULL buffer");
   TVBF_REQUIRE((cand_cnt == nullptr) == (cand_bound == nullptr),
                "tvbf_sym_sweep: pass both cand_cnt and cand_bound, or neither (packed rows)");
   SymPlan sp;
@@ -709,6 +710,18 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
   kp.cand_cnt = cand_cnt;
   kp.cand_theta = cand_bound;
   kp.cand_packed = cand_cnt == nullptr ? 1 : 0;
+  if (peer_ptrs != nullptr) {
+    TVBF_REQUIRE(world <= tvbf::kMaxPeers, "peer exchange supports at most %d GPUs", tvbf::kMaxPeers);
+    TVBF_REQUIRE(shard_rows > 0 && static_cast<int64_t>(shard_rows) * world >= f->n_shows,
+                 "tvbf_sym_sweep_peer: shard_rows * world must cover the catalogue");
+    kp.cand_packed = 2;
+    kp.peer_shard_rows = shard_rows;
+    kp.peer_rank = rank;
+    for (int r = 0; r < world; ++r) {
+      TVBF_REQUIRE(peer_ptrs[r] != 0, "tvbf_sym_sweep_peer: NULL peer buffer %d", r);
+      kp.peer_cand[r] = reinterpret_cast<uint2*>(static_cast<uintptr_t>(peer_ptrs[r]));
+    }
+  }
   TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
   if (sp.local_sb > 0) {
     rc = tvbf::k1_launch(f, kp, sp.pl.entries, 2, sp.pl.grid, st);
@@ -719,6 +732,22 @@ int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, i
     TVBF_CUDA_OK(cudaMemsetAsync(kp.g_cnt, 0, static_cast<size_t>(f->n_pad) * 4, st));
   }
   return tvbf::k4s_launch(kp, f->n_shows, st);
+}
+
+int tvbf_sym_sweep(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                   uint32_t* theta, void* cand, int32_t* cand_cnt, float* cand_bound,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  TVBF_REQUIRE(cand != nullptr, "tvbf_sym_sweep: NULL buffer");
+  return sym_sweep_impl(f, p, rank, world, theta, cand, cand_cnt, cand_bound, nullptr, 0, workspace,
+                        workspace_bytes, stream);
+}
+
+int tvbf_sym_sweep_peer(const tvbf_features* f, const tvbf_params* p, int32_t rank, int32_t world,
+                        uint32_t* theta, const uint64_t* peer_ptrs, int32_t shard_rows, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  TVBF_REQUIRE(peer_ptrs != nullptr, "tvbf_sym_sweep_peer: NULL peer pointer array");
+  return sym_sweep_impl(f, p, rank, world, theta, nullptr, nullptr, nullptr, peer_ptrs, shard_rows, workspace,
+                        workspace_bytes, stream);
 }
 
 int tvbf_rescore_lists(const tvbf_features* f, const tvbf_params* p, const void* cand_all,

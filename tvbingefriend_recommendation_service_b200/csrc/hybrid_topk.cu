@@ -854,6 +854,12 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
   const int kp = p.kp;
   uint2* dst = p.cand + static_cast<size_t>(r) * (p.cand_packed ? kp + 1 : kp);
+  if (p.cand_packed == 2) {
+    // fused compaction + exchange: the finished list goes to the GPU that rescores this show
+    const int owner = r / p.peer_shard_rows;
+    dst = p.peer_cand[owner] + (static_cast<size_t>(p.peer_rank) * p.peer_shard_rows + (r - owner * p.peer_shard_rows)) *
+                                   static_cast<size_t>(kp + 1);
+  }
   // Lists of up to 1024 entries are selected in one go from registers (32 per lane).  Longer ones
   // (kp > 64) in windows: the kp survivors so far, parked at the head of the list, plus the next
   // 1024 - kp entries; the kp-th value only rises from window to window, so the last one bounds

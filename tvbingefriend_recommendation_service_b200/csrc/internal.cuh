@@ -25,6 +25,7 @@ struct StatsAccum {
 
 // parameters of the tcgen05 candidate kernel (hybrid_topk.cu)
 constexpr int kMaxDealGroups = 192;
+constexpr int kMaxPeers = 16;
 constexpr int kMaxSweep = 5;   // weight triples that can share one symmetric tensor-core sweep
 
 struct K1Params {
@@ -67,7 +68,12 @@ struct K1Params {
   // thresholds are MAX-reduced over the GPUs anyway.
   int seed_world, seed_rank, seed_clusters;
   int wide_epilogue;       // symmetric sweep with 16 epilogue warps (small vocabularies: epilogue-bound)
-  int cand_packed;         // K4s writes {count, bound bits} as entry kp of each row, row stride kp + 1
+  int cand_packed;         // K4s writes {count, bound bits} as entry kp of each row, row stride kp + 1;
+                           // 2: ... straight into the OWNER GPU's receive buffer over NVLink (peer stores):
+                           // show r belongs to GPU r / peer_shard_rows, whose buffer peer_cand[owner] is laid
+                           // out [world][peer_shard_rows][kp + 1] -- slice peer_rank is this GPU's
+  uint2* peer_cand[kMaxPeers];
+  int peer_shard_rows, peer_rank;
   int tile_stride;         // one-sided sweep visits every tile_stride-th column tile (1 = all)
   int seed_theta;          // one-sided sweep only seeds g_theta with the kp-th best sampled score
   int sym_phase;           // 0: init + seed + sweep in one call; 1: init + seed only; 2: sweep only

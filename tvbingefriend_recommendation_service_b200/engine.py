@@ -662,7 +662,8 @@ class HybridTopKEngine:
         return theta
 
     def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
-                  theta: torch.Tensor, splits: int = 0, tuning: int = 0, packed_rows: int = 0):
+                  theta: torch.Tensor, splits: int = 0, tuning: int = 0, packed_rows: int = 0,
+                  peer_ptrs=None, peer_shard_rows: int = 0):
         """Phase 2: sweep this rank's tiles; returns partial candidate lists for ALL shows:
         (cand int32[N, L, 2], cnt int32[N], bound f32[N]), or -- with ``packed_rows`` >= N -- one
         int32[packed_rows, L + 1, 2] tensor whose entry L of each row holds {count, bound bits}
@@ -672,6 +673,11 @@ class HybridTopKEngine:
         with torch.cuda.device(dev):
             ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
             L = int(self.lib.tvbf_sym_list_len(C.byref(cat.c), C.byref(p)))
+            if peer_ptrs is not None:     # compaction fused with the exchange: rows go to their owners' buffers
+                check(self.lib.tvbf_sym_sweep_peer(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), peer_ptrs,
+                                                   int(peer_shard_rows), ws.data_ptr(), ws.numel(), self._stream()),
+                      "tvbf_sym_sweep_peer")
+                return None
             if packed_rows:
                 assert packed_rows >= n
                 packed = torch.empty((packed_rows, L + 1, 2), dtype=torch.int32, device=dev)
@@ -718,7 +724,7 @@ class HybridTopKEngine:
     def top_k_device_sym_sharded(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
                                  all_reduce_max, exchange, row_range, splits: int = 0, tuning: int = 0,
                                  events: dict | None = None, out: dict | None = None,
-                                 padded_rows: int | None = None) -> dict:
+                                 padded_rows: int | None = None, peer=None) -> dict:
         """This GPU's part of the tile-sharded symmetric job: the three phases with the two
         collectives between them passed in as callables: ``all_reduce_max(int32 tensor)`` in place,
         and ``exchange(packed [world * shard_rows, L + 1, 2]) -> [world, shard_rows, L + 1, 2]``
@@ -738,10 +744,19 @@ class HybridTopKEngine:
         mark("seed1")
         all_reduce_max(theta)            # raw bits of positive floats order like integers
         mark("reduce1")
-        packed = self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning,
-                                packed_rows=padded_rows)
-        mark("sweep1")
-        packed_all = exchange(packed)
+        if peer is not None:
+            # fused: K4s stores every finished candidate row into its owner's receive buffer (NVLink);
+            # a device-side barrier makes the rows visible -- no all-to-all
+            ptrs, packed_all, barrier = peer.next()
+            self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning,
+                           peer_ptrs=ptrs, peer_shard_rows=peer.rows)
+            mark("sweep1")
+            barrier()
+        else:
+            packed = self.sym_sweep(cat, weights, k, min_similarity, rank, world, theta, splits, tuning,
+                                    packed_rows=padded_rows)
+            mark("sweep1")
+            packed_all = exchange(packed)
         mark("exchange1")
         t = self.sym_rescore(cat, weights, k, min_similarity, packed_all, None, None, b, e, splits, tuning,
                              table_row0=b, out=out)

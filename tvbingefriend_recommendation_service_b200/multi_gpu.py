@@ -15,13 +15,43 @@
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from .engine import HybridTopKEngine, StagedCatalogue, TopK, stage
-from .sharding import (ShardedUpload, SharedHostTable, alloc_full_tables, exchange_packed, gather_full_tables,
-                       row_shard, shard_rows, shard_views)
+from .sharding import (PeerCandidateBuffers, ShardedUpload, SharedHostTable, alloc_full_tables, exchange_packed,
+                       gather_full_tables, row_shard, shard_rows, shard_views)
+
+_peer_cache: dict = {}
+
+
+def peer_buffers(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float, group=None):
+    """The fused exchange's receive buffers for this job shape (created collectively on first use,
+    then cached), or None when torch symmetric memory is unavailable or TVBF_PEER_EXCHANGE=0 -- the
+    driver then falls back to one NCCL all-to-all.  Every rank takes the same decision."""
+    if os.environ.get("TVBF_PEER_EXCHANGE", "1") == "0":
+        return None
+    world = dist.get_world_size(group)
+    p = eng._params(cat, weights, k, min_similarity)
+    import ctypes as C
+
+    L = int(eng.lib.tvbf_sym_list_len(C.byref(cat.c), C.byref(p)))
+    key = (eng.device.index, cat.n_shows, L, world, id(group))
+    if key not in _peer_cache:
+        ok = torch.ones((1,), dtype=torch.int32, device=eng.device)
+        bufs = None
+        try:
+            with torch.cuda.device(eng.device):
+                bufs = PeerCandidateBuffers(cat.n_shows, L, eng.device, group)
+        except Exception as exc:      # no symmetric memory on this system / build
+            ok.zero_()
+            print(f"tvbf: peer exchange unavailable ({type(exc).__name__}: {exc}); using all_to_all", flush=True)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        _peer_cache[key] = bufs if int(ok.item()) == 1 else None
+    return _peer_cache[key]
 
 
 def _local_tables(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float, exclude_self: bool, group,
@@ -41,7 +71,8 @@ def _local_tables(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: f
 
         return eng.top_k_device_sym_sharded(cat, weights, k, min_similarity, rank, world, all_reduce_max, exchange,
                                             (b, e), splits=splits, tuning=tuning, events=events, out=mine,
-                                            padded_rows=world * shard_rows(n, world))
+                                            padded_rows=world * shard_rows(n, world),
+                                            peer=peer_buffers(eng, cat, weights, k, min_similarity, group))
     if e > b:
         tun = tuning | (1 << 20)
         if events is None:

@@ -93,6 +93,44 @@ def exchange_packed(packed: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+class PeerCandidateBuffers:
+    """Receive buffers of the FUSED candidate exchange: ``[world, shard_rows, L + 1, 2]`` int32 on every
+    GPU, allocated as torch symmetric memory so that each rank holds a device mapping of every peer's
+    buffer.  The compaction kernel (K4s) of rank r stores each finished candidate row straight into
+    slice r of the owner's buffer over NVLink (``tvbf_sym_sweep_peer``); ``barrier()`` (a device-side
+    signal exchange on the current stream) replaces the all-to-all.  Two buffers are used in turn: a
+    fast rank may already be writing the next job's rows while a slow one still rescoring this job's."""
+
+    def __init__(self, n_shows: int, list_len: int, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.rows = shard_rows(n_shows, self.world)
+        self.key = (n_shows, list_len, self.world)
+        grp = group if group is not None else dist.group.WORLD
+        self.bufs, self.handles, self.ptrs = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.world * self.rows, list_len + 1, 2), dtype=torch.int32, device=device)
+            h = symm_mem.rendezvous(t, grp)
+            ptrs = [int(x) for x in h.buffer_ptrs]
+            if len(ptrs) != self.world or any(x == 0 for x in ptrs):
+                raise RuntimeError("symmetric memory rendezvous returned no peer mappings")
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptrs.append((C.c_uint64 * self.world)(*ptrs))
+        self.turn = 0
+
+    def next(self):
+        """(peer pointer array for tvbf_sym_sweep_peer, local receive view [world, rows, L + 1, 2],
+        barrier callable) of the next job."""
+        i = self.turn & 1
+        self.turn += 1
+        buf, h = self.bufs[i], self.handles[i]
+        return self.ptrs[i], buf.view(self.world, self.rows, buf.shape[1], 2), (lambda: h.barrier(channel=i))
+
+
 def empty_tables(k: int, device) -> dict:
     """Local tables of a rank that owns no rows."""
     t = {"indices": torch.empty((0, k), dtype=torch.int32, device=device),
