@@ -590,6 +590,7 @@ def main() -> None:
         if dtk is None:
             eng.release()
         for name in [x for x in args.extra.split(",") if x and x != args.config]:
+            time.sleep(1.0)      # let the power-cap controller settle: the next shape starts from an idle-ish GPU
             try:
                 if name == "one_sided":     # the sweep every job that is not eligible for the symmetric one gets
                     extra[f"{args.config}_one_sided"] = run_extra(name, eng, args, world, rank, weights, peaks,

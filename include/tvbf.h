@@ -78,6 +78,8 @@ typedef struct tvbf_features {
   const void* col_side;      /* [n_pad] 16-byte records {u64 genre bits, f32 1/sqrt(popc),    */
                              /*  u32 one-hot bits platform | type<<P | language<<(P+T)}       */
   const float* meta_scale;   /* [n_pad] MEAN3: 1/sqrt(3) ; HSTACK: 1/sqrt(#categories) or 0   */
+  const uint64_t* genre_hi;  /* [n_pad] genre bits 64..127 (multi-hot genres with 64 < G <= 128; zero    */
+                             /* padded), NULL for G <= 64: the popcount then runs over two words        */
   int32_t text_signed;       /* 1: text values may be negative (embeddings, SVD): the candidate   */
                              /* pass then bounds the fp16 error absolutely instead of relative to */
                              /* the accumulator (cancellation); 0 for TF-IDF                      */
@@ -161,9 +163,10 @@ int tvbf_prep_dense_normalize(const double* in, int32_t n_rows, int32_t dim, dou
 int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim, void* operand,
                                int32_t k_pad, int32_t col_offset, double scale, int32_t dtype,
                                void* stream);
-/* genre multi-hot bytes [n_rows, dim<=64] -> col_side[].genre_bits / genre_rnorm. */
+/* genre multi-hot bytes [n_rows, dim <= 128] -> col_side[].genre_bits / genre_rnorm (+ genre_hi[] for
+ * the columns 64.., required when dim > 64, [n_pad] entries zeroed by the caller). */
 int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,
-                         void* stream);
+                         uint64_t* genre_hi, void* stream);
 /* one-hot bytes of platform/type/language (P+T+L <= 32) -> col_side[].meta_bits and meta_scale[]. Rows
  * [n_rows, n_pad) are filled with "none". */
 int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* type, int32_t t_dim,
@@ -178,7 +181,7 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
  *      strictly ascending (unsorted / duplicates), 8 negative text values.  With 1 or 2 set the
  *      packed words are meaningless and the caller takes the general (folded float) path. */
 int tvbf_ingest_genre(const void* raw, int32_t dtype, int32_t n_rows, int32_t n_pad, int32_t dim, void* col_side,
-                      int32_t* flags, void* stream);
+                      uint64_t* genre_hi /* [n_pad], required for dim > 64 */, int32_t* flags, void* stream);
 int tvbf_ingest_meta(const void* platform, int32_t p_dtype, int32_t p_dim, const void* type, int32_t t_dtype,
                      int32_t t_dim, const void* language, int32_t l_dtype, int32_t l_dim, int32_t n_rows,
                      int32_t n_pad, int32_t meta_kind, void* col_side, float* meta_scale, int32_t* flags,

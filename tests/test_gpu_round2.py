@@ -390,3 +390,38 @@ def test_float32_inputs_follow_sklearns_dtype_rule(engine):
     top = comp.compute_top_k(f32, k=20, min_similarity=0.1)
     f64 = {k_: (v.astype(np.float64) if not sp.issparse(v) else sp.csr_matrix(v, dtype=np.float64)) for k_, v in f32.items()}
     assert_topk_matches(top, f64)
+
+
+# ---- multi-hot genres with 64 < G <= 128: two mask words (SURVEY.md section 3.5 "design for G up to 128") ----
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+@pytest.mark.parametrize("g", [65, 100, 128])
+def test_wide_genre_masks(engine, g, tuning):
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(1800, 600, nnz=14, n_genres=g, seed=100 + g)
+    f = cat.features()
+    w = (0.4, 0.5, 0.1)
+    dc = engine.ingest(f, "mean3", w)
+    assert not dc.folded and dc.c.genre_hi            # packed: nothing folded into the operand
+    top = engine.compute_top_k(f, w, 20, 0.1, tuning=tuning)
+    assert_topk_matches(top, f)
+    exact = engine.compute_top_k(f, w, 20, 0.1, force_exact=True)
+    assert np.array_equal(top.indices, exact.indices) and np.array_equal(top.counts, exact.counts)
+    m = top.indices >= 0
+    assert np.array_equal(top.hybrid[m], exact.hybrid[m])
+    # host-staged path packs the same words
+    ref = engine.upload(stage(f, "mean3"), w)
+    assert np.array_equal(dc.keep[4].cpu().numpy(), ref.keep[4].cpu().numpy())
+    hi_a = dc.keep[6].cpu().numpy()
+    bits = f["genre_features"][:, 64:].astype(np.uint64)
+    want = (bits << np.arange(bits.shape[1], dtype=np.uint64)[None, :]).sum(axis=1).astype(np.uint64)
+    assert np.array_equal(hi_a[:1800].view(np.uint64), want) and not hi_a[1800:].any()
+    # single-show query and hstack / normalised conventions on the same catalogue
+    q = engine.exact_rows(engine.ingest(f, "hstack", w), [3, 77, 1500], w, k=10, min_similarity=0.0)
+    from oracle.reference_paths import ProductionRows
+    pr = ProductionRows(f, *w, metadata_mode="hstack")
+    for r, i in enumerate([3, 77, 1500]):
+        h = pr.row(i)[0]
+        h[i] = -1.0
+        assert np.allclose(np.sort(h)[::-1][:10], q.hybrid[r], rtol=1e-12)

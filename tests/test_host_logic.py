@@ -41,11 +41,13 @@ def test_stage_folds_non_binary_groups():
 
 def test_stage_accepts_dense_text_and_wide_genre():
     rng = np.random.default_rng(0)
-    f = {"genre_features": (rng.random((6, 70)) < 0.1).astype(np.int64),      # > 64 bits -> folded
+    f = {"genre_features": (rng.random((6, 70)) < 0.1).astype(np.int64),      # 65..128 bits -> two mask words
          "text_features": rng.random((6, 12)), "platform_features": np.eye(6)[:, :3],
          "type_features": np.eye(6, dtype=bool)[:, :2], "language_features": np.eye(6)[:, :2]}
     st = stage(f, pin=False)
-    assert not st.genre_packed and st.meta_packed and st.vocab == 12
+    assert st.genre_packed and st.meta_packed and st.vocab == 12
+    wide = dict(f, genre_features=(rng.random((6, 130)) < 0.1).astype(np.int64))   # > 128 bits -> folded
+    assert not stage(wide, pin=False).genre_packed
     bad = dict(f, platform_features=np.eye(5)[:, :3])
     with pytest.raises(ValueError):
         stage(bad, pin=False)

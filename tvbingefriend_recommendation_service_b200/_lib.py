@@ -35,6 +35,7 @@ class Features(C.Structure):
         ("meta_mode", c_int32), ("meta_kind", c_int32), ("meta_groups", c_int32),
         ("meta_dims", c_int32 * 3), ("meta_dense", c_void_p * 3),
         ("col_side", c_void_p), ("meta_scale", c_void_p),
+        ("genre_hi", c_void_p),
         ("text_signed", c_int32),
     ]
 
@@ -74,10 +75,11 @@ SIGNATURES = {
     "tvbf_prep_dense_normalize": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "tvbf_prep_dense_to_operand": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                              c_double, c_int32, c_void_p]),
-    "tvbf_prep_genre_bits": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "tvbf_prep_genre_bits": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "tvbf_prep_meta_ids": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
-    "tvbf_ingest_genre": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "tvbf_ingest_genre": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "tvbf_ingest_meta": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                    c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tvbf_ingest_csr": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,

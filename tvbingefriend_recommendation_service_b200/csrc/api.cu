@@ -65,6 +65,12 @@ int validate_features(const tvbf_features* f) {
                "col_side / meta_scale must be 16-byte aligned");
   if (f->genre_mode == TVBF_GROUP_FOLDED)
     TVBF_REQUIRE(f->genre_dense && f->genre_dim > 0, "folded genre needs genre_dense");
+  if (f->genre_mode == TVBF_GROUP_PACKED) {
+    TVBF_REQUIRE(f->genre_dim >= 1 && f->genre_dim <= 128, "packed genre: %d columns outside 1..128", f->genre_dim);
+    TVBF_REQUIRE((f->genre_dim > 64) == (f->genre_hi != nullptr),
+                 "packed genre: genre_hi must be given exactly when there are more than 64 columns");
+    if (f->genre_hi) TVBF_REQUIRE((reinterpret_cast<uintptr_t>(f->genre_hi) & 15) == 0, "genre_hi must be 16-byte aligned");
+  }
   if (f->meta_mode == TVBF_GROUP_FOLDED) {
     TVBF_REQUIRE(f->meta_groups == (f->meta_kind == TVBF_META_MEAN3 ? 3 : 1), "bad meta_groups");
     for (int g = 0; g < f->meta_groups; ++g)
@@ -94,7 +100,7 @@ int make_plan(const tvbf_features* f, const tvbf_params* p, Plan* pl, int sweep 
   // tuning: bits 0-3 cta_group (0 = 2), bits 4-11 pacing chunk in k-blocks (0 = 16, 255 = off),
   // bits 12-15 pacing slack in chunks (0 = 2)
   const int tune = p->tuning;
-  pl->cg = (tune & 0xF) == 1 ? 1 : 2;
+  pl->cg = (tune & 0xF) == 1 && f->genre_hi == nullptr ? 1 : 2;   // two-word genre masks: CTA pairs only
   pl->sync_kb = ((tune >> 4) & 0xFF) == 0 ? 16 : (((tune >> 4) & 0xFF) == 255 ? 0 : ((tune >> 4) & 0xFF));
   pl->sync_slack = ((tune >> 12) & 0xF) == 0 ? 2 : ((tune >> 12) & 0xF);
   // bits 16-19 ring stages (0 = all); bits 20-21 symmetric mode (0 = auto, 1 = off, 2 = on)
@@ -263,6 +269,7 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   memset(&kp, 0, sizeof(kp));
   kp.col_side = static_cast<const TvbfColSide*>(f->col_side);
   kp.meta_scale = f->meta_scale;
+  kp.genre_hi = f->genre_mode == TVBF_GROUP_PACKED ? reinterpret_cast<const unsigned long long*>(f->genre_hi) : nullptr;
   kp.scratch = reinterpret_cast<uint2*>(ws + pl.off_scratch);
   kp.cand = reinterpret_cast<uint2*>(ws + pl.off_cand);
   kp.cand_cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
@@ -466,6 +473,7 @@ namespace {
 int sweep_plan(const tvbf_features* f, const tvbf_params* p, int n, tvbf_params* q, Plan* pl) {
   TVBF_REQUIRE(p != nullptr && n >= 1 && n <= tvbf::kMaxSweep, "weight sweep: 1..%d triples per call",
                tvbf::kMaxSweep);
+  TVBF_REQUIRE(n == 1 || f->genre_hi == nullptr, "the shared weight sweep supports at most 64 genre columns");
   for (int w = 0; w < n; ++w) {
     int rc = validate_params(f, &p[w]);
     if (rc != TVBF_OK) return rc;
@@ -800,8 +808,8 @@ int tvbf_similarity_stats(const tvbf_features* f, const tvbf_params* p, void* ac
   int rc = validate_features(f);
   if (rc != TVBF_OK) return rc;
   TVBF_REQUIRE(p && accum && workspace, "tvbf_similarity_stats: NULL argument");
-  TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED,
-               "streaming statistics need binary genre / one-hot metadata features");
+  TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED && f->genre_hi == nullptr,
+               "streaming statistics need binary genre (at most 64 columns) / one-hot metadata features");
   TVBF_REQUIRE(p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0,
                "streaming statistics need non-negative weights");
   tvbf_params q = *p;

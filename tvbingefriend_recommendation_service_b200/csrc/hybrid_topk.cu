@@ -255,7 +255,10 @@ struct Pacer {
 
 // kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep,
 // 5 symmetric top-k sweep for p.n_weights weight triples at once (one shared list per triple and show)
-template <int E, bool kDump, int CG, int kMode, bool kWide = false>
+// kG2: multi-hot genres with 64 < G <= 128 -- the second word of every column's mask is staged beside
+// the column-side records (in the threshold slices a single-triple sweep leaves unused) and the
+// popcount runs over both words.
+template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false>
 __global__ void __launch_bounds__(Roles<(kMode != 0), kWide>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
@@ -264,6 +267,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 (kWide: 16) epilogue warps
   constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
   constexpr bool kMulti = kMode == 5;    // weight sweep
+  static_assert(!(kG2 && (kMulti || kStats)), "two-word genre masks: single-triple top-k sweeps only");
+  constexpr uint32_t GH_BYTES = BN * 8;  // second genre word of the tile's 256 columns
   constexpr int STAGES = L::STAGES;
   using R = Roles<kSym, kWide>;
   constexpr int EPI = R::EPI, PRODUCER_WARP = R::PRODUCER, MMA_WARP = R::MMA;
@@ -344,8 +349,12 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             if (elect_one()) {
               const uint32_t n_th = kMulti ? static_cast<uint32_t>(p.n_weights) : 1u;
-              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u));
+              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u) +
+                                                      (kG2 ? GH_BYTES : 0u));
               bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
+              if (kG2)   // threshold slices 1-2 of this buffer (slice 0 holds the thresholds)
+                bulk_load_1d(smem + L::OFF_TH + (b * kMaxSweep + 1) * MS_BYTES, p.genre_hi + col0, GH_BYTES,
+                             &col_full[b]);
               bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
               if (kSym && !kStats)  // snapshot of the column shows' thresholds (stale = lower = conservative)
                 for (uint32_t w = 0; w < n_th; ++w)
@@ -458,12 +467,13 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int row = p.row_begin + row_local0 + row_in_tile;
       const bool row_valid = row < p.row_end;
       // row-side operands of the fused scores
-      unsigned long long g_bits = 0ull;
+      unsigned long long g_bits = 0ull, g_hi = 0ull;
       uint32_t m_bits = 0u;
       float rn_wg = 0.0f, ci_wm = 0.0f;
       if (row_valid && !kDump) {
         const TvbfColSide rs = p.col_side[row];
         g_bits = rs.genre_bits;
+        if (kG2) g_hi = p.genre_hi[row];
         m_bits = rs.meta_bits;
         rn_wg = rs.genre_rnorm * p.w_genre;
         // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories)
@@ -574,6 +584,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + L::OFF_COL + b * COL_BYTES);
         const float* sms = reinterpret_cast<const float*>(smem + L::OFF_MS + b * MS_BYTES);
         const float* sth = reinterpret_cast<const float*>(smem + L::OFF_TH + b * kMaxSweep * MS_BYTES);
+        const unsigned long long* sgh =
+            reinterpret_cast<const unsigned long long*>(smem + L::OFF_TH + (b * kMaxSweep + 1) * MS_BYTES);
         const uint32_t taddr = tmem_base + tmem_lane + b * BN;
         // off-diagonal tiles also feed the column shows (their mirror tile is never computed)
         const bool do_col = kSym && row_valid && jt != c.sb;
@@ -592,7 +604,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               p.dump[(row_local0 + row_in_tile) * BN + cbase + e] = a;
             } else {
               const TvbfColSide cs = scol[cbase + e];
-              const float gdot = static_cast<float>(__popcll(g_bits & cs.genre_bits)) * cs.genre_rnorm;
+              int gcount = __popcll(g_bits & cs.genre_bits);
+              if (kG2) gcount += __popcll(g_hi & sgh[cbase + e]);
+              const float gdot = static_cast<float>(gcount) * cs.genre_rnorm;
               float mdot = static_cast<float>(__popc(m_bits & cs.meta_bits));
               if (hstack) mdot *= sms[cbase + e];
               float u = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
@@ -844,7 +858,70 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
 // K4s: symmetric mode -- one warp per show: keep the kp best entries of its shared list as the
 // candidate set and derive the bound on everything that is not in it.
-__global__ void __launch_bounds__(128)
+// Lists of up to 32 * Q entries are selected in one go from registers (Q per lane; Q = 8 covers the
+// usual list and every partial list of a multi-GPU job at a quarter of the compares, Q = 32 the
+// rest).  Longer ones (kp > 64, Q = 32) in windows: the kp survivors so far, parked at the head of
+// the list, plus the next 1024 - kp entries; the kp-th value only rises from window to window, so
+// the last one bounds everything that was cut.  All loads of a window are issued back to back.
+template <int Q>
+__device__ __forceinline__ void compact_list(uint2* list, int n_all, int kp, uint2* dst, int lane,
+                                             uint32_t* best_out, int* kept_out) {
+  constexpr int W = 32 * Q;
+  uint32_t best = 0u;  // kp-th largest score bits (0 when n <= kp)
+  int done = 0, kept = 0;
+  do {
+    const int fresh = n_all - done < W - kept ? n_all - done : W - kept;
+    const int n = kept + fresh;
+    uint32_t v[Q], cidx[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int idx = q * 32 + lane;
+      uint2 e = make_uint2(0u, 0u);
+      if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
+      v[q] = idx < n ? e.x : 0u;
+      cidx[q] = e.y;
+    }
+    done += fresh;
+    const bool last = done >= n_all;
+    uint2* out_p = last ? dst : list;
+    best = 0u;
+    if (n > kp) {
+#pragma unroll 1
+      for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t t = best | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) c += (v[q] >= t);
+        c = __reduce_add_sync(kFullMask, c);
+        if (c >= kp) best = t;
+      }
+    }
+    __syncwarp();   // all loads of this window are done before its head is overwritten
+    // entries strictly above the kp-th value always fit; entries equal to it fill the rest
+    int out = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int idx = q * 32 + lane;
+        const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
+        const unsigned bal = __ballot_sync(kFullMask, take);
+        const int pos = out + __popc(bal & ((1u << lane) - 1u));
+        if (take && pos < kp) out_p[pos] = make_uint2(v[q], cidx[q]);
+        out += __popc(bal);
+      }
+      if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
+    }
+    kept = n < kp ? n : kp;
+    __syncwarp();
+    if (last) break;
+    __threadfence_block();
+  } while (true);
+  *best_out = best;
+  *kept_out = kept;
+}
+
+__global__ void __launch_bounds__(128, 6)
 sym_compact_kernel(const K1Params p, int n_rows) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -860,68 +937,10 @@ sym_compact_kernel(const K1Params p, int n_rows) {
     dst = p.peer_cand[owner] + (static_cast<size_t>(p.peer_rank) * p.peer_shard_rows + (r - owner * p.peer_shard_rows)) *
                                    static_cast<size_t>(kp + 1);
   }
-  // Lists of up to 1024 entries are selected in one go from registers (32 per lane).  Longer ones
-  // (kp > 64) in windows: the kp survivors so far, parked at the head of the list, plus the next
-  // 1024 - kp entries; the kp-th value only rises from window to window, so the last one bounds
-  // everything that was cut.
-  uint32_t best = 0u;  // kp-th largest score bits (0 when n <= kp)
-  int done = 0, kept = 0;
-  do {
-    const int fresh = n_all - done < 1024 - kept ? n_all - done : 1024 - kept;
-    const int n = kept + fresh;
-    uint32_t v[32], cidx[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) {
-      v[q] = 0u;
-      cidx[q] = 0u;
-      if (q * 32 < n) {   // warp-uniform: short lists (the usual case, and all partial lists of a
-                          // multi-GPU job) touch only the registers they fill
-        const int idx = q * 32 + lane;
-        uint2 e = make_uint2(0u, 0u);
-        if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
-        v[q] = idx < n ? e.x : 0u;
-        cidx[q] = e.y;
-      }
-    }
-    done += fresh;
-    const bool last = done >= n_all;
-    uint2* out_p = last ? dst : list;
-    best = 0u;
-    if (n > kp) {
-#pragma unroll 1
-      for (int bit = 30; bit >= 0; --bit) {
-        const uint32_t t = best | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (q * 32 < n) c += (v[q] >= t);
-        c = __reduce_add_sync(kFullMask, c);
-        if (c >= kp) best = t;
-      }
-    }
-    __syncwarp();   // all loads of this window are done before its head is overwritten
-    // entries strictly above the kp-th value always fit; entries equal to it fill the rest
-    int out = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        if (q * 32 < n) {
-          const int idx = q * 32 + lane;
-          const bool take = idx < n && (pass == 0 ? v[q] > best : v[q] == best);
-          const unsigned bal = __ballot_sync(kFullMask, take);
-          const int pos = out + __popc(bal & ((1u << lane) - 1u));
-          if (take && pos < kp) out_p[pos] = make_uint2(v[q], cidx[q]);
-          out += __popc(bal);
-        }
-      }
-      if (n <= kp) break;  // everything was taken in pass 0 (best == 0, all scores positive)
-    }
-    kept = n < kp ? n : kp;
-    __syncwarp();
-    if (last) break;
-    __threadfence_block();
-  } while (true);
+  uint32_t best = 0u;
+  int kept = 0;
+  if (n_all <= 256) compact_list<8>(list, n_all, kp, dst, lane, &best, &kept);     // warp-uniform
+  else compact_list<32>(list, n_all, kp, dst, lane, &best, &kept);
   if (lane == 0) {
     const unsigned int th_bits = p.g_theta[r];
     float bound = __int_as_float(0xff800000);                        // nothing dropped so far
@@ -1084,7 +1103,7 @@ static bool profiler_attached() {
   return cached != 0;
 }
 
-template <int E, bool kDump, int CG, int kMode, bool kWide = false>
+template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
   using L = Smem<CG, kWide>;
   CUtensorMap ta, tb;
@@ -1092,7 +1111,7 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   if (rc != TVBF_OK) return rc;
   rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode, kWide>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode, kWide, kG2>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(L::BYTES)));
   const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
@@ -1267,8 +1286,13 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
         // (once per triple of a weight sweep, into that triple's slice of g_theta)
         for (int w = 0; w < nw; ++w) {
           const K1Params seed = make_seed_params(kp, grid, w);
-          int rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
-                               : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
+          int rc;
+          if (kp.genre_hi != nullptr)
+            rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st)
+                             : launch_k1<8, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st);
+          else
+            rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
+                             : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
           if (rc != TVBF_OK) return rc;
           TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
         }
@@ -1285,14 +1309,33 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
     }
     K1Params sweep = kp;
     sweep.tile_stride = 1;
-    if (nw > 1) return launch_k1<4, false, 2, 5>(f, sweep, grid, st);
+    if (nw > 1) {
+      if (kp.genre_hi != nullptr) {
+        tvbf_set_error("the shared weight sweep supports at most 64 genre columns");
+        return TVBF_ERR_INVALID;
+      }
+      return launch_k1<4, false, 2, 5>(f, sweep, grid, st);
+    }
     if (kp.wide_epilogue) {
       if (sweep.stages > Smem<2, true>::STAGES) sweep.stages = Smem<2, true>::STAGES;
-      return launch_k1<4, false, 2, 1, true>(f, sweep, grid, st);
+      return kp.genre_hi ? launch_k1<4, false, 2, 1, true, true>(f, sweep, grid, st)
+                         : launch_k1<4, false, 2, 1, true>(f, sweep, grid, st);
     }
-    return launch_k1<4, false, 2, 1>(f, sweep, grid, st);
+    return kp.genre_hi ? launch_k1<4, false, 2, 1, false, true>(f, sweep, grid, st)
+                       : launch_k1<4, false, 2, 1>(f, sweep, grid, st);
   }
-  if (cta_group == 2) {
+  if (kp.genre_hi != nullptr) {
+    if (cta_group != 2) {
+      tvbf_set_error("two-word genre masks (G > 64) need cta_group 2");
+      return TVBF_ERR_INVALID;
+    }
+    switch (entries_per_lane) {
+      case 4: return launch_k1<4, false, 2, 0, false, true>(f, kp, grid, st);
+      case 8: return launch_k1<8, false, 2, 0, false, true>(f, kp, grid, st);
+      case 16: return launch_k1<16, false, 2, 0, false, true>(f, kp, grid, st);
+      default: break;
+    }
+  } else if (cta_group == 2) {
     switch (entries_per_lane) {
       case 4: return launch_k1<4, false, 2, 0>(f, kp, grid, st);
       case 8: return launch_k1<8, false, 2, 0>(f, kp, grid, st);

@@ -31,6 +31,7 @@ constexpr int kMaxSweep = 5;   // weight triples that can share one symmetric te
 struct K1Params {
   const TvbfColSide* col_side;
   const float* meta_scale;
+  const unsigned long long* genre_hi;   // genre bits 64..127 per show, or NULL (G <= 64)
   uint2* scratch;      // [gridDim.x][128][32*E] working candidate lists (score bits, column)
   uint2* cand;         // [rows][splits][kp] sorted candidates
   int* cand_cnt;       // [rows][splits]

@@ -189,8 +189,8 @@ int tvbf_text_moments(const tvbf_features* f, int32_t with_gram, double* out8, v
   // out8 has TVBF_MOMENTS (24) entries: [0..7] the text moments, [8..12] sum g, g^2, m, m^2, g*m,
   // [13..17] their diagonal terms
   TVBF_REQUIRE(f && out8 && workspace, "tvbf_text_moments: NULL argument");
-  TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED,
-               "tvbf_text_moments needs binary genre / one-hot metadata features");
+  TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED && f->genre_hi == nullptr,
+               "tvbf_text_moments needs binary genre (at most 64 columns) / one-hot metadata features");
   const size_t need = tvbf_text_moments_workspace_bytes(f, with_gram);
   if (workspace_bytes < need) {
     tvbf_set_error("tvbf_text_moments: workspace too small: %zu < %zu", workspace_bytes, need);

@@ -95,14 +95,17 @@ __global__ void dense_to_operand_kernel(const double* __restrict__ dense, int n_
 }
 
 __global__ void genre_bits_kernel(const uint8_t* __restrict__ genre, int n_rows, int dim,
-                                  TvbfColSide* __restrict__ col_side) {
+                                  TvbfColSide* __restrict__ col_side, unsigned long long* __restrict__ genre_hi) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
   const uint8_t* g = genre + static_cast<size_t>(row) * dim;
-  unsigned long long bits = 0ull;
+  unsigned long long bits = 0ull, hi = 0ull;
   for (int c = 0; c < dim; ++c)
-    if (g[c]) bits |= 1ull << c;
-  int pc = __popcll(bits);
+    if (g[c]) {
+      if (c < 64) bits |= 1ull << c; else hi |= 1ull << (c - 64);
+    }
+  int pc = __popcll(bits) + __popcll(hi);
+  if (genre_hi != nullptr) genre_hi[row] = hi;
   col_side[row].genre_bits = bits;
   col_side[row].genre_rnorm = pc ? 1.0f / sqrtf(static_cast<float>(pc)) : 0.0f;
 }
@@ -155,18 +158,22 @@ enum { INGEST_NOT_BINARY = 1, INGEST_NOT_ONE_HOT = 2, INGEST_NOT_CANONICAL = 4, 
 // genre multi-hot of any dtype -> col_side[].genre_bits / genre_rnorm; flags |= NOT_BINARY when a
 // value is neither 0 nor 1 (the caller then takes the general float path)
 __global__ void ingest_genre_kernel(const void* __restrict__ raw, int dtype, int n_rows, int n_pad, int dim,
-                                    TvbfColSide* __restrict__ col_side, int* __restrict__ flags) {
+                                    TvbfColSide* __restrict__ col_side, unsigned long long* __restrict__ genre_hi,
+                                    int* __restrict__ flags) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_pad) return;
-  unsigned long long bits = 0ull;
+  unsigned long long bits = 0ull, hi = 0ull;
   bool bad = false;
   if (row < n_rows)
     for (int c = 0; c < dim; ++c) {
       const double v = load_raw(raw, dtype, static_cast<size_t>(row) * dim + c);
       bad |= !(v == 0.0 || v == 1.0);
-      if (v != 0.0) bits |= 1ull << c;
+      if (v != 0.0) {
+        if (c < 64) bits |= 1ull << c; else hi |= 1ull << (c - 64);
+      }
     }
-  const int pc = __popcll(bits);
+  const int pc = __popcll(bits) + __popcll(hi);
+  if (genre_hi != nullptr) genre_hi[row] = hi;
   col_side[row].genre_bits = bits;
   col_side[row].genre_rnorm = pc ? 1.0f / sqrtf(static_cast<float>(pc)) : 0.0f;
   if (bad) atomicOr(flags, INGEST_NOT_BINARY);
@@ -360,12 +367,13 @@ int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim,
 }
 
 int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,
-                         void* stream) {
+                         uint64_t* genre_hi, void* stream) {
   TVBF_REQUIRE(genre && col_side && n_rows >= 0, "tvbf_prep_genre_bits: bad arguments");
-  TVBF_REQUIRE(dim >= 1 && dim <= 64, "tvbf_prep_genre_bits: dim %d outside 1..64", dim);
+  TVBF_REQUIRE(dim >= 1 && dim <= 128, "tvbf_prep_genre_bits: dim %d outside 1..128", dim);
+  TVBF_REQUIRE(dim <= 64 || genre_hi != nullptr, "tvbf_prep_genre_bits: dim %d needs genre_hi", dim);
   if (n_rows == 0) return TVBF_OK;
   genre_bits_kernel<<<blocks_for(n_rows, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      genre, n_rows, dim, static_cast<TvbfColSide*>(col_side));
+      genre, n_rows, dim, static_cast<TvbfColSide*>(col_side), reinterpret_cast<unsigned long long*>(genre_hi));
   TVBF_LAUNCH_OK("genre_bits_kernel");
   return TVBF_OK;
 }
@@ -388,13 +396,15 @@ int tvbf_prep_meta_ids(const uint8_t* platform, int32_t p_dim, const uint8_t* ty
 }
 
 int tvbf_ingest_genre(const void* raw, int32_t dtype, int32_t n_rows, int32_t n_pad, int32_t dim, void* col_side,
-                      int32_t* flags, void* stream) {
+                      uint64_t* genre_hi, int32_t* flags, void* stream) {
   TVBF_REQUIRE(raw && col_side && flags && n_rows >= 0 && n_pad >= n_rows, "tvbf_ingest_genre: bad arguments");
-  TVBF_REQUIRE(dim >= 1 && dim <= 64, "tvbf_ingest_genre: dim %d outside 1..64", dim);
+  TVBF_REQUIRE(dim >= 1 && dim <= 128, "tvbf_ingest_genre: dim %d outside 1..128", dim);
+  TVBF_REQUIRE(dim <= 64 || genre_hi != nullptr, "tvbf_ingest_genre: dim %d needs genre_hi", dim);
   TVBF_REQUIRE(dtype >= 0 && dtype <= 4, "tvbf_ingest_genre: bad dtype code %d", dtype);
   if (n_pad == 0) return TVBF_OK;
   ingest_genre_kernel<<<blocks_for(n_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      raw, dtype, n_rows, n_pad, dim, static_cast<TvbfColSide*>(col_side), flags);
+      raw, dtype, n_rows, n_pad, dim, static_cast<TvbfColSide*>(col_side),
+      reinterpret_cast<unsigned long long*>(genre_hi), flags);
   TVBF_LAUNCH_OK("ingest_genre_kernel");
   return TVBF_OK;
 }

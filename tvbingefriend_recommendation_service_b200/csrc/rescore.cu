@@ -43,45 +43,6 @@ __device__ __forceinline__ double text_dot(const tvbf_features& f, int i, int j)
   return s;
 }
 
-// Same sum as text_dot(i, j) -- products of the common columns in ascending column order, one rounding
-// per product and per add, so the result is bit-identical -- for a source row i whose entries are
-// staged in shared memory: the entries of row j are independent loads (several in flight) and each
-// is looked up in row i by binary search, instead of a serial merge whose every step waits for a
-// dependent global load.
-constexpr int K5_ROWNNZ = 160;   // entries of the source row staged per warp (longer rows: serial merge)
-
-__device__ __forceinline__ double text_dot_staged(const tvbf_features& f, const int* icols, const double* ivals,
-                                                  int ilen, int j) {
-  const int64_t bj = f.text_indptr[j], ej = f.text_indptr[j + 1];
-  if (ilen == 0 || bj == ej) return 0.0;
-  double s = 0.0;
-  for (int64_t e0 = bj; e0 < ej; e0 += 4) {
-    int c[4];
-    double v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t e = e0 + u;
-      c[u] = e < ej ? f.text_indices[e] : -1;
-      v[u] = e < ej ? f.text_values[e] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (c[u] < 0) break;
-      int lo = 0, hi = ilen;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const int cm = icols[mid];
-        if (cm == c[u]) {
-          s = __dadd_rn(s, __dmul_rn(ivals[mid], v[u]));
-          break;
-        }
-        if (cm < c[u]) lo = mid + 1; else hi = mid;
-      }
-    }
-  }
-  return s;
-}
-
 __device__ __forceinline__ double dense_dot(const double* x, int dim, int i, int j) {
   const double* a = x + static_cast<size_t>(i) * dim;
   const double* b = x + static_cast<size_t>(j) * dim;
@@ -94,9 +55,14 @@ __device__ __forceinline__ double genre_score(const tvbf_features& f, int i, int
   if (f.genre_mode == TVBF_GROUP_PACKED) {
     const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
     const unsigned long long bi = cs[i].genre_bits, bj = cs[j].genre_bits;
-    const int ni = __popcll(bi), nj = __popcll(bj);
+    int ni = __popcll(bi), nj = __popcll(bj), c = __popcll(bi & bj);
+    if (f.genre_hi != nullptr) {   // 64 < G <= 128: second word
+      const unsigned long long hi = f.genre_hi[i], hj = f.genre_hi[j];
+      ni += __popcll(hi);
+      nj += __popcll(hj);
+      c += __popcll(hi & hj);
+    }
     if (ni == 0 || nj == 0) return 0.0;
-    const int c = __popcll(bi & bj);
     return static_cast<double>(c) * ((1.0 / sqrt(static_cast<double>(ni))) *
                                      (1.0 / sqrt(static_cast<double>(nj))));
   }
@@ -168,17 +134,6 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   int* sj = reinterpret_cast<int*>(sm + max_cand);
   uint32_t* su = reinterpret_cast<uint32_t*>(sj + max_cand);
   __shared__ double s_kth[K5_WARPS];
-  // the source row's text entries, staged once for all its candidate pairs
-  __shared__ double s_ivals[K5_WARPS][K5_ROWNNZ];
-  __shared__ int s_icols[K5_WARPS][K5_ROWNNZ];
-  const int64_t ib = sp.f.text_indptr[i];
-  const int ilen = static_cast<int>(sp.f.text_indptr[i + 1] - ib);
-  const bool staged = ilen <= K5_ROWNNZ;
-  if (staged)
-    for (int e = lane; e < ilen; e += 32) {
-      s_icols[warp][e] = sp.f.text_indices[ib + e];
-      s_ivals[warp][e] = sp.f.text_values[ib + e];
-    }
 
   // gather the candidate columns (and their upper bounds U) of all lists
   int total = 0;
@@ -248,15 +203,7 @@ rescore_kernel(const ScoreParams sp, const uint2* __restrict__ cand,
   int valid = 0;
   for (int e = lane; e < total; e += 32) {
     const int j = sj[e];
-    Scores s;
-    if (staged) {
-      s.g = genre_score(sp.f, i, j);
-      s.t = text_dot_staged(sp.f, s_icols[warp], s_ivals[warp], ilen, j);
-      s.m = meta_score(sp.f, i, j);
-      s.h = hybrid_rn(sp.wg, s.g, sp.wt, s.t, sp.wm, s.m);
-    } else {
-      s = score_pair(sp, i, j);
-    }
+    const Scores s = score_pair(sp, i, j);
     const bool ok = (s.h >= sp.min_similarity) && !(sp.exclude_self && j == i);
     sh[e] = ok ? s.h : -INFINITY;
     sg[e] = s.g;
@@ -614,22 +561,22 @@ struct BatchRows {
   int row[MAXB];
   double floor[MAXB];
   double gr[MAXB], mr[MAXB];          // 1/sqrt(set size) of the row's genre / metadata bits
-  unsigned long long gb[MAXB];
+  unsigned long long gb[MAXB], gh[MAXB];
   unsigned int mb[MAXB];
-  double rs[65], m3[4];               // 1/sqrt(n), n/3
+  double rs[129], m3[4];              // 1/sqrt(n), n/3
 };
 
 // hybrid score of batch row r against column show j (text part given); same expressions as
 // genre_score() / meta_score() / score_pair()
 template <int MAXB>
 __device__ __forceinline__ double batch_hybrid(const ScoreParams& sp, const BatchRows<MAXB>& br, int r,
-                                               int j, bool packed, const TvbfColSide& cj, double g_rj,
-                                               double m_rj, double text) {
+                                               int j, bool packed, const TvbfColSide& cj, unsigned long long hj,
+                                               double g_rj, double m_rj, double text) {
   const tvbf_features& f = sp.f;
   double g = 0.0, mm = 0.0;
   if (packed) {
     if (f.genre_mode == TVBF_GROUP_PACKED)
-      g = static_cast<double>(__popcll(br.gb[r] & cj.genre_bits)) * (br.gr[r] * g_rj);
+      g = static_cast<double>(__popcll(br.gb[r] & cj.genre_bits) + __popcll(br.gh[r] & hj)) * (br.gr[r] * g_rj);
     if (f.meta_mode == TVBF_GROUP_PACKED) {
       const int eq = __popc(br.mb[r] & cj.meta_bits);
       mm = f.meta_kind == TVBF_META_MEAN3 ? br.m3[eq] : static_cast<double>(eq) * (br.mr[r] * m_rj);
@@ -643,19 +590,23 @@ __device__ __forceinline__ double batch_hybrid(const ScoreParams& sp, const Batc
 
 template <int MAXB>
 __device__ __forceinline__ void batch_rows_init(BatchRows<MAXB>& br, int tid) {
-  if (tid < 65) br.rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
+  if (tid < 129) br.rs[tid] = tid ? 1.0 / sqrt(static_cast<double>(tid)) : 0.0;
   if (tid < 4) br.m3[tid] = static_cast<double>(tid) / 3.0;
 }
 
 template <int MAXB>
 __device__ __forceinline__ void batch_rows_load(BatchRows<MAXB>& br, int slot, int i, double floor_v,
-                                                bool packed, const TvbfColSide* cs) {
+                                                bool packed, const TvbfColSide* cs,
+                                                const unsigned long long* genre_hi = nullptr) {
   br.row[slot] = i;
   br.floor[slot] = floor_v;
+  br.gh[slot] = 0ull;
   if (packed && i >= 0) {
     const TvbfColSide ci = cs[i];
-    const int gni = __popcll(ci.genre_bits), mni = __popc(ci.meta_bits);
+    const unsigned long long hi = genre_hi ? genre_hi[i] : 0ull;
+    const int gni = __popcll(ci.genre_bits) + __popcll(hi), mni = __popc(ci.meta_bits);
     br.gb[slot] = ci.genre_bits;
+    br.gh[slot] = hi;
     br.mb[slot] = ci.meta_bits;
     br.gr[slot] = gni ? 1.0 / sqrt(static_cast<double>(gni)) : 0.0;
     br.mr[slot] = mni ? 1.0 / sqrt(static_cast<double>(mni)) : 0.0;
@@ -734,6 +685,7 @@ exact_rows_notext_kernel(const ScoreParams sp, const int* __restrict__ rows, int
                 static_cast<size_t>(blockIdx.x) * MAXB * K6B_LIST;
   const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
   const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+  const unsigned long long* ghi = reinterpret_cast<const unsigned long long*>(f.genre_hi);
   // without floors every column is a survivor and the selection runs over dense keys; with floors
   // the survivor lists almost always suffice and the dense keys are not written at all
   const bool dense = floors == nullptr;
@@ -747,24 +699,26 @@ exact_rows_notext_kernel(const ScoreParams sp, const int* __restrict__ rows, int
       if (tid < nb) {
         const int r = rows[list0 + batch * B + tid];
         batch_rows_load(br, tid, rows_are_local ? row_begin + r : r,
-                        floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs);
+                        floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs, ghi);
       } else {
-        batch_rows_load(br, tid, -1, INFINITY, packed, cs);
+        batch_rows_load(br, tid, -1, INFINITY, packed, cs, ghi);
       }
     }
     __syncthreads();
     for (int j = tid; j < n; j += K6B_THREADS) {
       TvbfColSide cj;
+      unsigned long long hj = 0ull;
       double g_rj = 0.0, m_rj = 0.0;
       if (packed) {
         cj = cs[j];
-        g_rj = br.rs[__popcll(cj.genre_bits)];
+        if (ghi) hj = ghi[j];
+        g_rj = br.rs[__popcll(cj.genre_bits) + __popcll(hj)];
         m_rj = br.rs[__popc(cj.meta_bits)];
       }
 #pragma unroll
       for (int r = 0; r < MAXB; ++r) {
         if (r < nb) {
-          const double h = batch_hybrid(sp, br, r, j, packed, cj, g_rj, m_rj, 0.0);
+          const double h = batch_hybrid(sp, br, r, j, packed, cj, hj, g_rj, m_rj, 0.0);
           // only columns that reach the row's floor (a lower bound of its k-th best score) can
           // matter; everything else is "invalid"
           const bool ok = (h >= sp.min_similarity) && (h >= br.floor[r]) && !(sp.exclude_self && j == br.row[r]);
@@ -838,6 +792,7 @@ exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n
   unsigned long long* dense_keys = surv_key + static_cast<size_t>(cap_rows) * K6B_LIST * 3 / 2;
   const bool packed = f.genre_mode != TVBF_GROUP_FOLDED && f.meta_mode != TVBF_GROUP_FOLDED;
   const TvbfColSide* cs = static_cast<const TvbfColSide*>(f.col_side);
+  const unsigned long long* ghi = reinterpret_cast<const unsigned long long*>(f.genre_hi);
   const bool dense = floors == nullptr;
   batch_rows_init(br, tid);
 
@@ -851,12 +806,12 @@ exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n
       if (tid < nb) {
         const int r = rows[list0 + batch * B + tid];
         const int i = rows_are_local ? row_begin + r : r;
-        batch_rows_load(br, tid, i, floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs);
+        batch_rows_load(br, tid, i, floors ? floors[list0 + batch * B + tid] : -INFINITY, packed, cs, ghi);
         s_b[tid] = f.text_indptr[i];
         s_e[tid] = f.text_indptr[i + 1];
         if (!split) cnt[slot0 + tid] = 0;   // per-CTA slots are reused from batch to batch
       } else {
-        batch_rows_load(br, tid, -1, INFINITY, packed, cs);
+        batch_rows_load(br, tid, -1, INFINITY, packed, cs, ghi);
         s_b[tid] = 0; s_e[tid] = 0;
       }
     }
@@ -959,10 +914,12 @@ exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n
       // genre / metadata parts and the survivor test (all lanes stay in: ballots below)
       const bool in = j < n;
       TvbfColSide cj{0ull, 0.0f, 0u};
+      unsigned long long hj = 0ull;
       double g_rj = 0.0, m_rj = 0.0;
       if (packed && in) {
         cj = cs[j];
-        g_rj = br.rs[__popcll(cj.genre_bits)];
+        if (ghi) hj = ghi[j];
+        g_rj = br.rs[__popcll(cj.genre_bits) + __popcll(hj)];
         m_rj = br.rs[__popc(cj.meta_bits)];
       }
 #pragma unroll
@@ -971,7 +928,7 @@ exact_rows_text_kernel(const ScoreParams sp, const int* __restrict__ rows, int n
           bool ok = false;
           unsigned long long key = 0ull;
           if (in) {
-            const double h = batch_hybrid(sp, br, r, j, packed, cj, g_rj, m_rj, acc[r]);
+            const double h = batch_hybrid(sp, br, r, j, packed, cj, hj, g_rj, m_rj, acc[r]);
             ok = (h >= sp.min_similarity) && (h >= br.floor[r]) && !(sp.exclude_self && j == br.row[r]);
             key = ok ? f64_orderable(h) : 0ull;
             if (dense) dense_keys[static_cast<size_t>(slot0 + r) * n + j] = key;

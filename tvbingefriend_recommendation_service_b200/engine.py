@@ -88,7 +88,7 @@ def stage(features: dict, metadata_mode: str = "mean3", pin: bool = True) -> Sta
     for name, a in (("text", text), ("platform", plat), ("type", typ), ("language", lang)):
         if a.shape[0] != n:
             raise ValueError(f"{name}_features has {a.shape[0]} rows, genre_features has {n}")
-    genre_packed = genre.ndim == 2 and 1 <= genre.shape[1] <= 64 and _is_binary(genre)
+    genre_packed = genre.ndim == 2 and 1 <= genre.shape[1] <= 128 and _is_binary(genre)   # two 64-bit words
     # the three one-hot groups are packed into one 32-bit mask per show (reference defaults:
     # 21 platforms + 5 types + 6 languages = 32 columns, feature_extractor.py:122-193)
     meta_packed = (plat.shape[1] + typ.shape[1] + lang.shape[1] <= 32) and \
@@ -327,7 +327,14 @@ class HybridTopKEngine:
 
             if st.genre_packed:
                 g8 = raw["genre"]
-                check(lib.tvbf_prep_genre_bits(g8.data_ptr(), n, g8.shape[1], col_side.data_ptr(), stream),
+                genre_hi = None
+                if g8.shape[1] > 64:      # second mask word for genre columns 64..127
+                    genre_hi = torch.empty((n_pad,), dtype=torch.int64, device=dev)
+                    self._zero(genre_hi)
+                    keep.append(genre_hi)
+                    f.genre_hi = genre_hi.data_ptr()
+                check(lib.tvbf_prep_genre_bits(g8.data_ptr(), n, g8.shape[1], col_side.data_ptr(),
+                                               None if genre_hi is None else genre_hi.data_ptr(), stream),
                       "tvbf_prep_genre_bits")
                 f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(g8.shape[1])
             else:
@@ -397,7 +404,7 @@ class HybridTopKEngine:
 
         if not (sp.issparse(text) and text.format == "csr"):
             return slow()
-        ok = genre.ndim == 2 and 1 <= genre.shape[1] <= 64 and genre.dtype in self._RAW_DTYPES
+        ok = genre.ndim == 2 and 1 <= genre.shape[1] <= 128 and genre.dtype in self._RAW_DTYPES
         ok = ok and all(a.ndim == 2 and a.dtype in self._RAW_DTYPES for a in groups)
         ok = ok and sum(a.shape[1] for a in groups) <= 32 and all(a.shape[1] >= 1 for a in groups)
         ok = ok and text.data.dtype in (np.float32, np.float64) and text.indptr.dtype in (np.int32, np.int64) \
@@ -431,8 +438,10 @@ class HybridTopKEngine:
                                       int(text.indices.dtype == np.int64), d_values.data_ptr(),
                                       int(text.data.dtype == np.float64), n, indptr.data_ptr(), indices.data_ptr(),
                                       rawv.data_ptr(), flags.data_ptr(), stream), "tvbf_ingest_csr")
+            genre_hi = torch.empty((n_pad,), dtype=torch.int64, device=dev) if genre.shape[1] > 64 else None
             check(lib.tvbf_ingest_genre(d_genre.data_ptr(), self._RAW_DTYPES[genre.dtype], n, n_pad, int(genre.shape[1]),
-                                        col_side.data_ptr(), flags.data_ptr(), stream), "tvbf_ingest_genre")
+                                        col_side.data_ptr(), None if genre_hi is None else genre_hi.data_ptr(),
+                                        flags.data_ptr(), stream), "tvbf_ingest_genre")
             g0, g1, g2 = groups
             check(lib.tvbf_ingest_meta(d_groups[0].data_ptr(), self._RAW_DTYPES[g0.dtype], int(g0.shape[1]),
                                        d_groups[1].data_ptr(), self._RAW_DTYPES[g1.dtype], int(g1.shape[1]),
@@ -455,10 +464,11 @@ class HybridTopKEngine:
             f.col_side, f.meta_scale = col_side.data_ptr(), meta_scale.data_ptr()
             f.meta_kind = kind
             f.genre_mode, f.genre_dim = _lib.GROUP_PACKED, int(genre.shape[1])
+            f.genre_hi = None if genre_hi is None else genre_hi.data_ptr()
             f.meta_mode = _lib.GROUP_PACKED
             f.text_signed = int(bool(bits & 8))
         return DeviceCatalogue(c=f, n_shows=n, folded=False, weights_baked=None,
-                               keep=[indptr, indices, values, operand, col_side, meta_scale],
+                               keep=[indptr, indices, values, operand, col_side, meta_scale, genre_hi],
                                operand=operand, text_indptr=indptr, text_indices=indices)
 
     def _text_operand(self, indptr, indices, rawv, n: int, n_pad: int, k_pad: int,
@@ -553,6 +563,7 @@ class HybridTopKEngine:
         triples = [tuple(float(x) for x in w) for w in weight_list]
         if shared is None:
             shared = (exclude_self and cat.n_shows >= 40_000 and len(triples) > 1 and not kw
+                      and not cat.c.genre_hi        # the shared sweep keeps one-word genre masks
                       and all(self.sym_eligible(cat, w, k, min_similarity) for w in triples))
         if not shared:
             return [self.top_k_device(cat, w, k, min_similarity, exclude_self, tuning=tuning, **kw) for w in triples]
