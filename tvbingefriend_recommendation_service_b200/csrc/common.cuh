@@ -116,6 +116,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that can last a whole tile (the roles that run AHEAD of the bottleneck: in the
+// epilogue-bound regime the producer and the MMA issuer, in the MMA-bound regime the epilogue).  A
+// tight try_wait loop issues an instruction every ~12 cycles and, sharing a scheduler with working
+// warps, takes issue slots from them (ncu on P80k: half of all executed warp instructions were
+// these polls).  After `quick` failed polls the thread sleeps between polls.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t quick = 16,
+                                                  uint32_t sleep_ns = 64) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > quick) __nanosleep(sleep_ns);
+    if (spins > (1u << 23)) {
+      printf("tvbf: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
+             (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // One lane of a fully converged warp (warp-uniform control flow keeps addresses and descriptors
 // in uniform registers; a divergent `if (lane == 0)` region makes the compiler wrap every TMA /
 // tcgen05 instruction in an elect-and-loop sequence that costs more than the MMA it issues).

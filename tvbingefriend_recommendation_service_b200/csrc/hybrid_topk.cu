@@ -31,7 +31,7 @@ constexpr int UMMA_K = 16;
 constexpr uint32_t A_BYTES = BM * BK * 2;
 constexpr uint32_t COL_BYTES = BN * sizeof(TvbfColSide);
 constexpr uint32_t MS_BYTES = BN * sizeof(float);
-constexpr int SYMQ = 4;     // pending appends a thread can hold between two flushes
+constexpr int RING = 128;   // pending list appends an epilogue warp can hold between two flushes
 // warps 0..EPI-1: epilogue (warp w may touch TMEM lanes 32*(w%4)..+31); then the TMA producer and
 // the MMA issuer.  The SM's issue arbiter favours higher warp ids, so the two single-lane roles,
 // which share schedulers with epilogue warps, are never starved by the epilogue's ALU stream.
@@ -65,9 +65,9 @@ struct Smem {
   static constexpr uint32_t OFF_COL = OFF_B + STAGES * B_BYTES;
   static constexpr uint32_t OFF_MS = OFF_COL + 2 * COL_BYTES;
   static constexpr uint32_t OFF_TH = OFF_MS + 2 * MS_BYTES;   // symmetric mode: column thresholds
-  // symmetric mode: per-thread queues of pending list appends, SoA [3][SYMQ][256] words
+  // symmetric mode: one ring of pending list appends per epilogue warp, SoA [3][RING] words
   static constexpr uint32_t OFF_Q = OFF_TH + 2 * kMaxSweep * MS_BYTES;   // (one slice per triple of a weight sweep)
-  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * SYMQ * QTHREADS * 4;
+  static constexpr uint32_t OFF_BAR = OFF_Q + 3 * RING * (QTHREADS / 32) * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr uint32_t USED = OFF_TMEM + 16;
@@ -194,31 +194,113 @@ __host__ __device__ __forceinline__ ItemCoord item_coord(const K1Params& p, int 
 }
 
 // ---- symmetric mode helpers ---------------------------------------------------------------------
-// Raise the shared threshold of one show to the kp-th largest score of the first n entries of its
-// list (n a power of two).  Entries reserved but not yet written read as 0 = -inf, so the
-// result can only be too LOW, never too high.  Warp-cooperative, deliberately not inlined.
+// Raise the shared threshold of one show to (a lower bound of) the kp-th largest score of the first
+// n entries of its list.  Entries reserved but not yet written read as 0 = -inf, so the result can
+// only be too LOW, never too high.  Warp-cooperative, Q entries per lane (32 * Q >= n).
+// The radix select starts below the bits all written entries share (scores of one list lie within a
+// factor of two of each other, so sign, exponent and the leading mantissa bits are skipped) and stops
+// at bit 8: the threshold is rounded DOWN to 23 significant bits of the ordering, 2^-15 relative --
+// still a valid bound, and a refresh costs a third of the full 31-bit select.
+template <int Q>
+__device__ __forceinline__ void refresh_theta_q(const uint2* list, int n, int kp, unsigned int* theta_slot,
+                                                int lane) {
+  uint32_t v[Q];
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  int written = 0;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int idx = q * 32 + lane;
+    v[q] = idx < n ? __ldcg(list + idx).x : 0u;
+    if (v[q] != 0u) { lo = min(lo, v[q]); ++written; }
+    hi = max(hi, v[q]);
+  }
+  lo = __reduce_min_sync(kFullMask, lo);
+  hi = __reduce_max_sync(kFullMask, hi);
+  written = __reduce_add_sync(kFullMask, written);
+  if (written < kp) return;                       // warp-uniform
+  const int top = 31 - __clz(lo ^ hi);            // highest bit in which two written entries differ (-1: none)
+  uint32_t best = top >= 0 ? (hi >> (top + 1)) << (top + 1) : hi;   // the shared prefix: count(v >= best) = written >= kp
+#pragma unroll 1
+  for (int bit = top; bit >= 8; --bit) {
+    const uint32_t t = best | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) c += (v[q] >= t);
+    c = __reduce_add_sync(kFullMask, c);
+    if (c >= kp) best = t;
+  }
+  if (lane == 0) atomicMax(theta_slot, best);
+}
+
+// Deliberately not inlined: it runs a few times per show per sweep.
 __device__ __noinline__ void sym_refresh_theta(const uint2* list, int n, int kp,
                                                unsigned int* theta_slot, int lane) {
   // lists longer than 1024 (kp > 64): the most recent 1024 entries -- the kp-th largest of ANY
   // subset is a valid lower bound, and the latest entries passed the highest thresholds
   if (n > 1024) { list += n - 1024; n = 1024; }
-  uint32_t v[32];
+  if (n <= 64) refresh_theta_q<2>(list, n, kp, theta_slot, lane);
+  else if (n <= 128) refresh_theta_q<4>(list, n, kp, theta_slot, lane);
+  else if (n <= 256) refresh_theta_q<8>(list, n, kp, theta_slot, lane);
+  else if (n <= 512) refresh_theta_q<16>(list, n, kp, theta_slot, lane);
+  else refresh_theta_q<32>(list, n, kp, theta_slot, lane);
+}
+
+// Drain one epilogue warp's ring of pending appends {show, score bits, other show} into the shared
+// lists.  An append needs the slot returned by an atomicAdd (a ~700-cycle round trip): all atomics of
+// the ring are issued back to back, one entry per lane and pass, so the warp pays the round trip once
+// per flush.  A list that reaches 2*kp, 4*kp, ... entries gets its threshold refreshed.
+// Not inlined: the scoring loop around it must stay small enough for the instruction cache.
+__device__ __noinline__ void sym_ring_flush(const uint32_t* ring, int n, unsigned int* g_cnt, uint2* g_list,
+                                            unsigned int* g_theta, unsigned sym_cap, int kp, int lane) {
+  constexpr int J = RING / 32;
+  uint32_t sh[J];
+  unsigned pos[J];
 #pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    const int idx = q * 32 + lane;
-    v[q] = idx < n ? __ldcg(list + idx).x : 0u;
+  for (int j = 0; j < J; ++j) {
+    const int i = j * 32 + lane;
+    sh[j] = 0u;
+    pos[j] = 0xFFFFFFFFu;
+    if (i < n) {
+      sh[j] = ring[i];
+      pos[j] = atomicAdd(g_cnt + sh[j], 1u);
+    }
   }
-  uint32_t best = 0u;  // largest t with count(v >= t) >= kp  ==  kp-th largest value
-#pragma unroll 1
-  for (int bit = 30; bit >= 0; --bit) {
-    const uint32_t t = best | (1u << bit);
-    int c = 0;
+  unsigned trig = 0u;   // bit j: entry j of this lane completed a list length that asks for a refresh
+  const unsigned first = static_cast<unsigned>(2 * kp);
 #pragma unroll
-    for (int q = 0; q < 32; ++q) c += (v[q] >= t);
-    c = __reduce_add_sync(kFullMask, c);
-    if (c >= kp) best = t;
+  for (int j = 0; j < J; ++j) {
+    const int i = j * 32 + lane;
+    if (pos[j] < sym_cap) {   // lanes without an entry hold 0xFFFFFFFF; an overflowing list drops the entry
+      __stcg(g_list + static_cast<size_t>(sh[j]) * sym_cap + pos[j], make_uint2(ring[RING + i], ring[2 * RING + i]));
+      const unsigned np = pos[j] + 1u;
+      if (np >= first && (np & pos[j]) == 0u) trig |= 1u << j;
+    }
   }
-  if (lane == 0) atomicMax(theta_slot, best);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (j * 32 >= n) break;   // warp-uniform
+    unsigned need = __ballot_sync(kFullMask, ((trig >> j) & 1u) != 0u);
+    while (need) {
+      const int src_lane = __ffs(need) - 1;
+      need &= need - 1;
+      const uint32_t show = __shfl_sync(kFullMask, sh[j], src_lane);
+      const int len = static_cast<int>(__shfl_sync(kFullMask, pos[j], src_lane)) + 1;
+      sym_refresh_theta(g_list + static_cast<size_t>(show) * sym_cap, len, kp, g_theta + show, lane);
+    }
+  }
+}
+
+// u[e] for a run-time e without spilling the array to local memory: a select tree
+template <int GW>
+__device__ __forceinline__ float pick(const float (&u)[GW], int e) {
+  static_assert(GW == 4 || GW == 8, "group width");
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = (GW == 8 && (e & 4) != 0) ? u[(i + 4) % GW] : u[i];
+  const bool s2 = (e & 2) != 0, s1 = (e & 1) != 0;
+  const float c0 = s2 ? a[2] : a[0], c1 = s2 ? a[3] : a[1];
+  return s1 ? c1 : c0;
 }
 
 // Grid-wide pacing of the TMA producers.  Operand tiles are shared between CTAs only through L2
@@ -272,8 +354,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   constexpr int STAGES = L::STAGES;
   using R = Roles<kSym, kWide>;
   constexpr int EPI = R::EPI, PRODUCER_WARP = R::PRODUCER, MMA_WARP = R::MMA;
-  constexpr int QT = L::QTHREADS;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
+  constexpr int GW = kWide ? 4 : 8;               // columns scored together (independent chains)
   const uint32_t nstages = static_cast<uint32_t>(p.stages);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles; done as an OFFSET so the compiler still knows
@@ -346,7 +428,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t b = it & 1;
           const int col0 = kDump ? p.dump_col0 : jt * BN;
           if (!kDump) {
-            mbar_wait(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
+            mbar_wait_backoff(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
             if (elect_one()) {
               const uint32_t n_th = kMulti ? static_cast<uint32_t>(p.n_weights) : 1u;
               mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u) +
@@ -370,7 +452,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (kb) pacer.done_chunk(lane == 0);
               pacer.wait_turn();
             }
-            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_wait_backoff(&empty[stage], phase ^ 1);
             if (elect_one()) {
               uint8_t* sa = smem + L::OFF_A + stage * A_BYTES;
               uint8_t* sb = smem + L::OFF_B + stage * L::B_BYTES;
@@ -408,11 +490,11 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
         for (int jt = tile_beg; jt < tile_end; jt += p.tile_stride, ++it) {
           const uint32_t b = it & 1;
-          mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // every epilogue drained accumulator b
+          mbar_wait_backoff(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // every epilogue drained accumulator b
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + b * BN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(&full[stage], phase);
+            mbar_wait_backoff(&full[stage], phase, 64, 32);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da = desc_a0 + static_cast<uint64_t>(stage * (A_BYTES >> 4));
@@ -459,6 +541,9 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int b = threadIdx.x; b < 4 * kStatsBins; b += 32 * EPI) shist[b] = 0u;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
     }
+    // symmetric sweeps: this warp's ring of pending list appends and its (warp-uniform) fill count
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + L::OFF_Q) + warp * (3 * RING);
+    int ring_n = 0;
     for (int item = cluster_id; item < n_items; item += num_clusters) {
       ItemCoord c = item_coord(p, item);
       if (kDump) { c.sb = 0; c.tile0 = 0; c.tile1 = 1; }
@@ -476,11 +561,12 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (kG2) g_hi = p.genre_hi[row];
         m_bits = rs.meta_bits;
         rn_wg = rs.genre_rnorm * p.w_genre;
-        // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories)
-        ci_wm = p.meta_scale[row] * p.w_meta * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
+        // MEAN3: (matches / 3) * w = matches * (1/sqrt3)^2 * w; HSTACK: per-show 1/sqrt(#categories);
+        // meta_scale[] holds the factor of either kind, for the row here and per column in the epilogue
+        ci_wm = p.meta_scale[row] * p.w_meta;
         if (kStats || kMulti) {  // plain cosines here; the weights enter only the hybrid
           rn_wg = rs.genre_rnorm;
-          ci_wm = p.meta_scale[row] * (p.meta_hstack ? 1.0f : 0.57735026918962576f);
+          ci_wm = p.meta_scale[row];
         }
       }
       float theta = row_valid ? p.theta_init : __int_as_float(0x7f800000);  // +inf: never append
@@ -507,61 +593,42 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         terms = static_cast<float>(p.text_indptr[row + 1] - p.text_indptr[row]) + static_cast<float>(p.folded_cols);
       const float w_text = p.w_text, w_text_err = fmaf(terms, p.w_text_acc, p.w_text_err),
                   eps = fmaf(terms, p.eps_term, p.eps);
-      const bool hstack = p.meta_hstack != 0;
-      // symmetric mode: pending threshold refreshes (show, list length) raised by this lane
-      int pend_r = -1, pend_n = 0, pend2_r = -1, pend2_n = 0;
       const unsigned sym_cap = static_cast<unsigned>(p.sym_cap);
-      const unsigned sym_first = static_cast<unsigned>(2 * p.kp);
 
       // Shared-list appends need the slot returned by an atomicAdd; done on the spot that round trip
-      // (~700 cycles) would stall the warp once per append.  Appends are therefore queued in shared
-      // memory (per-thread FIFO) and flushed every 64 columns with the atomics of a whole batch in
-      // flight together.  A later append only delays a candidate, it never loses one.
-      uint32_t* q_show = reinterpret_cast<uint32_t*>(smem + L::OFF_Q) + (warp * 32 + lane);
-      uint32_t* q_score = q_show + SYMQ * QT;
-      uint32_t* q_other = q_score + SYMQ * QT;
-      int qn = 0;
-      auto sym_commit = [&](int show, uint32_t ubits, uint32_t other, unsigned pos) {
-        if (pos < sym_cap) {
-          __stcg(p.g_list + static_cast<size_t>(show) * sym_cap + pos, make_uint2(ubits, other));
-          const unsigned np = pos + 1u;
-          // refresh the show's threshold when its list reaches 2*kp, 4*kp, ... entries
-          if (np >= sym_first && (np & pos) == 0u) {
-            if (pend_n == 0) { pend_r = show; pend_n = static_cast<int>(np); }
-            else { pend2_r = show; pend2_n = static_cast<int>(np); }
-          }
-        }
+      // (~700 cycles) would stall the warp once per append.  Appends are therefore collected in a
+      // per-warp ring in shared memory -- filled densely by warp-uniform code: ballot + prefix, the
+      // fill count lives in a register -- and drained by sym_ring_flush with one entry per lane, all
+      // atomics of the ring in flight together.  A later append only delays a candidate, it never
+      // loses one.
+      auto ring_flush = [&]() {
+        __syncwarp();
+        sym_ring_flush(ring, ring_n, p.g_cnt, p.g_list, p.g_theta, sym_cap, p.kp, lane);
+        ring_n = 0;
+        __syncwarp();
       };
-      auto sym_append = [&](int show, float u, int other) {
-        if (qn < SYMQ) {
-          q_show[qn * QT] = static_cast<uint32_t>(show);
-          q_score[qn * QT] = __float_as_uint(u);
-          q_other[qn * QT] = static_cast<uint32_t>(other);
-          ++qn;
-        } else {  // queue full (rare): pay the round trip now
-          sym_commit(show, __float_as_uint(u), static_cast<uint32_t>(other), atomicAdd(p.g_cnt + show, 1u));
-        }
-      };
-      auto sym_flush = [&]() {
-        const int maxn = __reduce_max_sync(kFullMask, qn);
-        for (int base = 0; base < maxn; base += 4) {
-          unsigned pos[4];
-          uint32_t sh[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sh[j] = 0u;
-            pos[j] = 0xFFFFFFFFu;
-            if (base + j < qn) {
-              sh[j] = q_show[(base + j) * QT];
-              pos[j] = atomicAdd(p.g_cnt + sh[j], 1u);
-            }
+      // hits: bit e (e < GW) = offer u[e] to this thread's show, bit GW + e = offer it to column
+      // colbase + e; voff = first virtual show id of the weight triple
+      auto push_hits = [&](uint32_t hits, const float (&u)[GW], int colbase, int voff) {
+        while (__any_sync(kFullMask, hits != 0u)) {   // warp-uniform: max hits of any lane (usually 1)
+          if (ring_n > RING - 32) ring_flush();
+          const int bit = hits != 0u ? __ffs(hits) - 1 : 0;
+          const bool to_row = bit < GW;
+          const float ue = pick<GW>(u, bit & (GW - 1));
+          const int col = colbase + (bit & (GW - 1));
+          // a row-side append may only name a real show other than the row's own (checked here, on the
+          // rare path, instead of masking every group); padded columns carry threshold +inf
+          const bool act = hits != 0u && (!to_row || (col != self_col && col < p.n_shows));
+          hits &= hits - 1u;
+          const unsigned m = __ballot_sync(kFullMask, act);
+          const int slot = ring_n + __popc(m & ((1u << lane) - 1u));
+          if (act) {
+            ring[slot] = static_cast<uint32_t>(voff + (to_row ? row : col));
+            ring[RING + slot] = __float_as_uint(ue);
+            ring[2 * RING + slot] = static_cast<uint32_t>(to_row ? col : row);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (base + j < qn)
-              sym_commit(static_cast<int>(sh[j]), q_score[(base + j) * QT], q_other[(base + j) * QT], pos[j]);
+          ring_n += __popc(m);
         }
-        qn = 0;
       };
 
       const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
@@ -578,8 +645,8 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
           theta = __uint_as_float(tb);
         }
-        if (!kDump) mbar_wait(&col_full[b], ph);
-        mbar_wait(&acc_full[b], ph);
+        if (!kDump) mbar_wait_backoff(&col_full[b], ph, 32, 32);
+        mbar_wait_backoff(&acc_full[b], ph, 32, 32);
         tc_fence_after();
         const TvbfColSide* scol = reinterpret_cast<const TvbfColSide*>(smem + L::OFF_COL + b * COL_BYTES);
         const float* sms = reinterpret_cast<const float*>(smem + L::OFF_MS + b * MS_BYTES);
@@ -594,92 +661,142 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float stat_scale[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) stat_scale[q] = kStats ? static_cast<float>(kStatsBins) / p.stats->hi[q] : 0.f;
-        // score 16 accumulator columns held in registers
+
+        // plain genre / metadata dots of accumulator column cbase + e against this thread's show
+        auto side_dots = [&](int ce, float& gdot, float& mdot) {
+          const TvbfColSide cs = scol[ce];
+          int gcount = __popcll(g_bits & cs.genre_bits);
+          if (kG2) gcount += __popcll(g_hi & sgh[ce]);
+          gdot = static_cast<float>(gcount) * cs.genre_rnorm;
+          // per-column scale: 1/sqrt(#categories) (HSTACK) or 1/sqrt(3) (MEAN3: matches / 3), 0 for padding
+          mdot = static_cast<float>(__popc(m_bits & cs.meta_bits)) * sms[ce];
+        };
+        // Score 16 accumulator columns held in registers.  The candidate sweeps (everything but the
+        // statistics and dump variants) are written BRANCH-FREE: the sixteen upper bounds are
+        // independent dependency chains (LDS -> POPC -> I2F -> FMUL -> 4 FFMA) the scheduler can
+        // overlap (in groups of GW = 8, or 4 under the 96-register cap of the 16-warp variant), and the comparisons only set
+        // bits of two hit masks.  With a branch per element
+        // (round 1) the chains ran one after the other and the epilogue was latency-bound at ~13 % of
+        // the issue slots on small vocabularies.
         auto score16 = [&](const uint32_t (&acc)[16], int cbase) {
-          float gcv[kMulti ? 16 : 1], mcv[kMulti ? 16 : 1];   // weight sweep: cosines of the 16 columns
+          if constexpr (kDump) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float a = __uint_as_float(acc[e]);
-            if (kDump) {
-              p.dump[(row_local0 + row_in_tile) * BN + cbase + e] = a;
-            } else {
-              const TvbfColSide cs = scol[cbase + e];
-              int gcount = __popcll(g_bits & cs.genre_bits);
-              if (kG2) gcount += __popcll(g_hi & sgh[cbase + e]);
-              const float gdot = static_cast<float>(gcount) * cs.genre_rnorm;
-              float mdot = static_cast<float>(__popc(m_bits & cs.meta_bits));
-              if (hstack) mdot *= sms[cbase + e];
-              float u = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
-              u = fmaf(a, w_text, u);
-              u = fmaf(fabsf(a), w_text_err, u);
+            for (int e = 0; e < 16; ++e)
+              p.dump[(row_local0 + row_in_tile) * BN + cbase + e] = __uint_as_float(acc[e]);
+          } else if constexpr (kStats) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(acc[e]);
+              float gdot, mdot;
+              side_dots(cbase + e, gdot, mdot);
               const int col = col0 + cbase + e;
-              if (kStats) {
-                if (row_valid && col > row && col < p.n_shows) {   // strict upper triangle
-                  float v[4];
-                  v[0] = gdot * rn_wg;
-                  v[1] = a * p.inv_scale2;
-                  v[2] = mdot * ci_wm;
-                  v[3] = fmaf(p.w_genre, v[0], fmaf(p.w_text_plain, v[1], p.w_meta * v[2]));
-                  tile_gm = fmaf(v[0], v[2], tile_gm);
+              if (row_valid && col > row && col < p.n_shows) {   // strict upper triangle
+                float v[4];
+                v[0] = gdot * rn_wg;
+                v[1] = a * p.inv_scale2;
+                v[2] = mdot * ci_wm;
+                v[3] = fmaf(p.w_genre, v[0], fmaf(p.w_text_plain, v[1], p.w_meta * v[2]));
+                tile_gm = fmaf(v[0], v[2], tile_gm);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    tile_sum[q] += v[q];
-                    tile_sq[q] = fmaf(v[q], v[q], tile_sq[q]);
-                    st_min[q] = fminf(st_min[q], v[q]);
-                    st_max[q] = fmaxf(st_max[q], v[q]);
-                    if (v[q] == 0.0f) {
-                      ++st_zero[q];
-                    } else {
-                      int bin = static_cast<int>(v[q] * stat_scale[q]);
-                      bin = bin < 0 ? 0 : (bin >= kStatsBins ? kStatsBins - 1 : bin);
-                      atomicAdd(&shist[q * kStatsBins + bin], 1u);
-                    }
+                for (int q = 0; q < 4; ++q) {
+                  tile_sum[q] += v[q];
+                  tile_sq[q] = fmaf(v[q], v[q], tile_sq[q]);
+                  st_min[q] = fminf(st_min[q], v[q]);
+                  st_max[q] = fmaxf(st_max[q], v[q]);
+                  if (v[q] == 0.0f) {
+                    ++st_zero[q];
+                  } else {
+                    int bin = static_cast<int>(v[q] * stat_scale[q]);
+                    bin = bin < 0 ? 0 : (bin >= kStatsBins ? kStatsBins - 1 : bin);
+                    atomicAdd(&shist[q * kStatsBins + bin], 1u);
                   }
-                  if (v[1] > st_arg_v[0]) { st_arg_v[0] = v[1]; st_arg_i[0] = row; st_arg_j[0] = col; }
-                  if (v[3] > st_arg_v[1]) { st_arg_v[1] = v[3]; st_arg_i[1] = row; st_arg_j[1] = col; }
                 }
-              } else if (kMulti) {
-                gcv[e] = gdot * rn_wg;   // plain genre / metadata cosines, scored per triple below
-                mcv[e] = mdot * ci_wm;
-              } else if (kSym) {
-                if (u > theta && col != self_col && col < p.n_shows) sym_append(row, u, col);
-                // padded columns carry threshold +inf, so no bound check is needed here
-                if (do_col && u > sth[cbase + e]) sym_append(col, u, row);
-              } else if (u > theta) {
-                if (col != self_col && col < p.n_shows) {
-                  __stcg(my_list + cnt, make_uint2(__float_as_uint(u), static_cast<uint32_t>(col)));
-                  ++cnt;
-                }
+                if (v[1] > st_arg_v[0]) { st_arg_v[0] = v[1]; st_arg_i[0] = row; st_arg_j[0] = col; }
+                if (v[3] > st_arg_v[1]) { st_arg_v[1] = v[3]; st_arg_i[1] = row; st_arg_j[1] = col; }
               }
             }
-          }
-          if (kMulti) {
-            // Weight sweep: one pass per triple over the 16 columns (rolled over the triples so that
-            // the code stays the size of the single-triple kernel).  Triple w's lists live under the
-            // virtual show id w * n_pad + show.
-#pragma unroll 1
-            for (int w = 0; w < p.n_weights; ++w) {
-              const float wg = p.mw_genre[w], wm = p.mw_meta[w], wt = p.mw_text[w],
-                          wte = fmaf(terms, p.mw_text_acc[w], p.mw_text_err[w]),
-                          we = fmaf(terms, p.mw_eps_term[w], p.mw_eps[w]);
-              const float th = w == 0 ? thw[0] : (w == 1 ? thw[1] : (w == 2 ? thw[2] : (w == 3 ? thw[3] : thw[4])));
-              const float4* t4p = reinterpret_cast<const float4*>(sth + w * BN + cbase);
-              const int vrow = w * p.n_pad + row, vcol0 = w * p.n_pad + col0 + cbase;
+          } else if constexpr (kMulti) {
+            // Weight sweep: the plain cosines of 8 columns once, then one branch-free pass per triple
+            // (rolled over the triples so that the code stays the size of the single-triple kernel).
+            // Triple w's lists live under the virtual show id w * n_pad + show.
 #pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                const float4 t4 = t4p[e4];
+            for (int h = 0; h < 16 / GW; ++h) {
+              float gcv[GW], mcv[GW];
+#pragma unroll
+              for (int e = 0; e < GW; ++e) {
+                float gdot, mdot;
+                side_dots(cbase + h * GW + e, gdot, mdot);
+                gcv[e] = gdot * rn_wg;
+                mcv[e] = mdot * ci_wm;
+              }
+#pragma unroll 1
+              for (int w = 0; w < p.n_weights; ++w) {
+                const float wg = p.mw_genre[w], wm = p.mw_meta[w], wt = p.mw_text[w],
+                            wte = fmaf(terms, p.mw_text_acc[w], p.mw_text_err[w]),
+                            we = fmaf(terms, p.mw_eps_term[w], p.mw_eps[w]);
+                const float th = w == 0 ? thw[0] : (w == 1 ? thw[1] : (w == 2 ? thw[2] : (w == 3 ? thw[3] : thw[4])));
+                const float4* t4p = reinterpret_cast<const float4*>(sth + w * BN + cbase + h * GW);
+                float u[GW];
+                uint32_t hit_r = 0u, hit_c = 0u;
+#pragma unroll
+                for (int e4 = 0; e4 < GW / 4; ++e4) {
+                  const float4 t4 = t4p[e4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const int e = e4 * 4 + q;
+                    const float a = __uint_as_float(acc[h * GW + e]);
+                    float uw = fmaf(gcv[e], wg, fmaf(mcv[e], wm, we));
+                    uw = fmaf(a, wt, uw);
+                    uw = fmaf(fabsf(a), wte, uw);
+                    u[e] = uw;
+                    const float tc = q == 0 ? t4.x : (q == 1 ? t4.y : (q == 2 ? t4.z : t4.w));
+                    hit_r |= uw > th ? (1u << e) : 0u;
+                    hit_c |= uw > tc ? (1u << e) : 0u;   // padded columns carry threshold +inf
+                  }
+                }
+                if (!do_col) hit_c = 0u;
+                push_hits(hit_r | (hit_c << GW), u, col0 + cbase + h * GW, w * p.n_pad);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int h = 0; h < 16 / GW; ++h) {
+              float u[GW];
+              uint32_t hit_r = 0u, hit_c = 0u;
+#pragma unroll
+              for (int e4 = 0; e4 < GW / 4; ++e4) {
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kSym) t4 = reinterpret_cast<const float4*>(sth + cbase + h * GW)[e4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const int e = e4 * 4 + q;
-                  const float a = __uint_as_float(acc[e]);
-                  float uw = fmaf(gcv[e], wg, fmaf(mcv[e], wm, we));
-                  uw = fmaf(a, wt, uw);
-                  uw = fmaf(fabsf(a), wte, uw);
-                  const float tc = q == 0 ? t4.x : (q == 1 ? t4.y : (q == 2 ? t4.z : t4.w));
-                  const int col = col0 + cbase + e;
-                  if (uw > th && col != self_col && col < p.n_shows) sym_append(vrow, uw, col);
-                  // padded columns carry threshold +inf, so no bound check is needed here
-                  if (do_col && uw > tc) sym_append(vcol0 + e, uw, row);
+                  const float a = __uint_as_float(acc[h * GW + e]);
+                  float gdot, mdot;
+                  side_dots(cbase + h * GW + e, gdot, mdot);
+                  float ue = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
+                  ue = fmaf(a, w_text, ue);
+                  ue = fmaf(fabsf(a), w_text_err, ue);
+                  u[e] = ue;
+                  hit_r |= ue > theta ? (1u << e) : 0u;
+                  if (kSym) {
+                    const float tc = q == 0 ? t4.x : (q == 1 ? t4.y : (q == 2 ? t4.z : t4.w));
+                    hit_c |= ue > tc ? (1u << e) : 0u;   // padded columns carry threshold +inf
+                  }
+                }
+              }
+              if (kSym) {
+                if (!do_col) hit_c = 0u;
+                push_hits(hit_r | (hit_c << GW), u, col0 + cbase + h * GW, 0);
+              } else {
+                // private list of this thread's row (at most GW appends; 32 free slots are guaranteed)
+                while (hit_r) {
+                  const int e = __ffs(hit_r) - 1;
+                  hit_r &= hit_r - 1u;
+                  const int col = col0 + cbase + h * GW + e;
+                  if (col != self_col && col < p.n_shows) {
+                    __stcg(my_list + cnt, make_uint2(__float_as_uint(pick<GW>(u, e)), static_cast<uint32_t>(col)));
+                    ++cnt;
+                  }
                 }
               }
             }
@@ -688,53 +805,54 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
         // 16 chunks of 16 columns, two per loop iteration so that the TMEM load of the next chunk
         // is in flight while the current one is scored.  The loop is kept rolled on purpose: the
-        // whole body (~700 instructions) stays resident in the instruction cache.
-        uint32_t acc_a[16], acc_b[16];
+        // whole body stays resident in the instruction cache.
+        uint32_t acc_a[16], acc_b[kWide ? 1 : 16];
         const int ch0 = (warp >> 2) * (COLS_PER_WARP / 16), ch1 = ch0 + COLS_PER_WARP / 16;
-        tmem_ld_32x16(taddr + ch0 * 16, acc_a);
+        if (!kWide) tmem_ld_32x16(taddr + ch0 * 16, acc_a);
 #pragma unroll 1
         for (int ch = ch0; ch < ch1; ch += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x16(taddr + (ch + 1) * 16, acc_b);
-          score16(acc_a, ch * 16);
-          tmem_ld_wait();
-          if (ch + 2 < ch1) {
-            tmem_ld_32x16(taddr + (ch + 2) * 16, acc_a);
+          if constexpr (kWide) {
+            // 16 epilogue warps: four warps per scheduler hide the TMEM load latency, and the register
+            // budget (96 per thread at 576 threads) has no room for a second accumulator buffer
+#pragma unroll 1
+            for (int c2 = ch; c2 < ch + 2; ++c2) {
+              tmem_ld_32x16(taddr + c2 * 16, acc_a);
+              tmem_ld_wait();
+              if (c2 + 1 >= ch1) {
+                tc_fence_before();
+                if (CG == 2) mbar_arrive_cluster(&acc_empty[b], 0u);
+                else mbar_arrive(&acc_empty[b]);
+              }
+              score16(acc_a, c2 * 16);
+            }
           } else {
-            // every accumulator column of this tile is in registers: hand the TMEM buffer back
-            tc_fence_before();
-            if (CG == 2) mbar_arrive_cluster(&acc_empty[b], 0u);
-            else mbar_arrive(&acc_empty[b]);
+            tmem_ld_wait();
+            tmem_ld_32x16(taddr + (ch + 1) * 16, acc_b);
+            score16(acc_a, ch * 16);
+            tmem_ld_wait();
+            if (ch + 2 < ch1) {
+              tmem_ld_32x16(taddr + (ch + 2) * 16, acc_a);
+            } else {
+              // every accumulator column of this tile is in registers: hand the TMEM buffer back
+              tc_fence_before();
+              if (CG == 2) mbar_arrive_cluster(&acc_empty[b], 0u);
+              else mbar_arrive(&acc_empty[b]);
+            }
+            score16(acc_b, (ch + 1) * 16);
           }
-          score16(acc_b, (ch + 1) * 16);
-          if (kSym && !kStats && ((ch & 2) != 0 || ch + 2 >= ch1)) {
-            // every 64 columns: flush the queued appends, then serve the threshold refreshes they
-            // raised, one show at a time
-            sym_flush();
-            unsigned need = __ballot_sync(kFullMask, pend_n != 0);
-            while (need) {
-              const int src_lane = __ffs(need) - 1;
-              need &= need - 1;
-              const int show = __shfl_sync(kFullMask, pend_r, src_lane);
-              const int n = __shfl_sync(kFullMask, pend_n, src_lane);
-              sym_refresh_theta(p.g_list + static_cast<size_t>(show) * sym_cap, n, p.kp, p.g_theta + show, lane);
-            }
-            pend_n = 0;
-            need = __ballot_sync(kFullMask, pend2_n != 0);
-            while (need) {
-              const int src_lane = __ffs(need) - 1;
-              need &= need - 1;
-              const int show = __shfl_sync(kFullMask, pend2_r, src_lane);
-              const int n = __shfl_sync(kFullMask, pend2_n, src_lane);
-              sym_refresh_theta(p.g_list + static_cast<size_t>(show) * sym_cap, n, p.kp, p.g_theta + show, lane);
-            }
-            pend2_n = 0;
-            if (kMulti) {
-              load_thw();
-            } else if (row_valid) {  // pick up raises made by other CTAs (and by the refreshes above)
-              unsigned int tb;
-              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
-              theta = __uint_as_float(tb);
+          if (kSym && !kStats) {
+            // drain the ring when it holds two full passes of the flush, or a lane-full at the end of
+            // the tile; then pick up the raises made by other CTAs (and by the refreshes of the flush)
+            const bool tile_done = ch + 2 >= ch1;
+            if (ring_n >= 64 || (tile_done && ring_n >= 32)) {
+              ring_flush();
+              if (kMulti) {
+                load_thw();
+              } else if (row_valid) {
+                unsigned int tb;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tb) : "l"(p.g_theta + row) : "memory");
+                theta = __uint_as_float(tb);
+              }
             }
           } else if (!kDump && !kSym) {
             // keep 32 free slots for the next 32 columns; compact rows that are nearly full
@@ -761,6 +879,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           st_gm += tile_gm;
         }
       }
+      if (kSym && !kStats && ring_n > 0) ring_flush();   // nothing stays queued past the item (or the kernel)
 
       if (!kDump && !kSym) {
         // final compaction of every row of this warp: sorted best-kp list -> cand
