@@ -33,4 +33,4 @@ for tun in tunings:
         full.append(e0.elapsed_time(e2))
     st = t["stats"].cpu().numpy()
     print(f"{name} tuning {tun:#x}: K1 ms {np.round(times, 2).tolist()}  step ms {np.round(full[2:], 2).tolist()} "
-          f"flagged {int(st[0])} pairs {int(st[1])}", flush=True)
+          f"flagged {int(st[0])} pairs {int(st[1])} list entries ~{int(st[4]) * 16} (TVBF_DEBUG_COUNTS)", flush=True)

@@ -307,6 +307,17 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   kp.g_cnt = reinterpret_cast<unsigned int*>(ws + pl.off_gcnt);
   kp.g_list = reinterpret_cast<uint2*>(ws + pl.off_glist);
   kp.cooperative = ((p->tuning >> 30) & 1) ? 0 : 1;  // bit 30: plain launch (profilers that patch SASS)
+  {
+    // experiment knobs (environment, read once): TVBF_REFRESH_PERIOD (0 = doubling schedule),
+    // TVBF_WAIT_NS (first sleep of the backed-off waits)
+    static const int env_period = [] { const char* e = getenv("TVBF_REFRESH_PERIOD"); return e ? atoi(e) : -1; }();
+    static const int env_wait = [] { const char* e = getenv("TVBF_WAIT_NS"); return e ? atoi(e) : -1; }();
+    // default: the doubling schedule.  Measured on P80k / C3: refreshing every 32 appends leaves 24 %
+    // fewer list entries (19.1 M against 25.2 M / 24.9 M against 33.5 M) but the extra refreshes cost
+    // more than the appends they save (K1 9.5 against 8.9 ms / 56.7 against 56.9 ms)
+    kp.refresh_period = env_period >= 0 ? env_period : 0;
+    kp.wait_ns = env_wait >= 0 ? env_wait : 64;
+  }
   // 16 epilogue warps when the tile's MMAs (~0.27 us per 64-wide k-block) cannot hide the epilogue
   // (~30 us per tile with 8 warps); bits 28-29 of tuning: 0 auto, 1 off, 2 on
   {
@@ -452,6 +463,8 @@ int tvbf_hybrid_topk(const tvbf_features* f, const tvbf_params* p, const tvbf_to
     if (rc != TVBF_OK) return rc;
   }
   if ((phases & 2) && pl.sym) {
+    static const bool dbg_counts = getenv("TVBF_DEBUG_COUNTS") != nullptr;
+    if (dbg_counts) kp.dbg_entries = out->stats + 4;
     rc = tvbf::k4s_launch(kp, pl.rows, st);
     if (rc != TVBF_OK) return rc;
   }

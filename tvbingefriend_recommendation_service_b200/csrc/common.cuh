@@ -120,13 +120,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // epilogue-bound regime the producer and the MMA issuer, in the MMA-bound regime the epilogue).  A
 // tight try_wait loop issues an instruction every ~12 cycles and, sharing a scheduler with working
 // warps, takes issue slots from them (ncu on P80k: half of all executed warp instructions were
-// these polls).  After `quick` failed polls the thread sleeps between polls.
+// these polls).  After `quick` failed polls the thread sleeps between polls, twice as long each time
+// up to 8 * sleep_ns.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t quick = 16,
                                                   uint32_t sleep_ns = 64) {
-  uint32_t spins = 0;
+  uint32_t spins = 0, ns = sleep_ns;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > quick) __nanosleep(sleep_ns);
-    if (spins > (1u << 23)) {
+    if (++spins > quick) {
+      __nanosleep(ns);
+      if (ns < 8 * sleep_ns) ns *= 2;
+    }
+    if (spins > (1u << 21)) {
       printf("tvbf: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
              (int)threadIdx.x);
       __trap();

@@ -149,6 +149,62 @@ __device__ __noinline__ float warp_compact(const uint2* src, int n, uint2* dst, 
   return bound;
 }
 
+// Keep the kp best of the n entries of one row's list IN PLACE and UNORDERED (the order only matters
+// for the final hand-over, which sorts): exact radix select of the kp-th largest score over the bits
+// the entries do not share, then a ballot compaction -- about a quarter of the bitonic sort's
+// instructions.  The one-sided sweep compacts a row every ~96 appends; in the threshold seed pass,
+// which starts from min_similarity, that was four fifths of its time.
+// Returns (to every lane) the kp-th largest score: the bound on everything dropped.
+template <int E>
+__device__ __noinline__ float warp_select_compact(uint2* list, int n, int kp, int lane) {
+  if (n <= kp) return __int_as_float(0xff800000);   // nothing to drop
+  uint32_t v[E], col[E];
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  __syncwarp();  // the owner lane's appends (st.cg) are ordered before these loads
+#pragma unroll
+  for (int q = 0; q < E; ++q) {
+    const int idx = q * 32 + lane;
+    v[q] = 0u;
+    col[q] = 0u;
+    if (idx < n) {
+      const uint2 e = __ldcg(list + idx);
+      v[q] = f32_orderable(__uint_as_float(e.x));
+      col[q] = e.y;
+      lo = min(lo, v[q]);
+      hi = max(hi, v[q]);
+    }
+  }
+  lo = __reduce_min_sync(kFullMask, lo);
+  hi = __reduce_max_sync(kFullMask, hi);
+  const int top = 31 - __clz(lo ^ hi);   // highest bit in which two entries differ (-1: all equal)
+  uint32_t best = top >= 0 ? ((top == 31 ? 0u : (hi >> (top + 1)) << (top + 1))) : hi;
+#pragma unroll 1
+  for (int bit = top; bit >= 0; --bit) {
+    const uint32_t t = best | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < E; ++q) c += (q * 32 + lane < n && v[q] >= t);
+    c = __reduce_add_sync(kFullMask, c);
+    if (c >= kp) best = t;
+  }
+  __syncwarp();  // all loads done before anyone overwrites
+  int out = 0;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int q = 0; q < E; ++q) {
+      const bool take = q * 32 + lane < n && (pass == 0 ? v[q] > best : v[q] == best);
+      const unsigned bal = __ballot_sync(kFullMask, take);
+      const int pos = out + __popc(bal & ((1u << lane) - 1u));
+      if (take && pos < kp)
+        __stcg(list + pos, make_uint2(__float_as_uint(f32_from_orderable(v[q])), col[q]));
+      out += __popc(bal);
+    }
+  }
+  __syncwarp();
+  return f32_from_orderable(best);
+}
+
 struct ItemCoord {
   int sb;            // super block (128*CG rows) within the shard, -1 = nothing to do
   int split;
@@ -248,10 +304,13 @@ __device__ __noinline__ void sym_refresh_theta(const uint2* list, int n, int kp,
 // Drain one epilogue warp's ring of pending appends {show, score bits, other show} into the shared
 // lists.  An append needs the slot returned by an atomicAdd (a ~700-cycle round trip): all atomics of
 // the ring are issued back to back, one entry per lane and pass, so the warp pays the round trip once
-// per flush.  A list that reaches 2*kp, 4*kp, ... entries gets its threshold refreshed.
+// per flush.  A list gets its threshold refreshed when it reaches 2*kp entries and then every P further
+// ones (P = largest power of two <= kp).  Round 1 refreshed at 2*kp, 4*kp, 8*kp, ...: the threshold
+// then lags by up to a factor of two in rank and a show collected ~530 entries per sweep on P80k
+// (80 k shows); refreshing every P appends tracks the running kp-th best and needs ~200.
 // Not inlined: the scoring loop around it must stay small enough for the instruction cache.
 __device__ __noinline__ void sym_ring_flush(const uint32_t* ring, int n, unsigned int* g_cnt, uint2* g_list,
-                                            unsigned int* g_theta, unsigned sym_cap, int kp, int lane) {
+                                            unsigned int* g_theta, unsigned sym_cap, int kp, int period, int lane) {
   constexpr int J = RING / 32;
   uint32_t sh[J];
   unsigned pos[J];
@@ -267,13 +326,14 @@ __device__ __noinline__ void sym_ring_flush(const uint32_t* ring, int n, unsigne
   }
   unsigned trig = 0u;   // bit j: entry j of this lane completed a list length that asks for a refresh
   const unsigned first = static_cast<unsigned>(2 * kp);
+  const unsigned period_mask = static_cast<unsigned>(period) - 1u;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int i = j * 32 + lane;
     if (pos[j] < sym_cap) {   // lanes without an entry hold 0xFFFFFFFF; an overflowing list drops the entry
       __stcg(g_list + static_cast<size_t>(sh[j]) * sym_cap + pos[j], make_uint2(ring[RING + i], ring[2 * RING + i]));
       const unsigned np = pos[j] + 1u;
-      if (np >= first && (np & pos[j]) == 0u) trig |= 1u << j;
+      if (np >= first && (np & (period ? period_mask : pos[j])) == 0u) trig |= 1u << j;
     }
   }
   __syncwarp();
@@ -428,7 +488,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t b = it & 1;
           const int col0 = kDump ? p.dump_col0 : jt * BN;
           if (!kDump) {
-            mbar_wait_backoff(&col_empty[b], ((it >> 1) & 1) ^ 1);  // epilogue done with buffer b
+            mbar_wait_backoff(&col_empty[b], ((it >> 1) & 1) ^ 1, 16, p.wait_ns);  // epilogue done with buffer b
             if (elect_one()) {
               const uint32_t n_th = kMulti ? static_cast<uint32_t>(p.n_weights) : 1u;
               mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u) +
@@ -452,7 +512,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (kb) pacer.done_chunk(lane == 0);
               pacer.wait_turn();
             }
-            mbar_wait_backoff(&empty[stage], phase ^ 1);
+            mbar_wait_backoff(&empty[stage], phase ^ 1, 16, p.wait_ns);
             if (elect_one()) {
               uint8_t* sa = smem + L::OFF_A + stage * A_BYTES;
               uint8_t* sb = smem + L::OFF_B + stage * L::B_BYTES;
@@ -490,7 +550,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int tile_beg = kDump ? c.tile0 : c.real0, tile_end = kDump ? c.tile1 : c.real1;
         for (int jt = tile_beg; jt < tile_end; jt += p.tile_stride, ++it) {
           const uint32_t b = it & 1;
-          mbar_wait_backoff(&acc_empty[b], ((it >> 1) & 1) ^ 1);  // every epilogue drained accumulator b
+          mbar_wait_backoff(&acc_empty[b], ((it >> 1) & 1) ^ 1, 16, p.wait_ns);  // every epilogue drained accumulator b
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + b * BN;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -603,7 +663,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // loses one.
       auto ring_flush = [&]() {
         __syncwarp();
-        sym_ring_flush(ring, ring_n, p.g_cnt, p.g_list, p.g_theta, sym_cap, p.kp, lane);
+        sym_ring_flush(ring, ring_n, p.g_cnt, p.g_list, p.g_theta, sym_cap, p.kp, p.refresh_period, lane);
         ring_n = 0;
         __syncwarp();
       };
@@ -664,12 +724,13 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
         // plain genre / metadata dots of accumulator column cbase + e against this thread's show
         auto side_dots = [&](int ce, float& gdot, float& mdot) {
-          const TvbfColSide cs = scol[ce];
-          int gcount = __popcll(g_bits & cs.genre_bits);
+          // one LDS.128: {genre bits lo, hi, 1/sqrt(popcount) as float bits, metadata bits}
+          const uint4 cs = reinterpret_cast<const uint4*>(scol)[ce];
+          int gcount = __popc(static_cast<uint32_t>(g_bits) & cs.x) + __popc(static_cast<uint32_t>(g_bits >> 32) & cs.y);
           if (kG2) gcount += __popcll(g_hi & sgh[ce]);
-          gdot = static_cast<float>(gcount) * cs.genre_rnorm;
+          gdot = static_cast<float>(gcount) * __uint_as_float(cs.z);
           // per-column scale: 1/sqrt(#categories) (HSTACK) or 1/sqrt(3) (MEAN3: matches / 3), 0 for padding
-          mdot = static_cast<float>(__popc(m_bits & cs.meta_bits)) * sms[ce];
+          mdot = static_cast<float>(__popc(m_bits & cs.w)) * sms[ce];
         };
         // Score 16 accumulator columns held in registers.  The candidate sweeps (everything but the
         // statistics and dump variants) are written BRANCH-FREE: the sixteen upper bounds are
@@ -863,7 +924,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const uint2* lp = reinterpret_cast<const uint2*>(__shfl_sync(
                   kFullMask, reinterpret_cast<unsigned long long>(my_list), src_lane));
               const int n = __shfl_sync(kFullMask, cnt, src_lane);
-              const float bound = warp_compact<E>(lp, n, const_cast<uint2*>(lp), p.kp, lane);
+              const float bound = warp_select_compact<E>(const_cast<uint2*>(lp), n, p.kp, lane);
               if (lane == src_lane) {
                 cnt = p.kp;
                 theta = fmaxf(theta, bound);
@@ -893,7 +954,14 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (p.seed_theta) {
             // sampled sweep: the kp-th best sampled score is a valid lower bound of the show's
             // final threshold; it spares the symmetric sweep its warm-up flood of appends
-            const float bound = warp_compact<E>(lp, n, const_cast<uint2*>(lp), p.kp, lane);
+            float bound = warp_select_compact<E>(const_cast<uint2*>(lp), n, p.kp, lane);
+            if (n == p.kp) {   // exactly kp sampled candidates: the smallest of them
+              float mn = __int_as_float(0x7f800000);
+              for (int i = lane; i < n; i += 32) mn = fminf(mn, __uint_as_float(__ldcg(lp + i).x));
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(kFullMask, mn, o));
+              bound = mn;
+            }
             if (lane == src_lane && n >= p.kp && bound > p.theta_init)
               p.g_theta[p.row_begin + r] = __float_as_uint(bound);
             continue;
@@ -1047,6 +1115,7 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   if (r >= n_rows) return;
   const unsigned total = p.g_cnt[r];
   const int n_all = static_cast<int>(total < static_cast<unsigned>(p.sym_cap) ? total : p.sym_cap);
+  if (p.dbg_entries != nullptr && lane == 0) atomicAdd(p.dbg_entries, n_all >> 4);   // in units of 16 entries
   uint2* list = p.g_list + static_cast<size_t>(r) * p.sym_cap;
   const int kp = p.kp;
   uint2* dst = p.cand + static_cast<size_t>(r) * (p.cand_packed ? kp + 1 : kp);
@@ -1406,6 +1475,9 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
         for (int w = 0; w < nw; ++w) {
           const K1Params seed = make_seed_params(kp, grid, w);
           int rc;
+          // (512-entry private lists, which almost never compact inside the loop, were measured
+          // slower on P80k: 2.07 against 1.57 ms -- the final selection over the longer lists costs
+          // more than the in-loop compactions it saves)
           if (kp.genre_hi != nullptr)
             rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st)
                              : launch_k1<8, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st);

@@ -82,6 +82,10 @@ struct K1Params {
   unsigned int* g_theta;   // [n_pad] raw bits of the (positive) float threshold of each show
   unsigned int* g_cnt;     // [n_pad] appends so far (> sym_cap = overflow)
   uint2* g_list;           // [n_pad][sym_cap] (score bits, column)
+  int refresh_period;  // a list's threshold is refreshed at 2*kp entries and every refresh_period further ones
+                       // (a power of two; 0: at 2*kp, 4*kp, 8*kp, ...)
+  int wait_ns;         // first sleep of the backed-off mbarrier waits
+  int* dbg_entries;    // diagnostics (TVBF_DEBUG_COUNTS=1): K4s adds every list's length to stats[4]
   int cooperative;     // launch with the cooperative attribute (co-residency guaranteed)
   int kp;              // candidates kept per (row, split)
   int exclude_self;
