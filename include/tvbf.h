@@ -83,6 +83,14 @@ typedef struct tvbf_features {
   int32_t text_signed;       /* 1: text values may be negative (embeddings, SVD): the candidate   */
                              /* pass then bounds the fp16 error absolutely instead of relative to */
                              /* the accumulator (cancellation); 0 for TF-IDF                      */
+  int32_t bits_folded;       /* 1: besides the packed records, the operand carries the PACKED genre */
+                             /* and metadata groups as columns fold_col0 .. fold_col0 + genre_dim +  */
+                             /* 32 (tvbf_prep_fold_bits), scaled so that the tensor-core accumulator */
+                             /* is the whole hybrid for fold_weights: the candidate pass then skips  */
+                             /* its popcounts (small vocabularies, where the epilogue is the bound); */
+                             /* rescoring still uses the packed records                              */
+  int32_t fold_col0;
+  double fold_weights[3];    /* genre / text / metadata weights baked by tvbf_prep_fold_bits         */
 } tvbf_features;
 
 /* Parameters of one top-K job: populate_database.py:85-91 (weights, top_n_per_show,
@@ -163,6 +171,14 @@ int tvbf_prep_dense_normalize(const double* in, int32_t n_rows, int32_t dim, dou
 int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim, void* operand,
                                int32_t k_pad, int32_t col_offset, double scale, int32_t dtype,
                                void* stream);
+/* Packed genre / metadata records -> operand columns [col0, col0 + genre_dim + 32): genre column g of
+ * show i holds scale_genre / sqrt(popcount_i) where bit g is set, metadata column b holds
+ * scale_meta * meta_scale[i] where one-hot bit b is set, 0 elsewhere (every one of the columns is
+ * written).  With scale_group = 2^s * sqrt(w_group / w_text) the accumulator of the text GEMM becomes
+ * 2^2s / w_text times the hybrid of populate_database.py:190-192. */
+int tvbf_prep_fold_bits(const void* col_side, const uint64_t* genre_hi, const float* meta_scale,
+                        int32_t n_rows, int32_t genre_dim, void* operand, int32_t k_pad, int32_t col0,
+                        double scale_genre, double scale_meta, int32_t dtype, void* stream);
 /* genre multi-hot bytes [n_rows, dim <= 128] -> col_side[].genre_bits / genre_rnorm (+ genre_hi[] for
  * the columns 64.., required when dim > 64, [n_pad] entries zeroed by the caller). */
 int tvbf_prep_genre_bits(const uint8_t* genre, int32_t n_rows, int32_t dim, void* col_side,

@@ -425,3 +425,70 @@ def test_wide_genre_masks(engine, g, tuning):
         h = pr.row(i)[0]
         h[i] = -1.0
         assert np.allclose(np.sort(h)[::-1][:10], q.hybrid[r], rtol=1e-12)
+
+
+# ---- packed groups folded into the operand (small vocabularies) ---------------------------------------------
+FOLD_CASES = [((0.4, 0.5, 0.1), "mean3", 40), ((21.0, 5.0, 6.0), "mean3", 21), ((0.3, 0.6, 0.1), "hstack", 40),
+              ((0.5, 0.5, 0.0), "mean3", 100)]
+
+
+@pytest.mark.parametrize("weights,mode,genres", FOLD_CASES, ids=["default", "raw_21_5_6", "hstack", "g100_no_meta"])
+def test_upper_bound_holds_with_folded_bits(engine, weights, mode, genres):
+    """tvbf_features.bits_folded: the accumulator over text + genre + metadata columns, inflated by the
+    library's own slack, bounds the exact hybrid of every pair of the tile -- and tightly."""
+    from oracle.reference_paths import ProductionRows
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(1024, 500, nnz=15, n_genres=genres, seed=51)
+    f = cat.features()
+    dc = engine.ingest(f, mode, weights)
+    feats = engine._folded(dc, *[float(w) for w in weights], 20)
+    assert feats is not None and feats.bits_folded == 1 and feats.k_pad == (500 + genres + 32 + 63) // 64 * 64
+    sl = engine.debug_slack(dc, weights, feats=feats)
+    a = engine.debug_gemm_tile(dc, 128, 256, feats=feats).cpu().numpy().astype(np.float64)
+    pr = ProductionRows(f, *weights, metadata_mode=mode)
+    exact = pr.rows_block(np.arange(128, 256))[0][:, 256:512]
+    terms = (np.diff(sp.csr_matrix(f["text_features"]).indptr)[128:256] + genres + 3).astype(np.float64)[:, None]
+    u = (sl["w_text"] + sl["w_text_err"] + terms * sl["w_text_acc"]) * a + sl["eps"] + terms * sl["eps_term"]
+    assert np.all(u >= exact), float((exact - u).max())
+    assert float((u - exact).max()) <= 2.5e-3 * sum(weights), float((u - exact).max())
+
+
+@pytest.mark.parametrize("weights,mode,genres", FOLD_CASES, ids=["default", "raw_21_5_6", "hstack", "g100_no_meta"])
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+def test_folded_bits_give_the_same_table(engine, tuning, weights, mode, genres):
+    """The folded candidate pass changes which pairs are rescored, never the certified result: the table
+    equals the one of the popcount epilogue bit for bit, and the oracle's."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    cat = make_catalogue(3000, 400, nnz=12, n_genres=genres, seed=52)
+    f = cat.features()
+    ms = 0.1 * sum(weights)
+    engine._fold_owner = None
+    fold = engine.compute_top_k(f, weights, 20, ms, metadata_mode=mode, tuning=tuning)
+    assert engine._fold_owner is not None, "the folded operand was not used"
+    old = engine.fold_max_k
+    engine.fold_max_k = 0
+    try:
+        plain = engine.compute_top_k(f, weights, 20, ms, metadata_mode=mode, tuning=tuning)
+    finally:
+        engine.fold_max_k = old
+    for name in ("indices", "counts", "hybrid", "genre", "text", "metadata"):
+        assert np.array_equal(getattr(fold, name), getattr(plain, name), equal_nan=True), name
+    assert_topk_matches(fold, f, np.arange(0, 3000, 7), weights=weights, min_similarity=ms, metadata_mode=mode)
+
+
+def test_folded_operand_follows_the_weights_and_the_catalogue(engine):
+    """One device catalogue, several weight triples and a second catalogue in between: the folded
+    columns are rewritten per triple, and a catalogue whose buffer was taken over rebuilds it."""
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    a, b = make_catalogue(2000, 300, nnz=10, seed=53), make_catalogue(2000, 300, nnz=10, seed=54)
+    ca, cb = engine.ingest(a.features()), engine.ingest(b.features())
+    rows = np.arange(0, 2000, 9)
+    for w in ((0.4, 0.5, 0.1), (0.6, 0.3, 0.1), (0.4, 0.5, 0.1)):
+        ta = engine.to_host(engine.top_k_device(ca, w, 20, 0.1))
+        tb = engine.to_host(engine.top_k_device(cb, w, 20, 0.1))
+        assert ca.fold is not None and cb.fold is not None
+        assert_topk_matches(ta, a.features(), rows, weights=w)
+        assert_topk_matches(tb, b.features(), rows, weights=w)

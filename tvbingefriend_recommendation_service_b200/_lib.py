@@ -37,6 +37,7 @@ class Features(C.Structure):
         ("col_side", c_void_p), ("meta_scale", c_void_p),
         ("genre_hi", c_void_p),
         ("text_signed", c_int32),
+        ("bits_folded", c_int32), ("fold_col0", c_int32), ("fold_weights", c_double * 3),
     ]
 
 
@@ -69,6 +70,8 @@ SIGNATURES = {
     "tvbf_prep_csr_normalize": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "tvbf_prep_csr_to_operand": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                            c_int32, c_double, c_int32, c_void_p]),
+    "tvbf_prep_fold_bits": (C.c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                                      c_double, c_double, c_int32, c_void_p]),
     "tvbf_prep_clear_csr_positions": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32,
                                                 c_void_p]),
     "tvbf_device_zero": (C.c_int, [c_void_p, c_size_t, c_void_p]),

@@ -71,6 +71,15 @@ int validate_features(const tvbf_features* f) {
                  "packed genre: genre_hi must be given exactly when there are more than 64 columns");
     if (f->genre_hi) TVBF_REQUIRE((reinterpret_cast<uintptr_t>(f->genre_hi) & 15) == 0, "genre_hi must be 16-byte aligned");
   }
+  if (f->bits_folded) {
+    TVBF_REQUIRE(f->genre_mode == TVBF_GROUP_PACKED && f->meta_mode == TVBF_GROUP_PACKED && !f->text_signed,
+                 "bits_folded needs packed genre and metadata groups and non-negative text");
+    TVBF_REQUIRE(f->fold_col0 >= f->vocab && f->fold_col0 + f->genre_dim + 32 <= f->k_pad,
+                 "bits_folded: columns [%d, %d) do not fit k_pad %d", f->fold_col0, f->fold_col0 + f->genre_dim + 32,
+                 f->k_pad);
+    TVBF_REQUIRE(f->fold_weights[1] > 0.0 && f->fold_weights[0] >= 0.0 && f->fold_weights[2] >= 0.0,
+                 "bits_folded needs text_weight > 0 and non-negative genre / metadata weights");
+  }
   if (f->meta_mode == TVBF_GROUP_FOLDED) {
     TVBF_REQUIRE(f->meta_groups == (f->meta_kind == TVBF_META_MEAN3 ? 3 : 1), "bad meta_groups");
     for (int g = 0; g < f->meta_groups; ++g)
@@ -234,6 +243,12 @@ Slack make_slack(const tvbf_features* f, double wg, double wt, double wm, double
     const double per_group = f->meta_kind == TVBF_META_MEAN3 ? std::fabs(wm) / 3.0 : std::fabs(wm);
     if (wt > 0) op_max = std::fmax(op_max, std::sqrt(per_group / wt));
   }
+  if (f->bits_folded && wt > 0) {
+    // packed groups carried as operand columns (non-negative, so the relative bound below holds for
+    // the whole accumulator): largest operand magnitude relative to a text entry (<= 1)
+    op_max = std::fmax(op_max, std::sqrt(std::fabs(wg) / wt));
+    op_max = std::fmax(op_max, std::sqrt(std::fabs(wm) / wt));
+  }
   const double wsum = std::fabs(wg) + std::fabs(wt) + std::fabs(wm);
   const double eps0 = 4e-6 * (wsum + 1.0);   // fp32 rounding of the epilogue's four FMAs
   Slack s;
@@ -263,6 +278,15 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
     TVBF_REQUIRE(p->text_weight > 0.0, "folded feature groups need text_weight > 0");
     TVBF_REQUIRE(p->genre_weight >= 0.0 && p->metadata_weight >= 0.0,
                  "folded feature groups need non-negative weights");
+  }
+
+  if (f->bits_folded) {
+    TVBF_REQUIRE(n_sweep == 1, "a weight sweep needs the plain operand (bits_folded catalogues bake one triple)");
+    TVBF_REQUIRE(p->genre_weight == f->fold_weights[0] && p->text_weight == f->fold_weights[1] &&
+                     p->metadata_weight == f->fold_weights[2],
+                 "this operand carries the genre / metadata columns for weights (%g, %g, %g), not (%g, %g, %g)",
+                 f->fold_weights[0], f->fold_weights[1], f->fold_weights[2], p->genre_weight, p->text_weight,
+                 p->metadata_weight);
   }
 
   tvbf::K1Params& kp = *out_kp;
@@ -343,10 +367,13 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
     if (f->genre_mode == TVBF_GROUP_FOLDED) folded += f->genre_dim;
     if (f->meta_mode == TVBF_GROUP_FOLDED)
       for (int g = 0; g < f->meta_groups; ++g) folded += f->meta_dims[g];
+    if (f->bits_folded) folded = f->genre_dim + 3;   // non-zero folded entries of a row: its genres + 3 one-hots
     kp.folded_cols = folded;
   }
-  kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->genre_weight) : 0.0f;
-  kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED ? static_cast<float>(p->metadata_weight) : 0.0f;
+  kp.fold = f->bits_folded ? 1 : 0;
+  kp.w_genre = f->genre_mode == TVBF_GROUP_PACKED && !f->bits_folded ? static_cast<float>(p->genre_weight) : 0.0f;
+  kp.w_meta = f->meta_mode == TVBF_GROUP_PACKED && !f->bits_folded ? static_cast<float>(p->metadata_weight) : 0.0f;
+  if (f->bits_folded) kp.genre_hi = nullptr;   // the second mask word is in the operand as well
   kp.meta_hstack = f->meta_kind == TVBF_META_HSTACK ? 1 : 0;
   {
     // strictly below min_similarity in fp32 so that U >= min_similarity always passes "U > theta"
@@ -823,6 +850,7 @@ int tvbf_similarity_stats(const tvbf_features* f, const tvbf_params* p, void* ac
   TVBF_REQUIRE(p && accum && workspace, "tvbf_similarity_stats: NULL argument");
   TVBF_REQUIRE(f->genre_mode != TVBF_GROUP_FOLDED && f->meta_mode != TVBF_GROUP_FOLDED && f->genre_hi == nullptr,
                "streaming statistics need binary genre (at most 64 columns) / one-hot metadata features");
+  TVBF_REQUIRE(!f->bits_folded, "streaming statistics need the plain text operand (bits_folded is set)");
   TVBF_REQUIRE(p->genre_weight >= 0.0 && p->text_weight >= 0.0 && p->metadata_weight >= 0.0,
                "streaming statistics need non-negative weights");
   tvbf_params q = *p;

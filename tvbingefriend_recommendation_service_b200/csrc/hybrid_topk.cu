@@ -400,7 +400,12 @@ struct Pacer {
 // kG2: multi-hot genres with 64 < G <= 128 -- the second word of every column's mask is staged beside
 // the column-side records (in the threshold slices a single-triple sweep leaves unused) and the
 // popcount runs over both words.
-template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false>
+// kFold: the operand carries the packed genre / metadata groups as extra K columns scaled by
+// sqrt(w_group / w_text) (tvbf_prep_fold_bits), so the accumulator already is the whole hybrid: the
+// epilogue is one FMA and two compares per element instead of three popcounts, two conversions and
+// six FMAs.  For small vocabularies, where a tile's MMAs (even with one more k-block) are far shorter
+// than its epilogue.
+template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false, bool kFold = false>
 __global__ void __launch_bounds__(Roles<(kMode != 0), kWide>::THREADS, 1)
 hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
@@ -410,12 +415,13 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
   constexpr bool kMulti = kMode == 5;    // weight sweep
   static_assert(!(kG2 && (kMulti || kStats)), "two-word genre masks: single-triple top-k sweeps only");
+  static_assert(!(kFold && (kMulti || kStats || kDump || kG2)), "folded groups: single-triple top-k sweeps only");
   constexpr uint32_t GH_BYTES = BN * 8;  // second genre word of the tile's 256 columns
   constexpr int STAGES = L::STAGES;
   using R = Roles<kSym, kWide>;
   constexpr int EPI = R::EPI, PRODUCER_WARP = R::PRODUCER, MMA_WARP = R::MMA;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
-  constexpr int GW = kWide ? 4 : 8;               // columns scored together (independent chains)
+  constexpr int GW = (kWide && !kFold) ? 4 : 8;   // columns scored together (independent chains)
   const uint32_t nstages = static_cast<uint32_t>(p.stages);
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles; done as an OFFSET so the compiler still knows
@@ -491,13 +497,13 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_wait_backoff(&col_empty[b], ((it >> 1) & 1) ^ 1, 16, p.wait_ns);  // epilogue done with buffer b
             if (elect_one()) {
               const uint32_t n_th = kMulti ? static_cast<uint32_t>(p.n_weights) : 1u;
-              mbar_arrive_expect_tx(&col_full[b], COL_BYTES + MS_BYTES + ((kSym && !kStats) ? n_th * MS_BYTES : 0u) +
-                                                      (kG2 ? GH_BYTES : 0u));
-              bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
+              mbar_arrive_expect_tx(&col_full[b], (kFold ? 0u : COL_BYTES + MS_BYTES) +
+                                                      ((kSym && !kStats) ? n_th * MS_BYTES : 0u) + (kG2 ? GH_BYTES : 0u));
+              if (!kFold) bulk_load_1d(smem + L::OFF_COL + b * COL_BYTES, p.col_side + col0, COL_BYTES, &col_full[b]);
               if (kG2)   // threshold slices 1-2 of this buffer (slice 0 holds the thresholds)
                 bulk_load_1d(smem + L::OFF_TH + (b * kMaxSweep + 1) * MS_BYTES, p.genre_hi + col0, GH_BYTES,
                              &col_full[b]);
-              bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
+              if (!kFold) bulk_load_1d(smem + L::OFF_MS + b * MS_BYTES, p.meta_scale + col0, MS_BYTES, &col_full[b]);
               if (kSym && !kStats)  // snapshot of the column shows' thresholds (stale = lower = conservative)
                 for (uint32_t w = 0; w < n_th; ++w)
                   bulk_load_1d(smem + L::OFF_TH + (b * kMaxSweep + w) * MS_BYTES,
@@ -615,7 +621,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       unsigned long long g_bits = 0ull, g_hi = 0ull;
       uint32_t m_bits = 0u;
       float rn_wg = 0.0f, ci_wm = 0.0f;
-      if (row_valid && !kDump) {
+      if (row_valid && !kDump && !kFold) {
         const TvbfColSide rs = p.col_side[row];
         g_bits = rs.genre_bits;
         if (kG2) g_hi = p.genre_hi[row];
@@ -653,6 +659,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         terms = static_cast<float>(p.text_indptr[row + 1] - p.text_indptr[row]) + static_cast<float>(p.folded_cols);
       const float w_text = p.w_text, w_text_err = fmaf(terms, p.w_text_acc, p.w_text_err),
                   eps = fmaf(terms, p.eps_term, p.eps);
+      const float w_fold = w_text + w_text_err;   // kFold: upper bound = acc * (w + err) + eps
       const unsigned sym_cap = static_cast<unsigned>(p.sym_cap);
 
       // Shared-list appends need the slot returned by an atomicAdd; done on the spot that round trip
@@ -832,11 +839,16 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int q = 0; q < 4; ++q) {
                   const int e = e4 * 4 + q;
                   const float a = __uint_as_float(acc[h * GW + e]);
-                  float gdot, mdot;
-                  side_dots(cbase + h * GW + e, gdot, mdot);
-                  float ue = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
-                  ue = fmaf(a, w_text, ue);
-                  ue = fmaf(fabsf(a), w_text_err, ue);
+                  float ue;
+                  if (kFold) {
+                    ue = fmaf(a, w_fold, eps);   // all products are non-negative: |a| == a
+                  } else {
+                    float gdot, mdot;
+                    side_dots(cbase + h * GW + e, gdot, mdot);
+                    ue = fmaf(gdot, rn_wg, fmaf(mdot, ci_wm, eps));
+                    ue = fmaf(a, w_text, ue);
+                    ue = fmaf(fabsf(a), w_text_err, ue);
+                  }
                   u[e] = ue;
                   hit_r |= ue > theta ? (1u << e) : 0u;
                   if (kSym) {
@@ -1291,7 +1303,7 @@ static bool profiler_attached() {
   return cached != 0;
 }
 
-template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false>
+template <int E, bool kDump, int CG, int kMode, bool kWide = false, bool kG2 = false, bool kFold = false>
 static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaStream_t st) {
   using L = Smem<CG, kWide>;
   CUtensorMap ta, tb;
@@ -1299,7 +1311,7 @@ static int launch_k1(const tvbf_features* f, const K1Params& kp, int grid, cudaS
   if (rc != TVBF_OK) return rc;
   rc = make_operand_map(f, static_cast<int>(L::B_ROWS), &tb);
   if (rc != TVBF_OK) return rc;
-  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode, kWide, kG2>;
+  auto kern = hybrid_topk_kernel<E, kDump, CG, kMode, kWide, kG2, kFold>;
   TVBF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(L::BYTES)));
   const uint32_t idesc = umma_idesc_f16(f->text_dtype == TVBF_TEXT_BF16 ? 1u : 0u, BM * CG, BN);
@@ -1442,6 +1454,10 @@ int k1_join_pending_clear(const void* g_list, cudaStream_t st) {
 
 int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, int cta_group,
               int grid, cudaStream_t st) {
+  if (kp.fold && (cta_group != 2 || entries_per_lane != 4 || kp.kp > 64 || kp.n_weights > 1)) {
+    tvbf_set_error("an operand with folded genre / metadata columns supports CTA pairs and k <= 48 only");
+    return TVBF_ERR_INVALID;
+  }
   if (kp.sym) {
     if (cta_group != 2) {
       tvbf_set_error("symmetric mode needs cta_group 2");
@@ -1478,7 +1494,9 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
           // (512-entry private lists, which almost never compact inside the loop, were measured
           // slower on P80k: 2.07 against 1.57 ms -- the final selection over the longer lists costs
           // more than the in-loop compactions it saves)
-          if (kp.genre_hi != nullptr)
+          if (kp.fold)
+            rc = launch_k1<4, false, 2, 0, false, false, true>(f, seed, seed.rb_per_group * 2, st);
+          else if (kp.genre_hi != nullptr)
             rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st)
                              : launch_k1<8, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st);
           else
@@ -1509,12 +1527,15 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
     }
     if (kp.wide_epilogue) {
       if (sweep.stages > Smem<2, true>::STAGES) sweep.stages = Smem<2, true>::STAGES;
+      if (kp.fold) return launch_k1<4, false, 2, 1, true, false, true>(f, sweep, grid, st);
       return kp.genre_hi ? launch_k1<4, false, 2, 1, true, true>(f, sweep, grid, st)
                          : launch_k1<4, false, 2, 1, true>(f, sweep, grid, st);
     }
+    if (kp.fold) return launch_k1<4, false, 2, 1, false, false, true>(f, sweep, grid, st);
     return kp.genre_hi ? launch_k1<4, false, 2, 1, false, true>(f, sweep, grid, st)
                        : launch_k1<4, false, 2, 1>(f, sweep, grid, st);
   }
+  if (kp.fold) return launch_k1<4, false, 2, 0, false, false, true>(f, kp, grid, st);
   if (kp.genre_hi != nullptr) {
     if (cta_group != 2) {
       tvbf_set_error("two-word genre masks (G > 64) need cta_group 2");

@@ -82,6 +82,8 @@ struct K1Params {
   unsigned int* g_theta;   // [n_pad] raw bits of the (positive) float threshold of each show
   unsigned int* g_cnt;     // [n_pad] appends so far (> sym_cap = overflow)
   uint2* g_list;           // [n_pad][sym_cap] (score bits, column)
+  int fold;            // the operand carries the packed genre / metadata groups (tvbf_features.bits_folded):
+                       // the accumulator is the whole hybrid and the epilogue skips the popcounts
   int refresh_period;  // a list's threshold is refreshed at 2*kp entries and every refresh_period further ones
                        // (a power of two; 0: at 2*kp, 4*kp, 8*kp, ...)
   int wait_ns;         // first sleep of the backed-off mbarrier waits

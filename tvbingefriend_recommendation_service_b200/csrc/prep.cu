@@ -141,6 +141,28 @@ __global__ void meta_bits_kernel(const uint8_t* __restrict__ platform, int p_dim
   meta_scale[row] = s;
 }
 
+// Packed records -> operand columns (tvbf_prep_fold_bits): one thread per (show, column), consecutive
+// threads write consecutive 2-byte entries of a row.
+template <typename T>
+__global__ void fold_bits_kernel(const TvbfColSide* __restrict__ col_side,
+                                 const unsigned long long* __restrict__ genre_hi,
+                                 const float* __restrict__ meta_scale, int n_rows, int g_dim,
+                                 T* __restrict__ operand, int k_pad, int col0, double scale_genre, double scale_meta) {
+  const int width = g_dim + 32;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n_rows) * width) return;
+  const int row = static_cast<int>(i / width), c = static_cast<int>(i - static_cast<size_t>(row) * width);
+  const TvbfColSide cs = col_side[row];
+  double v = 0.0;   // one rounding, from fp64, like the text columns
+  if (c < g_dim) {
+    const unsigned long long word = c < 64 ? cs.genre_bits : genre_hi[row];
+    if ((word >> (c & 63)) & 1ull) v = static_cast<double>(cs.genre_rnorm) * scale_genre;
+  } else if ((cs.meta_bits >> (c - g_dim)) & 1u) {
+    v = static_cast<double>(meta_scale[row]) * scale_meta;
+  }
+  operand[static_cast<size_t>(row) * k_pad + col0 + c] = cvt_operand<T>(v);
+}
+
 // ---- device-side ingest of the raw feature arrays (any of the dtypes numpy hands over) --------------
 // dtype codes of the raw arrays: 0 uint8 / bool, 1 int32, 2 int64, 3 float32, 4 float64
 __device__ __forceinline__ double load_raw(const void* p, int dtype, size_t i) {
@@ -363,6 +385,31 @@ int tvbf_prep_dense_to_operand(const double* dense, int32_t n_rows, int32_t dim,
     dense_to_operand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
         dense, n_rows, dim, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset, scale);
   TVBF_LAUNCH_OK("dense_to_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_prep_fold_bits(const void* col_side, const uint64_t* genre_hi, const float* meta_scale,
+                        int32_t n_rows, int32_t genre_dim, void* operand, int32_t k_pad, int32_t col0,
+                        double scale_genre, double scale_meta, int32_t dtype, void* stream) {
+  TVBF_REQUIRE(col_side && meta_scale && operand && n_rows >= 0 && genre_dim >= 1 && genre_dim <= 128 &&
+                   col0 >= 0 && col0 + genre_dim + 32 <= k_pad,
+               "tvbf_prep_fold_bits: bad arguments");
+  TVBF_REQUIRE(genre_dim <= 64 || genre_hi != nullptr, "tvbf_prep_fold_bits: %d genre columns need genre_hi", genre_dim);
+  TVBF_REQUIRE(dtype == TVBF_TEXT_FP16 || dtype == TVBF_TEXT_BF16,
+               "tvbf_prep_fold_bits: dtype must be TVBF_TEXT_FP16 or TVBF_TEXT_BF16");
+  if (n_rows == 0) return TVBF_OK;
+  auto st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = blocks_for(static_cast<size_t>(n_rows) * (genre_dim + 32), 256);
+  const auto* cs = static_cast<const TvbfColSide*>(col_side);
+  const auto* gh = reinterpret_cast<const unsigned long long*>(genre_hi);
+  if (dtype == TVBF_TEXT_FP16)
+    fold_bits_kernel<__half><<<grid, 256, 0, st>>>(cs, gh, meta_scale, n_rows, genre_dim, static_cast<__half*>(operand),
+                                                    k_pad, col0, scale_genre, scale_meta);
+  else
+    fold_bits_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(cs, gh, meta_scale, n_rows, genre_dim,
+                                                           static_cast<__nv_bfloat16*>(operand), k_pad, col0,
+                                                           scale_genre, scale_meta);
+  TVBF_LAUNCH_OK("fold_bits_kernel");
   return TVBF_OK;
 }
 

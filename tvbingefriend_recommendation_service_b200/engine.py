@@ -17,6 +17,8 @@ from __future__ import annotations
 import ctypes as C
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -125,6 +127,7 @@ class DeviceCatalogue:
     operand: torch.Tensor | None = None    # [n_pad, k_pad] fp16 / bf16
     text_indptr: torch.Tensor | None = None
     text_indices: torch.Tensor | None = None
+    fold: dict | None = None               # second operand with the packed groups as K columns (engine._folded)
 
 
 @dataclass
@@ -212,6 +215,13 @@ class HybridTopKEngine:
         self._launch_base = int(self.lib.tvbf_kernel_launches())
         self._ws: torch.Tensor | None = None
         self._pinned: dict = {}
+        # Small vocabularies: the candidate pass is bound by its epilogue, not by the MMAs, so the
+        # packed genre / metadata groups are ALSO written into a second operand as K columns and the
+        # epilogue drops its popcounts (tvbf_features.bits_folded).  Used while the widened operand
+        # has at most fold_max_k columns (0 disables; TVBF_FOLD_MAX_K overrides).
+        self.fold_max_k = int(os.environ.get("TVBF_FOLD_MAX_K", "2048"))
+        self._fold_buf: torch.Tensor | None = None
+        self._fold_owner: dict | None = None      # the catalogue fold whose content the buffer holds
 
     @property
     def kernel_launches(self) -> int:
@@ -228,6 +238,8 @@ class HybridTopKEngine:
         useful between jobs of very different size, e.g. after a 200 k x 50 k catalogue."""
         self._ws = None
         self._pinned.clear()
+        self._fold_buf = None
+        self._fold_owner = None
         if torch.cuda.is_available():
             with torch.cuda.device(self.device):
                 torch.cuda.empty_cache()
@@ -499,6 +511,50 @@ class HybridTopKEngine:
               "tvbf_prep_csr_to_operand")
         return values, operand
 
+    def _folded(self, cat: DeviceCatalogue, gw: float, tw: float, mw: float, k: int) -> Features | None:
+        """``tvbf_features`` of ``cat`` over a second operand that carries the packed genre / metadata
+        groups as K columns for these weights, or None when the job does not qualify."""
+        c = cat.c
+        g_dim = int(c.genre_dim)
+        k_fold = (int(c.vocab) + g_dim + 32 + 63) // 64 * 64
+        ok = (self.fold_max_k > 0 and k_fold <= self.fold_max_k and k <= 48 and not cat.folded
+              and c.genre_mode == _lib.GROUP_PACKED and c.meta_mode == _lib.GROUP_PACKED and not c.text_signed
+              and self.text_dtype == "fp16" and tw > 0.0 and gw >= 0.0 and mw >= 0.0
+              and all(w == 0.0 or 1e-8 <= w / tw <= 1e4 for w in (gw, mw)))   # columns stay normal fp16 numbers
+        if not ok or cat.operand is None:
+            return None
+        lib, stream = self.lib, self._stream()
+        code, tdt = _DTYPES[self.text_dtype]
+        scale = float(2 ** TEXT_SCALE_LOG2)
+        fc = cat.fold
+        if fc is None:
+            n_pad = int(c.n_pad)
+            buf = self._fold_buf
+            if buf is None or tuple(buf.shape) != (n_pad, k_fold) or buf.dtype != tdt:
+                self._fold_buf = None
+                buf = torch.empty((n_pad, k_fold), dtype=tdt, device=self.device)
+                self._fold_buf = buf            # one buffer per engine, reused by the next catalogue of this shape
+            self._zero(buf)
+            check(lib.tvbf_prep_csr_to_operand(c.text_indptr, c.text_indices, c.text_values, cat.n_shows,
+                                               buf.data_ptr(), k_fold, 0, scale, code, stream),
+                  "tvbf_prep_csr_to_operand")
+            f = Features.from_buffer_copy(c)
+            f.operand, f.k_pad = buf.data_ptr(), k_fold
+            f.bits_folded, f.fold_col0 = 1, int(c.vocab)
+            fc = cat.fold = {"c": f, "operand": buf, "weights": None}
+            self._fold_owner = fc
+        elif self._fold_owner is not fc:
+            cat.fold = None                     # the engine's buffer went to another catalogue since
+            return self._folded(cat, gw, tw, mw, k)
+        if fc["weights"] != (gw, tw, mw):
+            f = fc["c"]
+            check(lib.tvbf_prep_fold_bits(c.col_side, c.genre_hi, c.meta_scale, cat.n_shows, g_dim, f.operand, k_fold,
+                                          int(c.vocab), scale * float(np.sqrt(gw / tw)), scale * float(np.sqrt(mw / tw)),
+                                          code, stream), "tvbf_prep_fold_bits")
+            f.fold_weights[0], f.fold_weights[1], f.fold_weights[2] = gw, tw, mw
+            fc["weights"] = (gw, tw, mw)
+        return fc["c"]
+
     # ------------------------------------------------------------------------------------ top-k
     _TABLE_FIELDS = ("indices", "counts", "hybrid", "genre", "text", "metadata", "stats")
 
@@ -537,13 +593,16 @@ class HybridTopKEngine:
                    splits=int(splits), candidates=int(candidates), force_exact=int(bool(force_exact)),
                    skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0, phases=int(phases), tuning=int(tuning))
         with torch.cuda.device(self.device):
-            nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(cat.c), C.byref(p))
+            feats = None if force_exact else self._folded(cat, gw, tw, mw, int(k))
+            if feats is None:
+                feats = cat.c
+            nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(feats), C.byref(p))
             if nbytes == 0:
                 check(-1, "tvbf_topk_workspace_bytes")
             ws = self._workspace(nbytes)
             t = out if out is not None else self._alloc_tables(rows, k)
             cout = self._c_tables(t)
-            check(self.lib.tvbf_hybrid_topk(C.byref(cat.c), C.byref(p), C.byref(cout), ws.data_ptr(),
+            check(self.lib.tvbf_hybrid_topk(C.byref(feats), C.byref(p), C.byref(cout), ws.data_ptr(),
                                             ws.numel(), self._stream()), "tvbf_hybrid_topk")
         t["row_begin"] = row_begin
         return t
@@ -993,20 +1052,22 @@ class HybridTopKEngine:
         return {"seed_tiles": seed, "sweep_tiles": sweep, "tile_rows": rows, "symmetric": bool(sym),
                 "flops": 2.0 * (seed + sweep) * rows * 256 * int(cat.c.k_pad)}
 
-    def debug_slack(self, cat: DeviceCatalogue, weights) -> dict:
-        """Constants of the candidate pass' upper bound (``tvbf_debug_slack``; tests only)."""
+    def debug_slack(self, cat: DeviceCatalogue, weights, feats: Features | None = None) -> dict:
+        """Constants of the candidate pass' upper bound (``tvbf_debug_slack``; tests only).  ``feats``:
+        the ``_folded`` variant of ``cat``'s features."""
         p = self._params(cat, weights, 20, 0.1)
         out = (C.c_float * 5)()
-        check(self.lib.tvbf_debug_slack(C.byref(cat.c), C.byref(p), out), "tvbf_debug_slack")
+        check(self.lib.tvbf_debug_slack(C.byref(cat.c if feats is None else feats), C.byref(p), out), "tvbf_debug_slack")
         return dict(zip(("w_text", "w_text_err", "w_text_acc", "eps", "eps_term"), (float(x) for x in out)))
 
-    def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int, pair: bool = False) -> torch.Tensor:
+    def debug_gemm_tile(self, cat: DeviceCatalogue, row0: int, col0: int, pair: bool = False,
+                        feats: Features | None = None) -> torch.Tensor:
         """Raw fp32 accumulators of one tensor-core tile (diagnostics / tests): 128 x 256 through
         cta_group::1, or 256 x 256 through a cta_group::2 CTA pair."""
         with torch.cuda.device(self.device):
             out = torch.zeros((256 if pair else 128, 256), dtype=torch.float32, device=self.device)
             fn = self.lib.tvbf_debug_gemm_tile_pair if pair else self.lib.tvbf_debug_gemm_tile
-            check(fn(C.byref(cat.c), int(row0), int(col0), out.data_ptr(), self._stream()),
+            check(fn(C.byref(cat.c if feats is None else feats), int(row0), int(col0), out.data_ptr(), self._stream()),
                   "tvbf_debug_gemm_tile")
         return out
 
