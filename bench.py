@@ -317,6 +317,35 @@ def nxn_variant(eng, weights, names=("C1", "C2")) -> dict:
     return out
 
 
+def weight_sweep(eng, config: str = "C3", reps: int = 3) -> dict:
+    """The reference notebook's five weight schemes (notebooks/03_content_similarity cell 6; BASELINE
+    config C5's sweep) on ``config`` through ONE shared symmetric tensor-core sweep (kMode 5): the text
+    GEMM is executed once, the epilogue scores every triple."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import CONFIGS, WEIGHT_SWEEP, make_config
+
+    cat = make_config(config)
+    k = CONFIGS[config]["k"]
+    dc = eng.upload(stage(cat.features()))
+    ts, out = [], None
+    for _ in range(1 + reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = eng.top_k_sweep_device(dc, WEIGHT_SWEEP, k, 0.1, shared=True)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    res = {"config": config, "triples": [list(w) for w in WEIGHT_SWEEP], "k": k, "ms_all_triples": float(np.mean(ts[1:])),
+           "ms_per_triple": float(np.mean(ts[1:])) / len(WEIGHT_SWEEP),
+           "flagged_rows": [int(t["stats"][0]) for t in out]}
+    del dc, out, cat
+    eng.release()
+    return res
+
+
 def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict, steps: int = 3,
               tuning: int = 0, config: str | None = None) -> dict:
     """One more BASELINE.json shape in the same run (same kernels, same drivers, device-resident
@@ -391,8 +420,8 @@ def run_extra(name: str, eng, args, world: int, rank: int, weights, peaks: dict,
     res = {"workload": f"{n} shows x vocab {cfg['vocab']} (~{cfg['nnz']} nnz/row), top-{k}, metadata {cfg['meta']}",
            "ms_per_step": ms, "shows_per_s": n / (ms * 1e-3), "k1_ms": k1, "executed_tflops": tf,
            "frac": tf / peaks["bf16_tflops_sustained"], "symmetric_sweep": plan["symmetric"],
-           "tiles": plan["seed_tiles"] + plan["sweep_tiles"], "tile": f"{plan['tile_rows']}x256x{int(dc.c.k_pad)}",
-           "flagged_rows": int(stats[0]), "steps": steps}
+           "tiles": plan["seed_tiles"] + plan["sweep_tiles"], "tile": f"{plan['tile_rows']}x256x{plan['k_pad']}",
+           "genre_metadata_in_operand": plan["folded_bits"], "flagged_rows": int(stats[0]), "steps": steps}
     del raw, st, cat, out, dc
     prev[0] = None
     eng.release()
@@ -422,7 +451,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-dense-probe", action="store_true")
-    ap.add_argument("--extra", default="P80k,C4,C5,one_sided,nxn", help="comma-separated extra configs timed in the same run ('' = none)")
+    ap.add_argument("--extra", default="P80k,C4,C5,one_sided,weight_sweep,nxn", help="comma-separated extra configs timed in the same run ('' = none)")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--one-sided", action="store_true", help="disable the symmetric sweep at N > 1")
     ap.add_argument("--tuning", type=lambda x: int(x, 0), default=0, help="tvbf_params.tuning bitfield")
@@ -598,6 +627,9 @@ def main() -> None:
                 elif name == "nxn":
                     if world == 1:
                         extra["nxn_variant"] = nxn_variant(eng, weights)
+                elif name == "weight_sweep":
+                    if world == 1:
+                        extra["weight_sweep"] = weight_sweep(eng, args.config)
                 else:
                     extra[name] = run_extra(name, eng, args, world, rank, weights, peaks)
             except Exception as exc:   # an extra must never take the headline down with it
@@ -635,6 +667,7 @@ def main() -> None:
             eng.plan_tiles(dc_plan, weights, k, 0.1, row_begin=rb, row_end=re_, splits=args.splits,
                            tuning=args.tuning | (1 << 20))
     else:
+        eng._folded(dc_plan, *[float(w) for w in weights], k)   # small vocabularies: plan over the operand the job ran on
         plan = eng.plan_tiles(dc_plan, weights, k, 0.1, splits=args.splits, tuning=args.tuning)
     used_sym = plan["symmetric"]
     exec_flops = plan["flops"]      # this GPU's tiles (seed pass + sweep) x tile rows x 256 x K_pad x 2
@@ -660,7 +693,7 @@ def main() -> None:
                 "flops_per_launch": exec_flops, "peak_kind": f"bf16 sustained, {peaks['source']}",
                 "peak_burst": peaks["bf16_tflops"], "frac_of_burst": exec_tflops / peaks["bf16_tflops"],
                 "symmetric_sweep": bool(used_sym), "seed_tiles": plan["seed_tiles"], "sweep_tiles": plan["sweep_tiles"],
-                "tile": f"{plan['tile_rows']}x256x{int(dc_plan.c.k_pad)}",
+                "tile": f"{plan['tile_rows']}x256x{plan['k_pad']}", "genre_metadata_in_operand": plan["folded_bits"],
                 "algorithmic_flops_per_launch": flops, "algorithmic_tflops": alg_tflops,
                 "frac_algorithmic": alg_tflops / peak if peak else None,
                 "note": "achieved / frac count the flops the tensor pipe EXECUTES (256x256xK_pad tiles "

@@ -389,6 +389,11 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
   }
   kp.n_weights = 1;
   kp.n_pad = f->n_pad;
+  // no upper bound U exceeds the sum of the weights by more than its (relative) slack
+  auto score_hi = [](const tvbf_params& q) {
+    return static_cast<float>((std::fabs(q.genre_weight) + std::fabs(q.text_weight) + std::fabs(q.metadata_weight)) * 1.02 + 1e-3);
+  };
+  kp.score_hi = score_hi(*p);
   if (n_sweep > 1) {
     // weight sweep over the triples p[0 .. n_sweep) (packed groups only, checked by the caller):
     // the epilogue constants of every triple, same formulas as above
@@ -403,6 +408,7 @@ int fill_k1_params(const tvbf_features* f, const tvbf_params* p, const Plan& pl,
       kp.mw_eps_term[w] = sl.eps_term;
       kp.mw_genre[w] = static_cast<float>(q.genre_weight);
       kp.mw_meta[w] = static_cast<float>(q.metadata_weight);
+      kp.mw_score_hi[w] = score_hi(q);
     }
   }
   return TVBF_OK;

@@ -396,6 +396,7 @@ struct Pacer {
 };
 
 // kMode: 0 one-sided top-k sweep, 1 symmetric top-k sweep, 2 symmetric statistics sweep,
+// 3 threshold seed pass (one-sided walk over sampled tiles, per-row score histograms, no lists),
 // 5 symmetric top-k sweep for p.n_weights weight triples at once (one shared list per triple and show)
 // kG2: multi-hot genres with 64 < G <= 128 -- the second word of every column's mask is staged beside
 // the column-side records (in the threshold slices a single-triple sweep leaves unused) and the
@@ -411,14 +412,23 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                    const __grid_constant__ CUtensorMap tmap_b, const K1Params p,
                    const uint32_t idesc) {
   using L = Smem<CG, kWide>;
-  constexpr bool kSym = kMode != 0;      // tiles on/above the diagonal, 8 (kWide: 16) epilogue warps
+  constexpr bool kHist = kMode == 3;     // threshold seed pass: per-row histograms of the sampled scores
+  constexpr bool kSym = kMode != 0 && !kHist;   // tiles on/above the diagonal, 8 (kWide: 16) epilogue warps
   constexpr bool kStats = kMode == 2;    // accumulate statistics instead of candidate lists
   constexpr bool kMulti = kMode == 5;    // weight sweep
   static_assert(!(kG2 && (kMulti || kStats)), "two-word genre masks: single-triple top-k sweeps only");
   static_assert(!(kFold && (kMulti || kStats || kDump || kG2)), "folded groups: single-triple top-k sweeps only");
+  // Seed pass: hist[bin][row of the CTA] (32-bit counters; bank = row % 32, so the 32 lanes of a warp
+  // never collide) in the two ring stages a seed launch does not use.  Bin 0 collects everything below
+  // the range (and the columns a row may not name), bin b >= 1 the scores in
+  // [lo + (b-1) w, lo + b w).  A row's seeded threshold is the lower edge of the bin in which the count
+  // from the top reaches kp: at least kp sampled columns score that high, so the kp-th best of ALL columns
+  // does too.  No lists, no compaction: the list-based seed pass spent 4/5 of its time selecting.
+  constexpr int kHistBins = 64;
+  static_assert(!kHist || (2 * A_BYTES >= kHistBins * BM * 4), "histogram does not fit two A stages");
   constexpr uint32_t GH_BYTES = BN * 8;  // second genre word of the tile's 256 columns
   constexpr int STAGES = L::STAGES;
-  using R = Roles<kSym, kWide>;
+  using R = Roles<(kMode != 0), kWide>;
   constexpr int EPI = R::EPI, PRODUCER_WARP = R::PRODUCER, MMA_WARP = R::MMA;
   constexpr int COLS_PER_WARP = BN / (EPI / 4);   // 256 (one-sided) or 128 (symmetric)
   constexpr int GW = (kWide && !kFold) ? 4 : 8;   // columns scored together (independent chains)
@@ -435,6 +445,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* col_full = bars + 2 * STAGES + 4;     // [2] column-side records landed
   uint64_t* col_empty = bars + 2 * STAGES + 6;    // [2] column-side buffer free again
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(smem + L::OFF_A + (STAGES - 2) * A_BYTES);   // kHist only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -605,6 +616,10 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     unsigned int* shist = reinterpret_cast<unsigned int*>(smem + L::OFF_A + (STAGES - 1) * A_BYTES);
     if (kStats) {
       for (int b = threadIdx.x; b < 4 * kStatsBins; b += 32 * EPI) shist[b] = 0u;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+    }
+    if (kHist) {
+      for (int i = threadIdx.x; i < kHistBins * BM; i += 32 * EPI) hist[i] = 0u;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
     }
     // symmetric sweeps: this warp's ring of pending list appends and its (warp-uniform) fill count
@@ -860,6 +875,15 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
               if (kSym) {
                 if (!do_col) hit_c = 0u;
                 push_hits(hit_r | (hit_c << GW), u, col0 + cbase + h * GW, 0);
+              } else if (kHist) {
+#pragma unroll
+                for (int e = 0; e < GW; ++e) {
+                  const int col = col0 + cbase + h * GW + e;
+                  int bin = __float2int_rd(fmaf(u[e], p.hist_inv_w, p.hist_off));
+                  bin = min(max(bin, 0), kHistBins - 1);
+                  if (col == self_col || col >= p.n_shows) bin = 0;
+                  atomicAdd(&hist[bin * BM + row_in_tile], 1u);
+                }
               } else {
                 // private list of this thread's row (at most GW appends; 32 free slots are guaranteed)
                 while (hit_r) {
@@ -927,7 +951,7 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 theta = __uint_as_float(tb);
               }
             }
-          } else if (!kDump && !kSym) {
+          } else if (!kDump && !kSym && !kHist) {
             // keep 32 free slots for the next 32 columns; compact rows that are nearly full
             unsigned need = __ballot_sync(kFullMask, cnt > CAP - 32);
             while (need) {
@@ -954,7 +978,29 @@ hybrid_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       if (kSym && !kStats && ring_n > 0) ring_flush();   // nothing stays queued past the item (or the kernel)
 
-      if (!kDump && !kSym) {
+      if (kHist) {
+        // every epilogue warp has added its columns: the first warp of each lane quarter turns the 32
+        // histograms of its rows into thresholds and clears them for the next item
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+        if ((warp >> 2) == 0) {
+          int c = 0, found = 0;
+          hist[row_in_tile] = 0u;
+#pragma unroll 4
+          for (int bin = kHistBins - 1; bin >= 1; --bin) {
+            c += static_cast<int>(hist[bin * BM + row_in_tile]);
+            hist[bin * BM + row_in_tile] = 0u;
+            if (c >= p.kp && found == 0) found = bin;
+          }
+          if (found != 0 && row_valid) {
+            // lower edge of the bin, minus a margin for the rounding of the bin computation
+            const float th = fmaf(static_cast<float>(found - 1) - 1e-3f, p.hist_w, p.hist_lo);
+            if (th > p.theta_init) p.g_theta[row] = __float_as_uint(th);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI) : "memory");
+      }
+
+      if (!kDump && !kSym && !kHist) {
         // final compaction of every row of this warp: sorted best-kp list -> cand
         const int rows_in_shard = p.row_end - p.row_begin;
         for (int src_lane = 0; src_lane < 32; ++src_lane) {
@@ -1369,6 +1415,17 @@ static K1Params make_seed_params(const K1Params& kp, int grid, int w) {
     seed.w_text_acc = kp.mw_text_acc[w];
     seed.eps_term = kp.mw_eps_term[w];
     seed.g_theta = kp.g_theta + static_cast<size_t>(w) * kp.n_pad;
+    seed.score_hi = kp.mw_score_hi[w];
+  }
+  {
+    // score histogram of the seed pass: 63 bins over [theta_init, score_hi)
+    const float lo = kp.theta_init, span = seed.score_hi > lo ? seed.score_hi - lo : 1.0f;
+    seed.hist_lo = lo;
+    seed.hist_w = span / 63.0f;
+    seed.hist_inv_w = 63.0f / span;
+    seed.hist_off = 1.0f - lo * seed.hist_inv_w;
+    const int max_stages = (kp.wide_epilogue ? Smem<2, true>::STAGES : Smem<2, false>::STAGES) - 2;
+    if (seed.stages > max_stages) seed.stages = max_stages;   // the histogram lives in the last two A stages
   }
   if (kp.seed_world > 1)   // blocks seed_rank, seed_rank + seed_world, ... of the col_tiles super blocks
     seed.rb_count = kp.col_tiles > kp.seed_rank ? (kp.col_tiles - kp.seed_rank + kp.seed_world - 1) / kp.seed_world : 0;
@@ -1491,17 +1548,18 @@ int k1_launch(const tvbf_features* f, const K1Params& kp, int entries_per_lane, 
         for (int w = 0; w < nw; ++w) {
           const K1Params seed = make_seed_params(kp, grid, w);
           int rc;
-          // (512-entry private lists, which almost never compact inside the loop, were measured
-          // slower on P80k: 2.07 against 1.57 ms -- the final selection over the longer lists costs
-          // more than the in-loop compactions it saves)
-          if (kp.fold)
-            rc = launch_k1<4, false, 2, 0, false, false, true>(f, seed, seed.rb_per_group * 2, st);
-          else if (kp.genre_hi != nullptr)
-            rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st)
-                             : launch_k1<8, false, 2, 0, false, true>(f, seed, seed.rb_per_group * 2, st);
-          else
-            rc = kp.kp <= 64 ? launch_k1<4, false, 2, 0>(f, seed, seed.rb_per_group * 2, st)
-                             : launch_k1<8, false, 2, 0>(f, seed, seed.rb_per_group * 2, st);
+          // kMode 3: per-row score histograms instead of private candidate lists (P80k: 1.43 ms with
+          // lists -- 4/5 of it selecting and compacting, with 4 epilogue warps -- against the sweep's 4.7)
+          const int sg = seed.rb_per_group * 2;
+          if (kp.wide_epilogue) {
+            if (kp.fold) rc = launch_k1<4, false, 2, 3, true, false, true>(f, seed, sg, st);
+            else if (kp.genre_hi != nullptr) rc = launch_k1<4, false, 2, 3, true, true>(f, seed, sg, st);
+            else rc = launch_k1<4, false, 2, 3, true>(f, seed, sg, st);
+          } else {
+            if (kp.fold) rc = launch_k1<4, false, 2, 3, false, false, true>(f, seed, sg, st);
+            else if (kp.genre_hi != nullptr) rc = launch_k1<4, false, 2, 3, false, true>(f, seed, sg, st);
+            else rc = launch_k1<4, false, 2, 3>(f, seed, sg, st);
+          }
           if (rc != TVBF_OK) return rc;
           TVBF_CUDA_OK(cudaMemsetAsync(kp.progress, 0, 256, st));
         }

@@ -82,6 +82,9 @@ struct K1Params {
   unsigned int* g_theta;   // [n_pad] raw bits of the (positive) float threshold of each show
   unsigned int* g_cnt;     // [n_pad] appends so far (> sym_cap = overflow)
   uint2* g_list;           // [n_pad][sym_cap] (score bits, column)
+  // threshold seed pass (kMode 3): bin = floor(u * hist_inv_w + hist_off), bin b >= 1 = [lo + (b-1) w, lo + b w)
+  float hist_lo, hist_w, hist_inv_w, hist_off;
+  float score_hi;      // no upper bound U exceeds this (sum of the weights, inflated)
   int fold;            // the operand carries the packed genre / metadata groups (tvbf_features.bits_folded):
                        // the accumulator is the whole hybrid and the epilogue skips the popcounts
   int refresh_period;  // a list's threshold is refreshed at 2*kp entries and every refresh_period further ones
@@ -111,6 +114,7 @@ struct K1Params {
   int n_pad;
   float mw_text[kMaxSweep], mw_text_err[kMaxSweep], mw_genre[kMaxSweep], mw_meta[kMaxSweep], mw_eps[kMaxSweep];
   float mw_text_acc[kMaxSweep], mw_eps_term[kMaxSweep];
+  float mw_score_hi[kMaxSweep];   // score_hi of each triple (histogram range of its seed pass)
 };
 
 // parameters of the exact fp64 scorers (rescore.cu)

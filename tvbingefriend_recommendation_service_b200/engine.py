@@ -722,14 +722,20 @@ class HybridTopKEngine:
         over the ranks."""
         p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
         with torch.cuda.device(self.device):
-            nbytes = self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world)
+            feats = self._k1_features(cat, weights, k)
+            nbytes = self.lib.tvbf_sym_workspace_bytes(C.byref(feats), C.byref(p), world)
             if nbytes == 0:
                 check(-1, "tvbf_sym_workspace_bytes")
             ws = self._workspace(nbytes)
             theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
-            check(self.lib.tvbf_sym_seed(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
+            check(self.lib.tvbf_sym_seed(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
                                          ws.numel(), self._stream()), "tvbf_sym_seed")
         return theta
+
+    def _k1_features(self, cat: DeviceCatalogue, weights, k) -> Features:
+        """The features the candidate pass runs on: the folded operand when the job qualifies."""
+        gw, tw, mw = (float(w) for w in weights)
+        return self._folded(cat, gw, tw, mw, int(k)) or cat.c
 
     def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
                   theta: torch.Tensor, splits: int = 0, tuning: int = 0, packed_rows: int = 0,
@@ -741,24 +747,25 @@ class HybridTopKEngine:
         p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
         dev, n = self.device, cat.n_shows
         with torch.cuda.device(dev):
-            ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(cat.c), C.byref(p), world))
-            L = int(self.lib.tvbf_sym_list_len(C.byref(cat.c), C.byref(p)))
+            feats = self._k1_features(cat, weights, k)
+            ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(feats), C.byref(p), world))
+            L = int(self.lib.tvbf_sym_list_len(C.byref(feats), C.byref(p)))
             if peer_ptrs is not None:     # compaction fused with the exchange: rows go to their owners' buffers
-                check(self.lib.tvbf_sym_sweep_peer(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), peer_ptrs,
+                check(self.lib.tvbf_sym_sweep_peer(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(), peer_ptrs,
                                                    int(peer_shard_rows), ws.data_ptr(), ws.numel(), self._stream()),
                       "tvbf_sym_sweep_peer")
                 return None
             if packed_rows:
                 assert packed_rows >= n
                 packed = torch.empty((packed_rows, L + 1, 2), dtype=torch.int32, device=dev)
-                check(self.lib.tvbf_sym_sweep(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(),
+                check(self.lib.tvbf_sym_sweep(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(),
                                               packed.data_ptr(), None, None, ws.data_ptr(), ws.numel(), self._stream()),
                       "tvbf_sym_sweep")
                 return packed
             cand = torch.empty((n, L, 2), dtype=torch.int32, device=dev)
             cnt = torch.empty((n,), dtype=torch.int32, device=dev)
             bound = torch.empty((n,), dtype=torch.float32, device=dev)
-            check(self.lib.tvbf_sym_sweep(C.byref(cat.c), C.byref(p), rank, world, theta.data_ptr(), cand.data_ptr(),
+            check(self.lib.tvbf_sym_sweep(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(), cand.data_ptr(),
                                           cnt.data_ptr(), bound.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
                   "tvbf_sym_sweep")
         return cand, cnt, bound
@@ -1041,16 +1048,22 @@ class HybridTopKEngine:
     def plan_tiles(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int = 0, world: int = 1,
                    tile_sharded: bool = False, row_begin: int = 0, row_end: int | None = None, splits: int = 0,
                    tuning: int = 0) -> dict:
-        """Tensor-core tiles the candidate pass of this job executes (``tvbf_plan_tiles``, host only)."""
+        """Tensor-core tiles the candidate pass of this job executes (``tvbf_plan_tiles``, host only).
+        A single-GPU job that ``top_k_device`` runs over the folded operand is planned over it (k_pad)."""
         p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end, splits=splits,
                          tuning=tuning)
         out = (C.c_int64 * 4)()
+        feats = cat.c
+        if world == 1 and cat.fold is not None and cat.fold["weights"] == tuple(float(w) for w in weights) \
+                and self._fold_owner is cat.fold:
+            feats = cat.fold["c"]
         with torch.cuda.device(self.device):
-            check(self.lib.tvbf_plan_tiles(C.byref(cat.c), C.byref(p), int(rank), int(world), int(bool(tile_sharded)),
+            check(self.lib.tvbf_plan_tiles(C.byref(feats), C.byref(p), int(rank), int(world), int(bool(tile_sharded)),
                                            out), "tvbf_plan_tiles")
         seed, sweep, rows, sym = (int(x) for x in out)
         return {"seed_tiles": seed, "sweep_tiles": sweep, "tile_rows": rows, "symmetric": bool(sym),
-                "flops": 2.0 * (seed + sweep) * rows * 256 * int(cat.c.k_pad)}
+                "k_pad": int(feats.k_pad), "folded_bits": bool(feats.bits_folded),
+                "flops": 2.0 * (seed + sweep) * rows * 256 * int(feats.k_pad)}
 
     def debug_slack(self, cat: DeviceCatalogue, weights, feats: Features | None = None) -> dict:
         """Constants of the candidate pass' upper bound (``tvbf_debug_slack``; tests only).  ``feats``:
