@@ -513,15 +513,27 @@ def main() -> None:
                 events.setdefault(name, []).append(ev)
 
         mark("step0")
+        h0 = time.perf_counter()
         dc = eng.prepare(raw, weights, recycle=state["prev"])     # the previous step's operand buffer is recycled
         state["prev"] = dc
         if world > 1:
-            return top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
-                                            symmetric=None if not args.one_sided else False, events=events)
+            h1 = time.perf_counter()
+            res = top_k_device_distributed(eng, dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
+                                           symmetric=None if not args.one_sided else False, events=events,
+                                           tables=state.get("tables"))
+            state["tables"] = res["_full"]      # the gather buffers are reused from step to step
+            if os.environ.get("BENCH_DEBUG") and rank == 0 and events:
+                print(f"host: prepare {1e3 * (h1 - h0):.2f} ms, distributed job {1e3 * (time.perf_counter() - h1):.2f} ms",
+                      file=sys.stderr)
+            return res
         if events is None:
-            return eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
+            state["tables"] = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
+                                               out=state.get("tables"))
+            return state["tables"]
         mark("seed0")
-        t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=1, tuning=args.tuning)
+        t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=1, tuning=args.tuning,
+                             out=state.get("tables"))
+        state["tables"] = t
         for name in ("seed1", "reduce1", "sweep1", "exchange1"):   # one launch sequence: seed + sweep = "sweep"
             mark(name)
         eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, phases=6, out=t, tuning=args.tuning)
@@ -559,8 +571,10 @@ def main() -> None:
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     ev0.record()
+    host_t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device(events)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / args.steps   # host time to ISSUE a step (no sync inside)
     ev1.record()
     sync()
     launches = eng.kernel_launches - launches0
@@ -594,12 +608,14 @@ def main() -> None:
         if world > 1:     # sliced upload + NVLink replication in, shared pinned host table out
             return dtk.run(st, weights, 0.1, True, symmetric=None if not args.one_sided else False,
                            splits=args.splits, tuning=args.tuning)
-        dc = eng.prepare(eng.h2d(st), weights, recycle=state["prev"])
+        dc = eng.prepare(eng.h2d(st, reuse=True), weights, recycle=state["prev"])
         state["prev"] = dc
-        t = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning)
+        t = state["tables"] = eng.top_k_device(dc, weights, k, 0.1, True, splits=args.splits, tuning=args.tuning,
+                                               out=state.get("tables"))
         return eng.to_host(t, copy=False)
 
-    step_e2e()
+    for _ in range(3):      # warm-up: both sets of cached buffers and the pinned host tables exist afterwards
+        step_e2e()
     sync()
     ev0.record()
     for _ in range(args.steps):
@@ -714,6 +730,7 @@ def main() -> None:
                         f"whole-job total) and NVLink all-gathers them; every rank copies its shard of the table "
                         f"into one pinned host table in shared memory (d2h_bytes_per_step is the whole table)"},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),   # rank 0; below ms_per_step = the GPU is the bound
         "phases_ms": phases_max,                 # max over ranks: a collective's entry includes waiting for the slowest rank
         "phases_ms_min_over_ranks": phases_min,  # ... the minimum is the collective itself
         "clocks": clocks,

@@ -128,6 +128,7 @@ class DeviceCatalogue:
     text_indptr: torch.Tensor | None = None
     text_indices: torch.Tensor | None = None
     fold: dict | None = None               # second operand with the packed groups as K columns (engine._folded)
+    buffers: dict = field(default_factory=dict)   # named per-catalogue device buffers a later catalogue can take over
 
 
 @dataclass
@@ -222,6 +223,7 @@ class HybridTopKEngine:
         self.fold_max_k = int(os.environ.get("TVBF_FOLD_MAX_K", "2048"))
         self._fold_buf: torch.Tensor | None = None
         self._fold_owner: dict | None = None      # the catalogue fold whose content the buffer holds
+        self._theta: torch.Tensor | None = None    # seeded thresholds of the tile-sharded job (valid until the next job)
 
     @property
     def kernel_launches(self) -> int:
@@ -240,6 +242,7 @@ class HybridTopKEngine:
         self._pinned.clear()
         self._fold_buf = None
         self._fold_owner = None
+        self._theta = None
         if torch.cuda.is_available():
             with torch.cuda.device(self.device):
                 torch.cuda.empty_cache()
@@ -251,16 +254,31 @@ class HybridTopKEngine:
         return self._ws
 
     # ------------------------------------------------------------------------------------ upload
-    def h2d(self, st: StagedCatalogue) -> dict:
-        """Host -> device copies of the staged buffers on the current stream (no kernels)."""
+    def h2d(self, st: StagedCatalogue, reuse: bool = False) -> dict:
+        """Host -> device copies of the staged buffers on the current stream (no kernels).
+        ``reuse``: copy into cached device buffers (two sets used in turn, so a stream of jobs allocates
+        nothing and the previous job's arrays -- which ``prepare(recycle=...)`` still reads to un-scatter
+        the operand -- stay intact); the tensors of the call before the previous one are overwritten."""
         dev = self.device
+        cache = None
+        if reuse:
+            gen = self._pinned.setdefault(("h2d_gen",), [0])
+            gen[0] ^= 1
+            cache = self._pinned.setdefault(("h2d", gen[0]), {})
+
+        def up(name: str, h: torch.Tensor) -> torch.Tensor:
+            if cache is None:
+                return h.to(dev, non_blocking=True)
+            d = cache.get(name)
+            if d is None or d.shape != h.shape or d.dtype != h.dtype:
+                d = cache[name] = torch.empty(h.shape, dtype=h.dtype, device=dev)
+            d.copy_(h, non_blocking=True)
+            return d
+
         with torch.cuda.device(dev):
-            return {"st": st,
-                    "indptr": st.text_indptr.to(dev, non_blocking=True),
-                    "indices": st.text_indices.to(dev, non_blocking=True),
-                    "values": st.text_values.to(dev, non_blocking=True),
-                    "genre": st.genre.to(dev, non_blocking=True),
-                    "meta": [m.to(dev, non_blocking=True) for m in st.meta]}
+            return {"st": st, "indptr": up("indptr", st.text_indptr), "indices": up("indices", st.text_indices),
+                    "values": up("values", st.text_values), "genre": up("genre", st.genre),
+                    "meta": [up(f"meta{i}", m) for i, m in enumerate(st.meta)]}
 
     def upload(self, st: StagedCatalogue, weights: tuple[float, float, float] = (0.4, 0.5, 0.1),
                recycle: DeviceCatalogue | None = None) -> DeviceCatalogue:
@@ -296,10 +314,21 @@ class HybridTopKEngine:
                 # a catalogue without any text: the C ABI wants non-NULL arrays, which are never read
                 indices = torch.zeros((1,), dtype=torch.int32, device=dev)
                 rawv = torch.zeros((1,), dtype=torch.float64, device=dev)
+            # a recycled catalogue hands over all its same-shaped buffers: a steady stream of jobs then
+            # allocates nothing (torch's caching allocator otherwise falls back to cudaMalloc -- a device
+            # synchronisation of tens of milliseconds -- whenever the lifetimes of a step's tensors shift)
+            spare = dict(recycle.buffers) if recycle is not None else {}
+
+            def take(name, shape, dtype):
+                t = spare.pop(name, None)
+                if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev:
+                    t = torch.empty(shape, dtype=dtype, device=dev)
+                return t
+
             values, operand = self._text_operand(indptr, indices, rawv, n, n_pad, k_pad, recycle,
-                                                 folded=folded_dims > 0)
-            col_side = torch.empty((n_pad, 2), dtype=torch.int64, device=dev)   # 16-byte records
-            meta_scale = torch.empty((n_pad,), dtype=torch.float32, device=dev)
+                                                 folded=folded_dims > 0, values=take("values", rawv.shape, rawv.dtype))
+            col_side = take("col_side", (n_pad, 2), torch.int64)   # 16-byte records
+            meta_scale = take("meta_scale", (n_pad,), torch.float32)
             self._zero(col_side)
             self._zero(meta_scale)
             keep += [indptr, indices, values, operand, col_side, meta_scale]
@@ -341,7 +370,7 @@ class HybridTopKEngine:
                 g8 = raw["genre"]
                 genre_hi = None
                 if g8.shape[1] > 64:      # second mask word for genre columns 64..127
-                    genre_hi = torch.empty((n_pad,), dtype=torch.int64, device=dev)
+                    genre_hi = take("genre_hi", (n_pad,), torch.int64)
                     self._zero(genre_hi)
                     keep.append(genre_hi)
                     f.genre_hi = genre_hi.data_ptr()
@@ -367,9 +396,14 @@ class HybridTopKEngine:
                     f.meta_dims[gi] = int(m.shape[1])
                     f.meta_dense[gi] = fold(m, per_group_w, "metadata")
             keep.append(raw)
+        bufs = {"values": values, "col_side": col_side, "meta_scale": meta_scale}
+        if f.genre_hi:
+            bufs["genre_hi"] = genre_hi
+        if recycle is not None:
+            recycle.buffers = {}
         return DeviceCatalogue(c=f, n_shows=n, folded=folded,
                                weights_baked=(gw, tw, mw) if folded else None, keep=keep,
-                               operand=operand, text_indptr=indptr, text_indices=indices)
+                               operand=operand, text_indptr=indptr, text_indices=indices, buffers=bufs)
 
     # ------------------------------------------------------------------------------------ device-side ingest
     _RAW_DTYPES = {np.dtype(np.bool_): 0, np.dtype(np.uint8): 0, np.dtype(np.int32): 1, np.dtype(np.int64): 2,
@@ -484,12 +518,13 @@ class HybridTopKEngine:
                                operand=operand, text_indptr=indptr, text_indices=indices)
 
     def _text_operand(self, indptr, indices, rawv, n: int, n_pad: int, k_pad: int,
-                      recycle: DeviceCatalogue | None, folded: bool = False):
+                      recycle: DeviceCatalogue | None, folded: bool = False, values: torch.Tensor | None = None):
         """fp64 row normalisation of the CSR values + the fp16 / bf16 tensor-core operand (fresh and
         zeroed, or ``recycle``'s with its old positions cleared)."""
         lib, dev, stream = self.lib, self.device, self._stream()
         code, tdt = _DTYPES[self.text_dtype]
-        values = torch.empty_like(rawv)
+        if values is None:
+            values = torch.empty_like(rawv)
         operand = None
         if (recycle is not None and recycle.operand is not None and not recycle.folded and not folded
                 and tuple(recycle.operand.shape) == (n_pad, k_pad) and recycle.operand.dtype == tdt
@@ -727,7 +762,9 @@ class HybridTopKEngine:
             if nbytes == 0:
                 check(-1, "tvbf_sym_workspace_bytes")
             ws = self._workspace(nbytes)
-            theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
+            theta = self._theta
+            if theta is None or theta.numel() != int(cat.c.n_pad):
+                theta = self._theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
             check(self.lib.tvbf_sym_seed(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
                                          ws.numel(), self._stream()), "tvbf_sym_seed")
         return theta

@@ -96,7 +96,8 @@ def _local_tables(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: f
 
 def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float,
                              exclude_self: bool = True, group=None, symmetric: bool | None = None,
-                             splits: int = 0, tuning: int = 0, events: dict | None = None) -> dict:
+                             splits: int = 0, tuning: int = 0, events: dict | None = None,
+                             tables: dict | None = None) -> dict:
     """One job over all ranks of ``group``; every rank returns the full gathered device table.
 
     * symmetric (default when eligible): tile sharding -- every rank sweeps the tiles on/above the
@@ -104,19 +105,32 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
       partial candidate lists go through ONE all-to-all over the row shards (N x 33 x 8 B sent per
       rank) and each rank rescores its row shard.  Halves the tensor-core work.
     * one-sided: row sharding, no exchange before the final gather.
+
+    ``tables``: the padded gather buffers of an earlier call of the same shape (``out["_full"]``) to
+    write into instead of allocating 72 MB per job; the earlier result is overwritten.
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = cat.n_shows
+    dbg = os.environ.get("TVBF_HOST_TIMES") and rank == 0
+    import time as _time
     with torch.cuda.device(eng.device):
-        full = alloc_full_tables(n, k, world, eng.device)
+        t0 = _time.perf_counter()
+        full = tables if tables is not None and tuple(tables["indices"].shape) == (world * shard_rows(n, world), k) \
+            else alloc_full_tables(n, k, world, eng.device)
         mine = shard_views(full, n, world, rank)
+        t1 = _time.perf_counter()
         _local_tables(eng, cat, weights, k, min_similarity, exclude_self, group, symmetric, splits, tuning, events, mine)
+        t2 = _time.perf_counter()
         out = gather_full_tables(full, n, group)
+        if dbg:
+            print(f"host: alloc {1e3 * (t1 - t0):.2f} local {1e3 * (t2 - t1):.2f} gather {1e3 * (_time.perf_counter() - t2):.2f} ms",
+                  flush=True)
         if events is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             events.setdefault("gather1", []).append(ev)
     out["row_begin"] = 0
+    out["_full"] = full
     return out
 
 
@@ -130,6 +144,7 @@ class DistributedTopK:
         self.upload = ShardedUpload(group)
         self.table = SharedHostTable(n_shows, k, group)
         self._prev = None
+        self._full = None          # padded device tables, reused from job to job
 
     def h2d(self, st: StagedCatalogue) -> dict:
         """1/world of every feature buffer over this rank's PCIe link + one all-gather over NVLink."""
@@ -146,7 +161,9 @@ class DistributedTopK:
         with torch.cuda.device(eng.device):
             cat = eng.prepare(self.h2d(st), weights, recycle=self._prev)
             self._prev = cat
-            full = alloc_full_tables(n, k, self.world, eng.device)
+            if self._full is None:
+                self._full = alloc_full_tables(n, k, self.world, eng.device)
+            full = self._full
             mine = shard_views(full, n, self.world, self.rank)
             _local_tables(eng, cat, weights, k, min_similarity, exclude_self, self.group, symmetric, splits, tuning,
                           None, mine)

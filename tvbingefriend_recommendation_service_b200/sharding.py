@@ -196,7 +196,8 @@ def gather_tables(local: dict, n_shows: int, k: int, group=None) -> dict:
 
 
 def tables_to_numpy(t: dict) -> dict:
-    return {n: (v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for n, v in t.items()}
+    return {n: (v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for n, v in t.items()
+            if not n.startswith("_")}
 
 
 # ---- features: each rank uploads a slice, NVLink replicates -------------------------------------------
@@ -210,14 +211,22 @@ class ShardedUpload:
     def __init__(self, group=None):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._cache: dict = {}     # device buffers of earlier calls (two sets used in turn), reused when the sizes repeat
+        self._gen = 0
 
     def __call__(self, host_tensors: list[torch.Tensor], device) -> list[torch.Tensor]:
+        """The returned tensors alias buffers that the call AFTER the next one overwrites (two sets are
+        used in turn: the previous job's CSR arrays are still read when its operand is recycled)."""
         world, rank = self.world, self.rank
         bufs, outs = [], []
-        for h in host_tensors:
+        self._gen ^= 1
+        for j, h in enumerate(host_tensors):
+            i = (self._gen, j)
             nbytes = h.numel() * h.element_size()
             chunk = (nbytes + world * self.ALIGN - 1) // (world * self.ALIGN) * self.ALIGN
-            dev = torch.empty((world * chunk,), dtype=torch.uint8, device=device)
+            dev = self._cache.get(i)
+            if dev is None or dev.numel() != world * chunk or dev.device != torch.device(device):
+                dev = self._cache[i] = torch.empty((world * chunk,), dtype=torch.uint8, device=device)
             src = h.view(-1).view(torch.uint8)
             b, e = min(rank * chunk, nbytes), min((rank + 1) * chunk, nbytes)
             if e > b:
