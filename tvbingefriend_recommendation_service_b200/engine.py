@@ -751,7 +751,7 @@ class HybridTopKEngine:
             return bool(self.lib.tvbf_sym_eligible(C.byref(cat.c), C.byref(p)))
 
     def sym_seed(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
-                 splits: int = 0, tuning: int = 0) -> torch.Tensor:
+                 splits: int = 0, tuning: int = 0, reuse_theta: bool = False) -> torch.Tensor:
         """Phase 1 of the tile-sharded symmetric job: thresholds of this rank's shows seeded from a
         sampled sweep; returns theta int32[n_pad] (raw bits of positive floats), to be MAX-reduced
         over the ranks."""
@@ -762,9 +762,11 @@ class HybridTopKEngine:
             if nbytes == 0:
                 check(-1, "tvbf_sym_workspace_bytes")
             ws = self._workspace(nbytes)
-            theta = self._theta
+            theta = self._theta if reuse_theta else None     # reuse: valid until this engine's next seeded job
             if theta is None or theta.numel() != int(cat.c.n_pad):
-                theta = self._theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
+                theta = torch.empty((int(cat.c.n_pad),), dtype=torch.int32, device=self.device)
+                if reuse_theta:
+                    self._theta = theta
             check(self.lib.tvbf_sym_seed(C.byref(feats), C.byref(p), rank, world, theta.data_ptr(), ws.data_ptr(),
                                          ws.numel(), self._stream()), "tvbf_sym_seed")
         return theta
@@ -854,7 +856,7 @@ class HybridTopKEngine:
         b, e = row_range
         padded_rows = padded_rows or cat.n_shows
         mark("seed0")
-        theta = self.sym_seed(cat, weights, k, min_similarity, rank, world, splits, tuning)
+        theta = self.sym_seed(cat, weights, k, min_similarity, rank, world, splits, tuning, reuse_theta=True)
         mark("seed1")
         all_reduce_max(theta)            # raw bits of positive floats order like integers
         mark("reduce1")
