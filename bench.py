@@ -334,11 +334,12 @@ def weight_sweep(eng, config: str = "C3", reps: int = 3) -> dict:
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out = eng.top_k_sweep_device(dc, WEIGHT_SWEEP, k, 0.1, shared=True)
+        out = eng.top_k_sweep_device(dc, WEIGHT_SWEEP, k, 0.1, shared=True, out=out)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     res = {"config": config, "triples": [list(w) for w in WEIGHT_SWEEP], "k": k, "ms_all_triples": float(np.mean(ts[1:])),
+           "ms_all_triples_per_rep": [round(t, 2) for t in ts[1:]],
            "ms_per_triple": float(np.mean(ts[1:])) / len(WEIGHT_SWEEP),
            "flagged_rows": [int(t["stats"][0]) for t in out]}
     del dc, out, cat

@@ -492,3 +492,32 @@ def test_folded_operand_follows_the_weights_and_the_catalogue(engine):
         assert ca.fold is not None and cb.fold is not None
         assert_topk_matches(ta, a.features(), rows, weights=w)
         assert_topk_matches(tb, b.features(), rows, weights=w)
+
+
+# ---- the threshold seed pass (per-row score histograms) ------------------------------------------------------
+@pytest.mark.parametrize("vocab", [400, 3000], ids=["folded_wide", "popcount"])
+def test_seeded_thresholds_are_lower_bounds_of_the_final_ones(engine, vocab):
+    """A seeded threshold must not exceed the K'-th best UPPER BOUND of the show over all columns (then
+    nothing that belongs in the candidate list is ever dropped).  Checked against the exact scores: the
+    K'-th best exact hybrid, inflated by the slack of the bound, is at least the seed; and the seed is
+    useful (above min_similarity for almost every show)."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.engine import stage
+    from tvbingefriend_recommendation_service_b200.synthetic import make_catalogue
+
+    n, w, k, ms = 9000, (0.4, 0.5, 0.1), 20, 0.1
+    cat = make_catalogue(n, vocab, nnz=15, seed=61)
+    f = cat.features()
+    dc = engine.upload(stage(f), w)
+    theta = engine.sym_seed(dc, w, k, ms, 0, 1)
+    torch.cuda.synchronize()
+    th = theta.view(torch.float32)[:n].cpu().numpy().astype(np.float64)
+    assert np.isfinite(th).all() and (th > ms * 0.99).mean() > 0.9
+    kp = 32                                   # candidates kept for k = 20
+    pr = ProductionRows(f, *w)
+    rows = np.arange(0, n, 150)
+    h = pr.rows_block(rows)[0]
+    h[np.arange(len(rows)), rows] = -1.0      # a show is not its own candidate
+    kth = -np.sort(-h, axis=1)[:, kp - 1]
+    assert np.all(th[rows] <= kth * (1 + 3e-3) + 1e-4), float((th[rows] - kth).max())

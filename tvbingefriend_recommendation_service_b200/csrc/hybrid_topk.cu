@@ -1118,6 +1118,7 @@ __device__ __forceinline__ void compact_list(uint2* list, int n_all, int kp, uin
     const int fresh = n_all - done < W - kept ? n_all - done : W - kept;
     const int n = kept + fresh;
     uint32_t v[Q], cidx[Q];
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const int idx = q * 32 + lane;
@@ -1125,14 +1126,21 @@ __device__ __forceinline__ void compact_list(uint2* list, int n_all, int kp, uin
       if (idx < n) e = __ldcg(list + (idx < kept ? idx : done + (idx - kept)));
       v[q] = idx < n ? e.x : 0u;
       cidx[q] = e.y;
+      if (idx < n) { lo = min(lo, v[q]); hi = max(hi, v[q]); }
     }
     done += fresh;
     const bool last = done >= n_all;
     uint2* out_p = last ? dst : list;
     best = 0u;
     if (n > kp) {
+      // exact radix select below the bits all n entries share (scores of one list lie within a
+      // factor of two: sign, exponent and the leading mantissa bits are skipped)
+      lo = __reduce_min_sync(kFullMask, lo);
+      hi = __reduce_max_sync(kFullMask, hi);
+      const int top = 31 - __clz(lo ^ hi);     // -1: all entries equal
+      best = top >= 0 ? (hi >> (top + 1)) << (top + 1) : hi;   // positive floats: top <= 30
 #pragma unroll 1
-      for (int bit = 30; bit >= 0; --bit) {
+      for (int bit = top; bit >= 0; --bit) {
         const uint32_t t = best | (1u << bit);
         int c = 0;
 #pragma unroll
@@ -1186,6 +1194,7 @@ sym_compact_kernel(const K1Params p, int n_rows) {
   uint32_t best = 0u;
   int kept = 0;
   if (n_all <= 256) compact_list<8>(list, n_all, kp, dst, lane, &best, &kept);     // warp-uniform
+  else if (n_all <= 512) compact_list<16>(list, n_all, kp, dst, lane, &best, &kept);
   else compact_list<32>(list, n_all, kp, dst, lane, &best, &kept);
   if (lane == 0) {
     const unsigned int th_bits = p.g_theta[r];

@@ -643,14 +643,16 @@ class HybridTopKEngine:
         return t
 
     def top_k_sweep_device(self, cat: DeviceCatalogue, weight_list, k: int = 20, min_similarity: float = 0.1,
-                           exclude_self: bool = True, shared: bool | None = None, tuning: int = 0, **kw) -> list[dict]:
+                           exclude_self: bool = True, shared: bool | None = None, tuning: int = 0,
+                           out: list | None = None, **kw) -> list[dict]:
         """Weight sweep (BASELINE config C5; notebooks/03 cell 6 of the reference): one table per
         weight triple over ONE device-resident catalogue.  H2D, normalisation, the fp16 operand and
         the packed genre / metadata words never depend on the weights.  ``shared`` (default: when
         every triple is eligible for the symmetric sweep and the catalogue has >= 40 000 shows)
         also shares the tensor-core sweep between up to 5 triples per launch
         (``tvbf_hybrid_topk_sweep``: one candidate list per (triple, show)); otherwise the candidate
-        sweep runs once per triple.  Either way the tables equal those of separate jobs."""
+        sweep runs once per triple.  Either way the tables equal those of separate jobs.
+        ``out``: the list an earlier call of the same shape returned, to be overwritten (no allocation)."""
         if cat.folded:
             raise _lib.TvbfError("a catalogue with folded (non-binary) groups bakes the weights into the "
                                  "operand; use compute_top_k_sweep, which uploads once per triple")
@@ -661,7 +663,7 @@ class HybridTopKEngine:
                       and all(self.sym_eligible(cat, w, k, min_similarity) for w in triples))
         if not shared:
             return [self.top_k_device(cat, w, k, min_similarity, exclude_self, tuning=tuning, **kw) for w in triples]
-        k, rows, dev, out = int(k), cat.n_shows, self.device, []
+        k, rows, dev, spare, out = int(k), cat.n_shows, self.device, list(out or []), []
         with torch.cuda.device(dev):
             for g0 in range(0, len(triples), 5):
                 part = triples[g0:g0 + 5]
@@ -676,7 +678,8 @@ class HybridTopKEngine:
                 if nbytes == 0:
                     check(-1, "tvbf_topk_sweep_workspace_bytes")
                 ws = self._workspace(nbytes)
-                tabs = [self._alloc_tables(rows, k, 0) for _ in range(n)]
+                tabs = [spare.pop(0) if spare and tuple(spare[0]["indices"].shape) == (rows, k)
+                        else self._alloc_tables(rows, k, 0) for _ in range(n)]
                 couts = (TopKOut * n)()
                 for w, t in enumerate(tabs):
                     couts[w] = self._c_tables(t)
