@@ -1091,12 +1091,12 @@ class HybridTopKEngine:
                    tile_sharded: bool = False, row_begin: int = 0, row_end: int | None = None, splits: int = 0,
                    tuning: int = 0) -> dict:
         """Tensor-core tiles the candidate pass of this job executes (``tvbf_plan_tiles``, host only).
-        A single-GPU job that ``top_k_device`` runs over the folded operand is planned over it (k_pad)."""
+        A job that runs over the folded operand is planned over it (k_pad)."""
         p = self._params(cat, weights, k, min_similarity, row_begin=row_begin, row_end=row_end, splits=splits,
                          tuning=tuning)
         out = (C.c_int64 * 4)()
         feats = cat.c
-        if world == 1 and cat.fold is not None and cat.fold["weights"] == tuple(float(w) for w in weights) \
+        if cat.fold is not None and cat.fold["weights"] == tuple(float(w) for w in weights) \
                 and self._fold_owner is cat.fold:
             feats = cat.fold["c"]
         with torch.cuda.device(self.device):
