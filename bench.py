@@ -434,9 +434,10 @@ def bench_config(args, cfg) -> dict:
                         f"(~{cfg['nnz']} nnz/row), {cfg['n_genres']} genres, metadata one-hot {cfg['meta']}, "
                         f"hybrid weights 0.4/0.5/0.1, top-{cfg['k']}, min_similarity 0.1",
             "n_shows": cfg["n_shows"], "vocab": cfg["vocab"], "k": cfg["k"],
-            "parallelism": f"features replicated; x{args.gpus}: tile-sharded symmetric sweep, candidate lists "
-                           f"exchanged by one all-to-all over the row shards (or row-sharded one-sided "
-                           f"with --one-sided)",
+            "parallelism": f"features replicated; x{args.gpus}: tile-sharded symmetric sweep, finished candidate "
+                           f"rows stored into the owner GPU's buffer over NVLink (one all-to-all without "
+                           f"symmetric memory), one coalesced all-gather of the tables (or row-sharded "
+                           f"one-sided with --one-sided)",
             "l2_policy": "inputs larger than L2 (fp16 operand %.1f GB, streamed every step)"
                          % (cfg["n_shows"] * cfg["vocab"] * 2 / 1e9)}
 

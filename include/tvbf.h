@@ -162,6 +162,15 @@ int tvbf_prep_csr_to_operand(const int64_t* indptr, const int32_t* indices, cons
 int tvbf_prep_clear_csr_positions(const int64_t* indptr, const int32_t* indices, int32_t n_rows,
                                   void* operand, int32_t k_pad, int32_t col_offset, int32_t dtype,
                                   void* stream);
+/* Several GPUs: replicate this GPU's slices of a set of identically laid out buffers into every
+ * peer's copy with plain stores over NVLink (peer mappings, e.g. torch symmetric memory):
+ * for every field f and every peer p != rank,
+ *   peer_base[p] + offsets[f] .. + bytes[f]  <-  peer_base[rank] + offsets[f] .. + bytes[f].
+ * Replaces the all-gather of the [N, k] result tables (each rank has just written its row shard of
+ * every field); the caller follows it with a device-side barrier.  n_fields <= 8, world <= 16,
+ * offsets and sizes multiples of 4 bytes. */
+int tvbf_peer_push(const uint64_t* peer_base, int32_t world, int32_t rank, const uint64_t* offsets,
+                   const uint64_t* bytes, int32_t n_fields, void* stream);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (fresh operand / column-side buffers). */
 int tvbf_device_zero(void* ptr, size_t bytes, void* stream);
 /* out[r, :] = in[r, :] / ||in[r, :]||_2 (fp64, zero rows stay zero). */

@@ -75,6 +75,7 @@ SIGNATURES = {
     "tvbf_prep_clear_csr_positions": (C.c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32,
                                                 c_void_p]),
     "tvbf_device_zero": (C.c_int, [c_void_p, c_size_t, c_void_p]),
+    "tvbf_peer_push": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "tvbf_prep_dense_normalize": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "tvbf_prep_dense_to_operand": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32,
                                              c_double, c_int32, c_void_p]),

@@ -163,6 +163,31 @@ __global__ void fold_bits_kernel(const TvbfColSide* __restrict__ col_side,
   operand[static_cast<size_t>(row) * k_pad + col0 + c] = cvt_operand<T>(v);
 }
 
+// tvbf_peer_push: blockIdx.y picks the peer, the blocks of a peer stride over 16-byte words (4-byte
+// words for a field whose slice is not 16-byte aligned) of every field in turn.
+struct PeerPush {
+  unsigned long long base[16];
+  unsigned long long off[8], bytes[8];
+  int world, rank, n_fields;
+};
+__global__ void peer_push_kernel(const PeerPush a) {
+  int p = static_cast<int>(blockIdx.y);
+  if (p >= a.rank) ++p;   // every peer but this GPU itself
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (int f = 0; f < a.n_fields; ++f) {
+    const unsigned long long src = a.base[a.rank] + a.off[f], dst = a.base[p] + a.off[f];
+    if (((src | dst | a.bytes[f]) & 15ull) == 0ull) {
+      const uint4* s = reinterpret_cast<const uint4*>(src);
+      uint4* d = reinterpret_cast<uint4*>(dst);
+      for (size_t i = tid; i < a.bytes[f] / 16; i += stride) d[i] = s[i];
+    } else {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+      uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+      for (size_t i = tid; i < a.bytes[f] / 4; i += stride) d[i] = s[i];
+    }
+  }
+}
+
 // ---- device-side ingest of the raw feature arrays (any of the dtypes numpy hands over) --------------
 // dtype codes of the raw arrays: 0 uint8 / bool, 1 int32, 2 int64, 3 float32, 4 float64
 __device__ __forceinline__ double load_raw(const void* p, int dtype, size_t i) {
@@ -347,6 +372,36 @@ int tvbf_prep_clear_csr_positions(const int64_t* indptr, const int32_t* indices,
     csr_clear_operand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
         indptr, indices, n_rows, static_cast<__nv_bfloat16*>(operand), k_pad, col_offset);
   TVBF_LAUNCH_OK("csr_clear_operand_kernel");
+  return TVBF_OK;
+}
+
+int tvbf_peer_push(const uint64_t* peer_base, int32_t world, int32_t rank, const uint64_t* offsets,
+                   const uint64_t* bytes, int32_t n_fields, void* stream) {
+  TVBF_REQUIRE(peer_base && offsets && bytes && world >= 1 && world <= 16 && rank >= 0 && rank < world &&
+                   n_fields >= 1 && n_fields <= 8,
+               "tvbf_peer_push: bad arguments");
+  if (world == 1) return TVBF_OK;
+  PeerPush a;
+  size_t most = 0;
+  for (int p = 0; p < world; ++p) {
+    TVBF_REQUIRE(peer_base[p] != 0 && (peer_base[p] & 15) == 0, "tvbf_peer_push: peer %d has no 16-byte aligned mapping", p);
+    a.base[p] = peer_base[p];
+  }
+  for (int f = 0; f < n_fields; ++f) {
+    TVBF_REQUIRE((offsets[f] & 3) == 0 && (bytes[f] & 3) == 0, "tvbf_peer_push: field %d is not 4-byte aligned", f);
+    a.off[f] = offsets[f];
+    a.bytes[f] = bytes[f];
+    most = bytes[f] > most ? bytes[f] : most;
+  }
+  a.world = world;
+  a.rank = rank;
+  a.n_fields = n_fields;
+  if (most == 0) return TVBF_OK;
+  // enough blocks per peer to keep the NVLink stores of all peers in flight (16 B per thread and step)
+  unsigned bx = static_cast<unsigned>((most / 16 + 255) / 256);
+  bx = bx < 1 ? 1 : (bx > 64 ? 64 : bx);
+  peer_push_kernel<<<dim3(bx, static_cast<unsigned>(world - 1)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  TVBF_LAUNCH_OK("peer_push_kernel");
   return TVBF_OK;
 }
 

@@ -22,8 +22,11 @@ import torch
 import torch.distributed as dist
 
 from .engine import HybridTopKEngine, StagedCatalogue, TopK, stage
-from .sharding import (PeerCandidateBuffers, ShardedUpload, SharedHostTable, alloc_full_tables, exchange_packed,
-                       gather_full_tables, row_shard, shard_rows, shard_views)
+import time
+
+from ._lib import check
+from .sharding import (PeerCandidateBuffers, PeerTables, ShardedUpload, SharedHostTable, alloc_full_tables,
+                       exchange_packed, gather_full_tables, row_shard, shard_rows, shard_views)
 
 _peer_cache: dict = {}
 
@@ -52,6 +55,31 @@ def peer_buffers(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: fl
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         _peer_cache[key] = bufs if int(ok.item()) == 1 else None
     return _peer_cache[key]
+
+
+_peer_table_cache: dict = {}
+
+
+def peer_tables(eng: HybridTopKEngine, n_shows: int, k: int, group=None):
+    """Result tables in symmetric memory for this job shape (created collectively on first use, then
+    cached), or None when torch symmetric memory is unavailable or TVBF_PEER_GATHER=0 -- the driver
+    then gathers with one coalesced NCCL all-gather.  Every rank takes the same decision."""
+    if os.environ.get("TVBF_PEER_GATHER", "1") == "0":
+        return None
+    world = dist.get_world_size(group)
+    key = (eng.device.index, n_shows, k, world, id(group))
+    if key not in _peer_table_cache:
+        ok = torch.ones((1,), dtype=torch.int32, device=eng.device)
+        tabs = None
+        try:
+            with torch.cuda.device(eng.device):
+                tabs = PeerTables(n_shows, k, eng.device, group)
+        except Exception as exc:      # no symmetric memory on this system / build
+            ok.zero_()
+            print(f"tvbf: peer gather unavailable ({type(exc).__name__}: {exc}); using all_gather", flush=True)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        _peer_table_cache[key] = tabs if int(ok.item()) == 1 else None
+    return _peer_table_cache[key]
 
 
 def _local_tables(eng: HybridTopKEngine, cat, weights, k: int, min_similarity: float, exclude_self: bool, group,
@@ -106,24 +134,37 @@ def top_k_device_distributed(eng: HybridTopKEngine, cat, weights, k: int, min_si
       rank) and each rank rescores its row shard.  Halves the tensor-core work.
     * one-sided: row sharding, no exchange before the final gather.
 
-    ``tables``: the padded gather buffers of an earlier call of the same shape (``out["_full"]``) to
-    write into instead of allocating 72 MB per job; the earlier result is overwritten.
+    The tables live in torch symmetric memory and are replicated by ``tvbf_peer_push`` (NVLink stores
+    + a device-side barrier; two sets used in turn, so a result stays valid until the job after the
+    next one).  Without symmetric memory (or ``TVBF_PEER_GATHER=0``): one coalesced NCCL all-gather;
+    ``tables`` then names the padded gather buffers of an earlier call (``out["_full"]``) to reuse.
     """
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = cat.n_shows
     dbg = os.environ.get("TVBF_HOST_TIMES") and rank == 0
-    import time as _time
     with torch.cuda.device(eng.device):
-        t0 = _time.perf_counter()
-        full = tables if tables is not None and tuple(tables["indices"].shape) == (world * shard_rows(n, world), k) \
-            else alloc_full_tables(n, k, world, eng.device)
+        t0 = time.perf_counter()
+        ptab = peer_tables(eng, n, k, group)
+        if ptab is not None:
+            full, ptrs, barrier = ptab.next()
+        else:
+            full = tables if tables is not None and tuple(tables["indices"].shape) == (world * shard_rows(n, world), k) \
+                else alloc_full_tables(n, k, world, eng.device)
         mine = shard_views(full, n, world, rank)
-        t1 = _time.perf_counter()
+        t1 = time.perf_counter()
         _local_tables(eng, cat, weights, k, min_similarity, exclude_self, group, symmetric, splits, tuning, events, mine)
-        t2 = _time.perf_counter()
-        out = gather_full_tables(full, n, group)
+        t2 = time.perf_counter()
+        if ptab is not None:
+            # this rank's shard of every field -> the seven other copies over NVLink, then a device-side barrier
+            check(eng.lib.tvbf_peer_push(ptrs, world, rank, ptab.offsets, ptab.sizes, ptab.n_fields, eng._stream()),
+                  "tvbf_peer_push")
+            barrier()
+            out = {name: full[name][:n] for name in ("indices", "counts", "hybrid", "genre", "text", "metadata")}
+            out["stats"] = full["stats"]
+        else:
+            out = gather_full_tables(full, n, group)
         if dbg:
-            print(f"host: alloc {1e3 * (t1 - t0):.2f} local {1e3 * (t2 - t1):.2f} gather {1e3 * (_time.perf_counter() - t2):.2f} ms",
+            print(f"host: alloc {1e3 * (t1 - t0):.2f} local {1e3 * (t2 - t1):.2f} gather {1e3 * (time.perf_counter() - t2):.2f} ms",
                   flush=True)
         if events is not None:
             ev = torch.cuda.Event(enable_timing=True)

@@ -131,6 +131,56 @@ class PeerCandidateBuffers:
         return self.ptrs[i], buf.view(self.world, self.rows, buf.shape[1], 2), (lambda: h.barrier(channel=i))
 
 
+class PeerTables:
+    """The ``[world * shard_rows, k]`` result tables of ``alloc_full_tables`` in torch symmetric memory
+    (one allocation, the fields back to back), so that every rank holds a device mapping of every
+    peer's copy.  After the kernels have written a rank's row shard into ITS copy, ``tvbf_peer_push``
+    stores that shard into the seven other copies over NVLink and ``barrier()`` (device-side, on the
+    current stream) makes all shards visible everywhere: the all-gather without NCCL's ring.  Two sets
+    are used in turn -- a fast rank may already be pushing the next job's rows."""
+
+    def __init__(self, n_shows: int, k: int, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_shows, self.k = n_shows, k
+        rows = shard_rows(n_shows, self.world)
+        total = self.world * rows
+        specs = [("indices", torch.int32, (total, k), rows * k * 4), ("counts", torch.int32, (total,), rows * 4)]
+        specs += [(name, torch.float64, (total, k), rows * k * 8) for name in ("hybrid", "genre", "text", "metadata")]
+        specs += [("stats", torch.int32, (self.world, 8), 32)]
+        off, layout = 0, []
+        for name, dt, shape, shard_bytes in specs:
+            nbytes = shard_bytes * self.world
+            layout.append((name, dt, shape, off, nbytes, shard_bytes))
+            off = (off + nbytes + 255) // 256 * 256
+        self.nbytes = off
+        grp = group if group is not None else dist.group.WORLD
+        self.sets = []
+        for _ in range(2):
+            t = symm_mem.empty((self.nbytes,), dtype=torch.uint8, device=device)
+            h = symm_mem.rendezvous(t, grp)
+            ptrs = [int(x) for x in h.buffer_ptrs]
+            if len(ptrs) != self.world or any(x == 0 for x in ptrs):
+                raise RuntimeError("symmetric memory rendezvous returned no peer mappings")
+            views = {name: t[o:o + nb].view(dt).view(shape) for name, dt, shape, o, nb, _sb in layout}
+            self.sets.append((t, h, (C.c_uint64 * self.world)(*ptrs), views))
+        # this rank's slice of every field: what it pushes to the peers
+        self.n_fields = len(layout)
+        self.offsets = (C.c_uint64 * self.n_fields)(*[o + self.rank * sb for _n, _d, _s, o, _nb, sb in layout])
+        self.sizes = (C.c_uint64 * self.n_fields)(*[sb for *_x, sb in layout])
+        self.turn = 0
+
+    def next(self):
+        """(tables dict like ``alloc_full_tables``, peer pointer array, barrier callable) of the next job."""
+        i = self.turn & 1
+        self.turn += 1
+        _t, h, ptrs, views = self.sets[i]
+        return views, ptrs, (lambda: h.barrier(channel=i))
+
+
 def empty_tables(k: int, device) -> dict:
     """Local tables of a rank that owns no rows."""
     t = {"indices": torch.empty((0, k), dtype=torch.int32, device=device),
