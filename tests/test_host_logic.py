@@ -221,3 +221,54 @@ def test_one_sided_schedule_covers_every_tile_of_the_row_shard_once(tiles, block
         if sb >= 0:
             seen[sb, r0:r1] += 1
     assert (seen == 1).all()
+
+
+def test_peer_table_layout_tiles_the_buffer():
+    """The symmetric-memory result tables (``sharding.PeerTables``): every rank's slice of every field is
+    a contiguous, 4-byte aligned range; the slices of all ranks tile the field; fields do not overlap;
+    views of the buffer have exactly the shapes of ``alloc_full_tables``."""
+    import torch
+
+    from tvbingefriend_recommendation_service_b200.sharding import alloc_full_tables, peer_table_layout, shard_rows
+
+    for n, k, world in ((100_000, 20, 8), (6000, 100, 3), (130, 7, 2), (1, 1, 1)):
+        layout, total = peer_table_layout(n, k, world)
+        ref = alloc_full_tables(n, k, world, "cpu")
+        buf = torch.zeros((total,), dtype=torch.uint8)
+        end = 0
+        for name, dt, shape, off, nbytes, shard_bytes in layout:
+            assert off % 256 == 0 and off >= end and shard_bytes % 4 == 0 and shard_bytes * world == nbytes
+            end = off + nbytes
+            view = buf[off:off + nbytes].view(dt).view(shape)
+            assert tuple(view.shape) == tuple(ref[name].shape) and view.dtype == ref[name].dtype
+            rows = shard_rows(n, world) if name != "stats" else 1
+            for r in range(world):      # rank r's slice == rows [r * rows, (r + 1) * rows) of the field
+                view[r * rows:(r + 1) * rows] = r + 1
+                raw = buf[off + r * shard_bytes: off + (r + 1) * shard_bytes].view(dt)
+                assert bool((raw == r + 1).all())
+        assert end <= total
+
+
+def test_new_entry_points_validate_their_arguments_without_a_gpu():
+    """tvbf_peer_push / tvbf_prep_fold_bits reject bad arguments before any CUDA call."""
+    import ctypes as C
+
+    from tvbingefriend_recommendation_service_b200 import _lib
+
+    lib = _lib.load()
+    ptrs = (C.c_uint64 * 2)(256, 512)
+    off = (C.c_uint64 * 1)(0)
+    nb = (C.c_uint64 * 1)(64)
+    assert lib.tvbf_peer_push(ptrs, 0, 0, off, nb, 1, None) != 0            # world out of range
+    assert lib.tvbf_peer_push(ptrs, 2, 2, off, nb, 1, None) != 0            # rank out of range
+    assert lib.tvbf_peer_push(ptrs, 2, 0, off, nb, 9, None) != 0            # too many fields
+    assert lib.tvbf_peer_push(None, 2, 0, off, nb, 1, None) != 0
+    assert lib.tvbf_peer_push((C.c_uint64 * 2)(256, 0), 2, 0, off, nb, 1, None) != 0     # a peer without a mapping
+    assert lib.tvbf_peer_push(ptrs, 2, 0, (C.c_uint64 * 1)(2), nb, 1, None) != 0         # unaligned field
+    assert b"tvbf_peer_push" in lib.tvbf_last_error()
+    assert lib.tvbf_peer_push(ptrs, 1, 0, off, nb, 1, None) == 0            # one GPU: nothing to push
+    assert lib.tvbf_prep_fold_bits(None, None, None, 10, 40, None, 576, 500, 1.0, 1.0, 0, None) != 0
+    assert lib.tvbf_prep_fold_bits(1, None, 1, 10, 200, 1, 576, 500, 1.0, 1.0, 0, None) != 0   # more than 128 genre columns
+    assert lib.tvbf_prep_fold_bits(1, None, 1, 10, 40, 1, 512, 500, 1.0, 1.0, 0, None) != 0    # columns do not fit k_pad
+    assert lib.tvbf_prep_fold_bits(1, None, 1, 10, 100, 1, 704, 500, 1.0, 1.0, 0, None) != 0   # G > 64 without genre_hi
+    assert b"tvbf_prep_fold_bits" in lib.tvbf_last_error()

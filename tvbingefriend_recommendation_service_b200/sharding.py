@@ -131,6 +131,24 @@ class PeerCandidateBuffers:
         return self.ptrs[i], buf.view(self.world, self.rows, buf.shape[1], 2), (lambda: h.barrier(channel=i))
 
 
+def peer_table_layout(n_shows: int, k: int, world: int) -> tuple[list, int]:
+    """Byte layout of the result tables inside ONE buffer: ``[(name, dtype, shape, offset, nbytes,
+    shard_bytes)]`` and the total size.  Every field is padded to ``world * shard_rows`` rows, so rank
+    r's rows of a field are the ``shard_bytes`` at ``offset + r * shard_bytes``; offsets are multiples
+    of 256."""
+    rows = shard_rows(n_shows, world)
+    total = world * rows
+    specs = [("indices", torch.int32, (total, k), rows * k * 4), ("counts", torch.int32, (total,), rows * 4)]
+    specs += [(name, torch.float64, (total, k), rows * k * 8) for name in ("hybrid", "genre", "text", "metadata")]
+    specs += [("stats", torch.int32, (world, 8), 32)]
+    off, layout = 0, []
+    for name, dt, shape, shard_bytes in specs:
+        nbytes = shard_bytes * world
+        layout.append((name, dt, shape, off, nbytes, shard_bytes))
+        off = (off + nbytes + 255) // 256 * 256
+    return layout, off
+
+
 class PeerTables:
     """The ``[world * shard_rows, k]`` result tables of ``alloc_full_tables`` in torch symmetric memory
     (one allocation, the fields back to back), so that every rank holds a device mapping of every
@@ -146,17 +164,7 @@ class PeerTables:
 
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_shows, self.k = n_shows, k
-        rows = shard_rows(n_shows, self.world)
-        total = self.world * rows
-        specs = [("indices", torch.int32, (total, k), rows * k * 4), ("counts", torch.int32, (total,), rows * 4)]
-        specs += [(name, torch.float64, (total, k), rows * k * 8) for name in ("hybrid", "genre", "text", "metadata")]
-        specs += [("stats", torch.int32, (self.world, 8), 32)]
-        off, layout = 0, []
-        for name, dt, shape, shard_bytes in specs:
-            nbytes = shard_bytes * self.world
-            layout.append((name, dt, shape, off, nbytes, shard_bytes))
-            off = (off + nbytes + 255) // 256 * 256
-        self.nbytes = off
+        layout, self.nbytes = peer_table_layout(n_shows, k, self.world)
         grp = group if group is not None else dist.group.WORLD
         self.sets = []
         for _ in range(2):
