@@ -10,11 +10,17 @@ from helpers import assert_topk_matches
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["popcount", "folded"])
+def engine(request):
+    """Every test of this module runs twice: with the popcount epilogue (what large vocabularies get)
+    and with the packed groups folded into the operand (what these small test vocabularies get by
+    default: ``HybridTopKEngine.fold_max_k``)."""
     from tvbingefriend_recommendation_service_b200.engine import HybridTopKEngine
 
-    return HybridTopKEngine(0)
+    eng = HybridTopKEngine(0)
+    if request.param == "popcount":
+        eng.fold_max_k = 0
+    return eng
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])

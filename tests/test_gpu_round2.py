@@ -495,7 +495,7 @@ def test_folded_operand_follows_the_weights_and_the_catalogue(engine):
 
 
 # ---- the threshold seed pass (per-row score histograms) ------------------------------------------------------
-@pytest.mark.parametrize("vocab", [400, 3000], ids=["folded_wide", "popcount"])
+@pytest.mark.parametrize("vocab", [400, 6000], ids=["folded_wide", "popcount"])
 def test_seeded_thresholds_are_lower_bounds_of_the_final_ones(engine, vocab):
     """A seeded threshold must not exceed the K'-th best UPPER BOUND of the show over all columns (then
     nothing that belongs in the candidate list is ever dropped).  Checked against the exact scores: the

@@ -219,8 +219,11 @@ class HybridTopKEngine:
         # Small vocabularies: the candidate pass is bound by its epilogue, not by the MMAs, so the
         # packed genre / metadata groups are ALSO written into a second operand as K columns and the
         # epilogue drops its popcounts (tvbf_features.bits_folded).  Used while the widened operand
-        # has at most fold_max_k columns (0 disables; TVBF_FOLD_MAX_K overrides).
-        self.fold_max_k = int(os.environ.get("TVBF_FOLD_MAX_K", "2048"))
+        # has at most fold_max_k columns (0 disables; TVBF_FOLD_MAX_K overrides).  Measured at
+        # N = 80 000 (tools/time_fold_crossover.py), K1 ms popcount / folded: V = 500 8.9 / 6.3,
+        # 1 000 7.9 / 6.0, 1 900 9.4 / 7.9, 3 000 12.2 / 11.5, 4 500 17.2 / 16.9 -- the gain fades as the
+        # MMAs take over; the folded bound is slightly looser (3-5 % more rows go to the exact kernel).
+        self.fold_max_k = int(os.environ.get("TVBF_FOLD_MAX_K", "4096"))
         self._fold_buf: torch.Tensor | None = None
         self._fold_owner: dict | None = None      # the catalogue fold whose content the buffer holds
         self._theta: torch.Tensor | None = None    # seeded thresholds of the tile-sharded job (valid until the next job)
@@ -546,13 +549,16 @@ class HybridTopKEngine:
               "tvbf_prep_csr_to_operand")
         return values, operand
 
-    def _folded(self, cat: DeviceCatalogue, gw: float, tw: float, mw: float, k: int) -> Features | None:
+    def _folded(self, cat: DeviceCatalogue, gw: float, tw: float, mw: float, k: int, tuning: int = 0,
+                candidates: int = 0) -> Features | None:
         """``tvbf_features`` of ``cat`` over a second operand that carries the packed genre / metadata
-        groups as K columns for these weights, or None when the job does not qualify."""
+        groups as K columns for these weights, or None when the job does not qualify (the folded
+        kernels exist for CTA pairs and up to 64 candidates per list)."""
         c = cat.c
         g_dim = int(c.genre_dim)
         k_fold = (int(c.vocab) + g_dim + 32 + 63) // 64 * 64
         ok = (self.fold_max_k > 0 and k_fold <= self.fold_max_k and k <= 48 and not cat.folded
+              and (tuning & 0xF) != 1 and candidates <= 64
               and c.genre_mode == _lib.GROUP_PACKED and c.meta_mode == _lib.GROUP_PACKED and not c.text_signed
               and self.text_dtype == "fp16" and tw > 0.0 and gw >= 0.0 and mw >= 0.0
               and all(w == 0.0 or 1e-8 <= w / tw <= 1e4 for w in (gw, mw)))   # columns stay normal fp16 numbers
@@ -580,7 +586,7 @@ class HybridTopKEngine:
             self._fold_owner = fc
         elif self._fold_owner is not fc:
             cat.fold = None                     # the engine's buffer went to another catalogue since
-            return self._folded(cat, gw, tw, mw, k)
+            return self._folded(cat, gw, tw, mw, k, tuning, candidates)
         if fc["weights"] != (gw, tw, mw):
             f = fc["c"]
             check(lib.tvbf_prep_fold_bits(c.col_side, c.genre_hi, c.meta_scale, cat.n_shows, g_dim, f.operand, k_fold,
@@ -628,7 +634,7 @@ class HybridTopKEngine:
                    splits=int(splits), candidates=int(candidates), force_exact=int(bool(force_exact)),
                    skip_fallback=int(bool(skip_fallback)), text_rel_err=0.0, phases=int(phases), tuning=int(tuning))
         with torch.cuda.device(self.device):
-            feats = None if force_exact else self._folded(cat, gw, tw, mw, int(k))
+            feats = None if force_exact else self._folded(cat, gw, tw, mw, int(k), int(tuning), int(candidates))
             if feats is None:
                 feats = cat.c
             nbytes = self.lib.tvbf_topk_workspace_bytes(C.byref(feats), C.byref(p))
@@ -760,7 +766,7 @@ class HybridTopKEngine:
         over the ranks."""
         p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
         with torch.cuda.device(self.device):
-            feats = self._k1_features(cat, weights, k)
+            feats = self._k1_features(cat, weights, k, tuning)
             nbytes = self.lib.tvbf_sym_workspace_bytes(C.byref(feats), C.byref(p), world)
             if nbytes == 0:
                 check(-1, "tvbf_sym_workspace_bytes")
@@ -774,10 +780,10 @@ class HybridTopKEngine:
                                          ws.numel(), self._stream()), "tvbf_sym_seed")
         return theta
 
-    def _k1_features(self, cat: DeviceCatalogue, weights, k) -> Features:
+    def _k1_features(self, cat: DeviceCatalogue, weights, k, tuning: int = 0) -> Features:
         """The features the candidate pass runs on: the folded operand when the job qualifies."""
         gw, tw, mw = (float(w) for w in weights)
-        return self._folded(cat, gw, tw, mw, int(k)) or cat.c
+        return self._folded(cat, gw, tw, mw, int(k), int(tuning)) or cat.c
 
     def sym_sweep(self, cat: DeviceCatalogue, weights, k, min_similarity, rank: int, world: int,
                   theta: torch.Tensor, splits: int = 0, tuning: int = 0, packed_rows: int = 0,
@@ -789,7 +795,7 @@ class HybridTopKEngine:
         p = self._params(cat, weights, k, min_similarity, splits=splits, tuning=tuning)
         dev, n = self.device, cat.n_shows
         with torch.cuda.device(dev):
-            feats = self._k1_features(cat, weights, k)
+            feats = self._k1_features(cat, weights, k, tuning)
             ws = self._workspace(self.lib.tvbf_sym_workspace_bytes(C.byref(feats), C.byref(p), world))
             L = int(self.lib.tvbf_sym_list_len(C.byref(feats), C.byref(p)))
             if peer_ptrs is not None:     # compaction fused with the exchange: rows go to their owners' buffers
@@ -1097,7 +1103,7 @@ class HybridTopKEngine:
         out = (C.c_int64 * 4)()
         feats = cat.c
         if cat.fold is not None and cat.fold["weights"] == tuple(float(w) for w in weights) \
-                and self._fold_owner is cat.fold:
+                and self._fold_owner is cat.fold and (int(tuning) & 0xF) != 1 and int(k) <= 48:
             feats = cat.fold["c"]
         with torch.cuda.device(self.device):
             check(self.lib.tvbf_plan_tiles(C.byref(feats), C.byref(p), int(rank), int(world), int(bool(tile_sharded)),
