@@ -66,6 +66,18 @@ def make_c1() -> None:
     _populate_case("populate_c1", make_config("C1"), [{}])
 
 
+def make_v500() -> None:
+    """The reference's production shape in miniature: ``max_text_features`` = 500
+    (scripts/compute_features.py:174), metadata widths 21 / 5 / 6, 1 500 shows through the UNMODIFIED
+    production loop, all rows, reference defaults and the raw-weight case.  On the GPU this is the
+    regime of the folded operand (genre / metadata as K columns of the text GEMM)."""
+    cat = make_catalogue(1500, 500, nnz=20, n_genres=40, meta=(21, 5, 6), seed=2026)
+    _populate_case("populate_v500_n1500", cat, [
+        {},
+        {"genre_weight": 21.0, "text_weight": 5.0, "metadata_weight": 6.0, "top_n_per_show": 10, "min_similarity": 2.0},
+    ])
+
+
 def main() -> None:
     logging.disable(logging.CRITICAL)
     GOLDEN.mkdir(parents=True, exist_ok=True)
@@ -74,7 +86,11 @@ def main() -> None:
     if "--only-c1" in sys.argv:
         make_c1()
         return
+    if "--only-v500" in sys.argv:
+        make_v500()
+        return
     make_c1()
+    make_v500()
 
     # (1) production loop (variant B) on a synthetic catalogue
     cat = make_catalogue(300, 2000, nnz=30, n_genres=40, meta=(5, 3, 2), seed=7)

@@ -45,6 +45,37 @@ def test_golden_c1_all_rows(engine, tuning):
         assert err.max() <= 1e-14, (name, err.max())
 
 
+@pytest.mark.parametrize("fold", [True, False], ids=["folded", "popcount"])
+@pytest.mark.parametrize("tuning", [SYM_OFF, SYM_ON], ids=["one_sided", "symmetric"])
+def test_golden_production_shape_v500_all_rows(engine, tuning, fold):
+    """The reference's production shape in miniature (500-term vocabulary, metadata widths 21 / 5 / 6):
+    the table of the UNMODIFIED reference hot loop for 1 500 shows, all rows, reference defaults and a
+    raw-weight case -- with the packed groups folded into the tensor-core operand (the default at this
+    vocabulary) and with the popcount epilogue."""
+    z, cat = load_golden("populate_v500_n1500")
+    old = engine.fold_max_k
+    engine.fold_max_k = old if fold else 0
+    try:
+        for c in range(int(z["n_cases"])):
+            gw, tw, mw, k, ms = z[f"case{c}_params"].tolist()
+            k = int(k)
+            engine._fold_owner = None
+            top = engine.compute_top_k(cat.features(), (gw, tw, mw), k, ms, tuning=tuning)
+            assert (engine._fold_owner is not None) == fold
+            pr = ProductionRows(cat.features(), gw, tw, mw)
+            rep = compare_topk(z[f"case{c}_idx"].astype(np.int64), z[f"case{c}_cnt"], z[f"case{c}_scores"][0],
+                               top.indices, top.counts, top.hybrid, lambda r, js: pr.pair_scores(r, js), k, ms)
+            assert rep.ok and rep.rows == 1500, rep.summary() + "\n" + "\n".join(rep.failures)
+            assert int(top.counts.sum()) == int(z[f"case{c}_total_records"])
+            same = (z[f"case{c}_idx"] == top.indices) & (top.indices >= 0)
+            for f_, name in enumerate(("hybrid", "genre", "text", "metadata")):
+                ref = z[f"case{c}_scores"][f_][same]
+                err = np.abs(getattr(top, name)[same] - ref)
+                assert np.all(err <= 1e-14 * np.maximum(1.0, np.abs(ref))), (name, err.max())
+    finally:
+        engine.fold_max_k = old
+
+
 def test_c1_through_the_populate_driver(engine, tmp_path):
     """Same fixture through the drop-in of ``compute_and_store_similarities`` (file contract, sink)."""
     from oracle.reference_paths import dict_to_arrays

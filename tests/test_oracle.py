@@ -88,7 +88,7 @@ def _cases(z):
                       top_n_per_show=int(k), min_similarity=ms)
 
 
-@pytest.mark.parametrize("name", ["populate_n300", "populate_random_float_n48"])
+@pytest.mark.parametrize("name", ["populate_n300", "populate_random_float_n48", "populate_v500_n1500"])
 def test_production_loop_matches_real_reference(name):
     z, cat = load_golden(name)
     for c, kw in _cases(z):
