@@ -129,8 +129,18 @@ def _gloo_worker(rank, world, port, n, k, q):
         # features: every rank contributes 1/world of the bytes, all ranks end with every byte
         host = [torch.arange(1001, dtype=torch.int64), torch.arange(77, dtype=torch.float64) / 7,
                 (torch.arange(300) % 3 == 0).to(torch.uint8).reshape(100, 3), torch.zeros(0, dtype=torch.int32)]
-        dev = ShardedUpload()(host, torch.device("cpu"))
+        up = ShardedUpload()
+        dev = up(host, torch.device("cpu"))
         ok = ok and all(torch.equal(a, b_) and a.dtype == b_.dtype and a.shape == b_.shape for a, b_ in zip(dev, host))
+        # the device buffers are reused from call to call, two sets in turn: the previous call's arrays
+        # (which prepare(recycle=...) still reads) stay intact, the one before is overwritten
+        host2 = [h + 1 if h.dtype != torch.uint8 else 1 - h for h in host]
+        dev2 = up(host2, torch.device("cpu"))
+        ok = ok and all(torch.equal(a, b_) for a, b_ in zip(dev2, host2))
+        ok = ok and all(torch.equal(a, b_) for a, b_ in zip(dev, host))                 # first call untouched
+        ok = ok and all(a.data_ptr() != b_.data_ptr() for a, b_ in zip(dev[:3], dev2[:3]))
+        dev3 = up(host, torch.device("cpu"))
+        ok = ok and all(a.data_ptr() == b_.data_ptr() for a, b_ in zip(dev[:3], dev3[:3]))   # set 0 again, no allocation
         # result: one host table in shared memory, each rank stores its shard
         table = SharedHostTable(n, k)
         table.store_shard({name: local[name] for name in ("indices", "counts", "hybrid", "genre", "text", "metadata",
