@@ -282,3 +282,44 @@ def test_new_entry_points_validate_their_arguments_without_a_gpu():
     assert lib.tvbf_prep_fold_bits(1, None, 1, 10, 40, 1, 512, 500, 1.0, 1.0, 0, None) != 0    # columns do not fit k_pad
     assert lib.tvbf_prep_fold_bits(1, None, 1, 10, 100, 1, 704, 500, 1.0, 1.0, 0, None) != 0   # G > 64 without genre_hi
     assert b"tvbf_prep_fold_bits" in lib.tvbf_last_error()
+
+
+def test_histogram_seed_threshold_is_a_lower_bound_model():
+    """The arithmetic of the threshold seed pass (hybrid_topk.cu, kMode 3; constants from
+    make_seed_params) restated in float32 numpy: 63 bins over [lo, hi), bin = floor(u * inv_w + off),
+    threshold = lower edge of the bin where the count from the top reaches kp, minus a margin.  For any
+    sample of scores at least kp of them are >= the threshold -- including scores on bin edges, below the
+    range, above it, and ties."""
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    for trial in range(200):
+        lo = f32(rng.choice([0.0, 0.1, 0.3, 2.0]))
+        hi = f32(lo + rng.choice([0.5, 0.92, 3.0, 32.0]))
+        kp = int(rng.choice([8, 32, 128]))
+        n = int(rng.choice([5, 40, 300, 2000]))
+        span = f32(hi - lo)
+        w, inv_w = f32(span / f32(63.0)), f32(f32(63.0) / span)
+        off = f32(f32(1.0) - lo * inv_w)
+        kind = trial % 4
+        if kind == 0:
+            u = rng.uniform(lo - 0.2, hi + 0.2, n)
+        elif kind == 1:      # exactly on bin edges
+            u = lo + w * rng.integers(-2, 66, n)
+        elif kind == 2:      # heavy ties
+            u = rng.choice(rng.uniform(lo, hi, 5), n)
+        else:                # clustered near the top
+            u = hi - np.abs(rng.normal(0, 0.01, n))
+        u = u.astype(f32)
+        t = (u * inv_w + off).astype(f32)                      # the kernel uses one FMA; the margin covers the difference
+        bins = np.clip(np.floor(t).astype(np.int64), 0, 63)
+        hist = np.bincount(bins, minlength=64)
+        c, found = 0, 0
+        for b in range(63, 0, -1):
+            c += hist[b]
+            if c >= kp and found == 0:
+                found = b
+        if found == 0:
+            assert (bins >= 1).sum() < kp
+            continue
+        theta = f32(f32(f32(found - 1) - f32(1e-3)) * w + lo)
+        assert int((u >= theta).sum()) >= kp, (trial, lo, hi, kp, n, found, theta)
