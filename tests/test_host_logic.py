@@ -323,3 +323,55 @@ def test_histogram_seed_threshold_is_a_lower_bound_model():
             continue
         theta = f32(f32(f32(found - 1) - f32(1e-3)) * w + lo)
         assert int((u >= theta).sum()) >= kp, (trial, lo, hi, kp, n, found, theta)
+
+
+@pytest.mark.parametrize("weights,mode", [((0.4, 0.5, 0.1), "mean3"), ((21.0, 5.0, 6.0), "mean3"),
+                                          ((0.3, 0.6, 0.1), "hstack"), ((0.5, 0.5, 0.0), "mean3")])
+def test_folded_bound_model_with_the_librarys_constants(weights, mode):
+    """CPU model of the folded candidate pass (tvbf_features.bits_folded): the operand as
+    tvbf_prep_csr_to_operand / tvbf_prep_fold_bits build it (one rounding to fp16 from float64), exact
+    products, an accumulator that loses 3 * 2^-23 per non-zero term (more than the tensor core does),
+    inflated by the slack constants the LIBRARY computes (tvbf_debug_slack is host-only) -- the result
+    bounds the exact hybrid of every pair.  The GPU twin is test_upper_bound_holds_with_folded_bits."""
+    import ctypes as C
+
+    from oracle.cosine import normalize_rows
+    from oracle.reference_paths import ProductionRows
+    from tvbingefriend_recommendation_service_b200 import _lib
+    from tvbingefriend_recommendation_service_b200.engine import TEXT_SCALE_LOG2
+
+    gw, tw, mw = weights
+    cat = make_catalogue(400, 300, nnz=12, n_genres=40, meta=(21, 5, 6), seed=9)
+    f = cat.features()
+    lib = _lib.load()
+    feats = _lib.Features()
+    feats.text_scale_log2, feats.text_dtype = TEXT_SCALE_LOG2, 0
+    feats.genre_mode = feats.meta_mode = _lib.GROUP_PACKED
+    feats.meta_kind = _lib.META_MEAN3 if mode == "mean3" else _lib.META_HSTACK
+    feats.genre_dim, feats.bits_folded = 40, 1
+    feats.fold_weights[0], feats.fold_weights[1], feats.fold_weights[2] = gw, tw, mw
+    p = _lib.Params(genre_weight=gw, text_weight=tw, metadata_weight=mw, min_similarity=0.1, k=20, exclude_self=1,
+                    row_begin=0, row_end=400)
+    out = (C.c_float * 5)()
+    assert lib.tvbf_debug_slack(C.byref(feats), C.byref(p), out) == 0
+    w_text, w_text_err, w_text_acc, eps, eps_term = (float(x) for x in out)
+    assert w_text_err > 0 and w_text_acc > 0          # the relative bound: all products are non-negative
+
+    scale = 2.0 ** TEXT_SCALE_LOG2
+    text = normalize_rows(sp.csr_matrix(f["text_features"])).toarray()
+    g = np.asarray(f["genre_features"], dtype=np.float64)
+    rn = np.where(g.sum(1) > 0, 1.0 / np.sqrt(np.maximum(g.sum(1), 1)), 0.0).astype(np.float32).astype(np.float64)
+    onehots = np.hstack([np.asarray(f[k_], dtype=np.float64) for k_ in ("platform_features", "type_features",
+                                                                         "language_features")])
+    valid = onehots.sum(1)
+    ms = (np.full(400, 1 / np.sqrt(3.0)) if mode == "mean3"
+          else np.where(valid > 0, 1.0 / np.sqrt(np.maximum(valid, 1)), 0.0)).astype(np.float32).astype(np.float64)
+    op = np.hstack([(text * scale).astype(np.float16).astype(np.float64),
+                    (g * (rn * scale * np.sqrt(gw / tw))[:, None]).astype(np.float16).astype(np.float64),
+                    (onehots * (ms * scale * np.sqrt(mw / tw))[:, None]).astype(np.float16).astype(np.float64)])
+    terms = (np.diff(sp.csr_matrix(f["text_features"]).indptr) + 40 + 3).astype(np.float64)[:, None]
+    acc = (op @ op.T) * (1.0 - terms * 3.0 * 2.0 ** -23)
+    u = (w_text + w_text_err + terms * w_text_acc) * acc + eps + terms * eps_term
+    exact = ProductionRows(f, gw, tw, mw, metadata_mode=mode).rows_block(np.arange(400))[0]
+    assert np.all(u >= exact), float((exact - u).max())
+    assert float((u - exact).max()) <= 3e-3 * (gw + tw + mw)      # ... and tightly
